@@ -1,0 +1,273 @@
+/*
+ * pasture_b200.h -- C ABI of the B200-native implementation of pasture's per-point hot path.
+ *
+ * Every entry point names the reference interface it stands in for (paths relative to the
+ * igd-geo/pasture checkout, v0.5.0 @ 1b0b39c).  The reference has no FFI for this path (it is a
+ * Rust trait surface); INTEGRATION.md shows the Rust-side binding a maintainer would add.
+ *
+ * Conventions
+ *   - plain C types only; all handles are opaque; caller owns all point memory.
+ *   - return value: 0 = ok, negative = error.  Contract violations that `panic!` in the reference
+ *     come back as the PB200_ERR_* code documented on the function; pb200_last_error() gives the
+ *     thread-local message.
+ *   - handles are not thread-safe (the reference's BufferLayoutConverter is !Send as well,
+ *     buffer_conversion.rs:14).  One CUDA stream per context.
+ *   - buffers are described, not owned: a pb200_buffer_desc is the (base, offset, stride, size)
+ *     addressing of containers/raw_attribute_view.rs:10-71 for a whole buffer.
+ *   - memspace DEVICE: pointers are device pointers valid on the context's device; calls are
+ *     asynchronous on the context's stream unless they return a value to the host.
+ *     memspace HOST: the library stages chunks through device memory (H2D, kernel, D2H overlapped).
+ *   - there is NO CPU fallback: without a CUDA device every compute entry point fails with
+ *     PB200_ERR_NO_DEVICE.
+ */
+#ifndef PASTURE_B200_H
+#define PASTURE_B200_H
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define PB200_ABI_VERSION 1
+#define PB200_MAX_ATTRIBUTES 48
+#define PB200_MAX_NAME 64
+
+/* PointAttributeDataType, declaration order of pasture-core/src/layout/point_layout.rs:23-68 */
+enum pb200_dtype {
+    PB200_U8 = 0, PB200_I8 = 1, PB200_U16 = 2, PB200_I16 = 3, PB200_U32 = 4, PB200_I32 = 5,
+    PB200_U64 = 6, PB200_I64 = 7, PB200_F32 = 8, PB200_F64 = 9,
+    PB200_VEC3U8 = 10, PB200_VEC3U16 = 11, PB200_VEC3F32 = 12, PB200_VEC3I32 = 13, PB200_VEC3F64 = 14,
+    PB200_VEC4U8 = 15, PB200_BYTEARRAY = 16, PB200_CUSTOM = 17
+};
+
+enum pb200_status {
+    PB200_OK = 0,
+    PB200_ERR_ATTR_NOT_FOUND = -1,  /* "Attribute not found" panics: buffer_conversion.rs:114,164,168 */
+    PB200_ERR_NO_CONVERSION = -2,   /* "No conversion from .. to .." buffer_conversion.rs:383-388 */
+    PB200_ERR_TRANSFORM_DTYPE = -3, /* assert_eq!(T::data_type(), ..) buffer_conversion.rs:209-213 */
+    PB200_ERR_LAYOUT_MISMATCH = -4, /* buffer_conversion.rs:302-303 */
+    PB200_ERR_RANGE = -5,           /* buffer_conversion.rs:304-306 ; reprojection.rs:212-214 */
+    PB200_ERR_DUPLICATE_ATTR = -6,  /* point_layout.rs:783-788 */
+    PB200_ERR_OVERLAP = -7,         /* point_layout.rs:737-743 */
+    PB200_ERR_INVALID = -8,         /* bad argument / would panic (e.g. AABB min > max, math/bounds.rs:21-26) */
+    PB200_ERR_TOO_FEW_POINTS = -9,  /* normal_estimation.rs:86-91,296-298 */
+    PB200_ERR_UNSUPPORTED = -10,    /* voxel_grid.rs:452-459,682-687 ; raw_readers.rs:56 ; closure transforms */
+    PB200_ERR_NO_DEVICE = -100,     /* no CUDA device / extension unusable: there is no CPU fallback */
+    PB200_ERR_CUDA = -101,          /* CUDA runtime error (message in pb200_last_error) */
+    PB200_ERR_OOM = -102
+};
+
+enum pb200_buffer_kind { PB200_INTERLEAVED = 0, PB200_COLUMNAR = 1 }; /* VectorBuffer / HashMapBuffer */
+enum pb200_memspace { PB200_HOST = 0, PB200_DEVICE = 1 };
+
+typedef struct pb200_ctx pb200_ctx;
+typedef struct pb200_layout pb200_layout;
+typedef struct pb200_converter pb200_converter;
+typedef struct pb200_result_buffer pb200_result_buffer;
+
+/* PointAttributeMember (point_layout.rs:353-357) */
+typedef struct pb200_attr {
+    char name[PB200_MAX_NAME];
+    uint32_t dtype;
+    uint32_t _pad;
+    uint64_t extra_size;  /* ByteArray(n) length / Custom size */
+    uint64_t extra_align; /* Custom min_alignment */
+    uint64_t offset;
+    uint64_t size;
+} pb200_attr;
+
+/* A borrowed point buffer: BorrowedBuffer + InterleavedBuffer|ColumnarBuffer (point_buffer.rs:17-654).
+ * INTERLEAVED: `aos` holds len * size_of_point_entry bytes (VectorBuffer / ExternalMemoryBuffer).
+ * COLUMNAR  : `columns[i]` holds len * size(attribute i) bytes, layout order (HashMapBuffer). */
+typedef struct pb200_buffer_desc {
+    const pb200_layout* layout;
+    int32_t kind;     /* pb200_buffer_kind */
+    int32_t memspace; /* pb200_memspace */
+    uint64_t len;
+    void* aos;
+    void** columns;
+} pb200_buffer_desc;
+
+/* The closures that exist in-tree, enumerated (closures cannot cross an FFI):
+ *   SCALE_OFFSET      Vec3f64/f64: (v*s)+o          Vec3f32/f32: ((v as f64*s)+o) as f32   pasture-io/src/las/raw_readers.rs:42-55
+ *   INV_SCALE_OFFSET  Vec3f64/f64: (v-o)/s                                                 pasture-io/src/las/write_helpers.rs:15-17
+ *   ADD               Vec3f64/f64: v+o              Vec3f32/f32: (v as f64+o) as f32       pasture-io/src/tiles3d/pnts_reader.rs:265-277
+ *   SHIFT_MASK        u8/u16/u32/u64: (v >> shift) & mask                                  pasture-io/src/las/raw_readers.rs:61-164
+ * No FMA contraction anywhere: results are bit-identical to the Rust closures. */
+enum pb200_transform_kind {
+    PB200_T_NONE = 0, PB200_T_SCALE_OFFSET = 1, PB200_T_INV_SCALE_OFFSET = 2, PB200_T_ADD = 3, PB200_T_SHIFT_MASK = 4
+};
+typedef struct pb200_transform {
+    uint32_t kind;
+    uint32_t shift;
+    uint64_t mask;
+    double s[3];
+    double o[3];
+} pb200_transform;
+
+/* ---- library / context ------------------------------------------------------------------------ */
+int pb200_abi_version(void);
+const char* pb200_last_error(void);
+/* number of kernels this library has launched in this process (bench.py `gpu_launches`) */
+uint64_t pb200_kernel_launch_count(void);
+
+int pb200_ctx_create(int device, pb200_ctx** out);
+/* borrow an external CUDA stream (cudaStream_t as void*, e.g. torch.cuda.current_stream().cuda_stream) */
+int pb200_ctx_set_stream(pb200_ctx* ctx, void* cuda_stream);
+void* pb200_ctx_get_stream(pb200_ctx* ctx);
+int pb200_ctx_synchronize(pb200_ctx* ctx);
+/* tuning knobs of the tile pipeline: "convert.tile_points", "convert.threads", "convert.stages",
+ * "convert.ctas_per_sm", "convert.force_direct" */
+int pb200_ctx_set_param(pb200_ctx* ctx, const char* key, int64_t value);
+void pb200_ctx_destroy(pb200_ctx* ctx);
+
+/* pinned host / device memory helpers (ExternalMemoryBuffer-style foreign memory, point_buffer.rs:1479-1503) */
+int pb200_host_alloc(uint64_t bytes, void** out);
+int pb200_host_free(void* p);
+int pb200_device_alloc(pb200_ctx* ctx, uint64_t bytes, void** out);
+int pb200_device_free(pb200_ctx* ctx, void* p);
+int pb200_memcpy_h2d(pb200_ctx* ctx, void* dst_device, const void* src_host, uint64_t bytes);
+int pb200_memcpy_d2h(pb200_ctx* ctx, void* dst_host, const void* src_device, uint64_t bytes);
+int pb200_memset_device(pb200_ctx* ctx, void* dst_device, int value, uint64_t bytes);
+
+/* ---- PointLayout (pasture-core/src/layout/point_layout.rs:648-997) ------------------------------ */
+uint64_t pb200_dtype_size(uint32_t dtype, uint64_t extra_size);            /* :72-97   */
+uint64_t pb200_dtype_min_alignment(uint32_t dtype, uint64_t extra_align);  /* :100-126 */
+int pb200_layout_create(pb200_layout** out);                               /* PointLayout::default() :1011-1024 */
+/* add_attribute :778-822. packed_n == 0 -> FieldAlignment::Default, else FieldAlignment::Packed(packed_n).
+ * PB200_ERR_DUPLICATE_ATTR if the name is present. */
+int pb200_layout_add_attribute(pb200_layout* l, const char* name, uint32_t dtype, uint64_t extra_size,
+                               uint64_t extra_align, uint64_t packed_n);
+/* from_members_and_alignment :719-759 (uses name, dtype, extra_*, offset of each attr) */
+int pb200_layout_from_members_and_alignment(const pb200_attr* members, uint32_t n, uint64_t type_alignment,
+                                            pb200_layout** out);
+int pb200_layout_clone(const pb200_layout* l, pb200_layout** out);
+uint32_t pb200_layout_num_attributes(const pb200_layout* l);
+int pb200_layout_get_attribute(const pb200_layout* l, uint32_t index, pb200_attr* out);      /* at() :898 */
+uint64_t pb200_layout_size_of_point_entry(const pb200_layout* l);                            /* :930 */
+uint64_t pb200_layout_alignment(const pb200_layout* l);
+int pb200_layout_index_by_name(const pb200_layout* l, const char* name);                     /* :887, -1 if absent */
+int pb200_layout_index_of(const pb200_layout* l, const char* name, uint32_t dtype);          /* :951 */
+int pb200_layout_equal(const pb200_layout* a, const pb200_layout* b);                        /* derived PartialEq */
+int pb200_layout_compare_without_offsets(const pb200_layout* a, const pb200_layout* b);      /* :960-971 */
+void pb200_layout_destroy(pb200_layout* l);
+/* LAS layouts: pasture-io/src/las/las_layout.rs:64-125 (exact binary) and las_types.rs LasPointFormatN */
+int pb200_las_raw_layout(int point_format, pb200_layout** out);
+int pb200_las_default_layout(int point_format, pb200_layout** out);
+
+/* ---- BufferLayoutConverter (pasture-core/src/layout/conversion/buffer_conversion.rs:98-663) ---- */
+/* for_layouts :112 (with_default=0, PB200_ERR_ATTR_NOT_FOUND if a target attribute is missing in
+ * `from`) / for_layouts_with_default :126 (with_default=1). PB200_ERR_NO_CONVERSION if a same-named
+ * pair has no cast (attribute_conversion.rs:184-271). */
+int pb200_converter_create(pb200_ctx* ctx, const pb200_layout* from, const pb200_layout* to, int with_default,
+                           pb200_converter** out);
+/* set_custom_mapping :156-183 */
+int pb200_converter_set_custom_mapping(pb200_converter* cv, const char* from_name, uint32_t from_dtype,
+                                       const char* to_name, uint32_t to_dtype);
+/* set_custom_mapping_with_transformation :194-234. `transform_dtype` plays the role of T: it must equal the
+ * source dtype (apply_to_source != 0) or the target dtype, else PB200_ERR_TRANSFORM_DTYPE. */
+int pb200_converter_set_custom_mapping_with_transformation(pb200_converter* cv, const char* from_name,
+                                                           uint32_t from_dtype, const char* to_name,
+                                                           uint32_t to_dtype, uint32_t transform_dtype,
+                                                           const pb200_transform* t, int apply_to_source);
+/* get_default_las_converter, pasture-io/src/las/raw_readers.rs:31-167 */
+int pb200_las_default_converter(pb200_ctx* ctx, const pb200_layout* raw_las_layout, const pb200_layout* target,
+                                const double scale[3], const double offset[3], pb200_converter** out);
+uint32_t pb200_converter_num_mappings(const pb200_converter* cv);
+/* convert_into_range :292-359. out_of_range_count (nullable): number of values for which a mapping with an
+ * INV_SCALE_OFFSET transform followed by a float->int cast left the target integer range, i.e. the points
+ * for which write_position_as_las_position (write_helpers.rs:15-17) would panic. Reading it synchronises. */
+int pb200_converter_convert_into_range(pb200_converter* cv, const pb200_buffer_desc* src, uint64_t src_begin,
+                                       uint64_t src_end, const pb200_buffer_desc* dst, uint64_t dst_begin,
+                                       uint64_t dst_end, uint64_t* out_of_range_count);
+/* convert_into :268-283 */
+int pb200_converter_convert_into(pb200_converter* cv, const pb200_buffer_desc* src, const pb200_buffer_desc* dst,
+                                 uint64_t* out_of_range_count);
+/* convert_into_range fused with calculate_bounds (pasture-algorithms/src/bounds.rs:30-54) over the produced
+ * target POSITION_3D (Vec3f64) values: saves the separate 24 B/point pass. is_some=0 for an
+ * empty range or a target without a mapped Vec3f64 "Position3D". Synchronises. */
+int pb200_converter_convert_into_range_with_bounds(pb200_converter* cv, const pb200_buffer_desc* src,
+                                                   uint64_t src_begin, uint64_t src_end,
+                                                   const pb200_buffer_desc* dst, uint64_t dst_begin,
+                                                   uint64_t dst_end, double out_min[3], double out_max[3],
+                                                   int* is_some);
+/* same, but leaves [minx,miny,minz,-maxx,-maxy,-maxz] in a device array (6 doubles) without synchronising,
+ * ready for one ncclAllReduce(min) across point-range shards. Empty range: +MAX / +MAX. */
+int pb200_converter_convert_into_range_with_bounds_device(pb200_converter* cv, const pb200_buffer_desc* src,
+                                                          uint64_t src_begin, uint64_t src_end,
+                                                          const pb200_buffer_desc* dst, uint64_t dst_begin,
+                                                          uint64_t dst_end, double* device_minmax6);
+void pb200_converter_destroy(pb200_converter* cv);
+
+/* BorrowedMutBuffer::transform_attribute (point_buffer.rs:391-404) with an enumerated transform, in place */
+int pb200_transform_attribute(pb200_ctx* ctx, const pb200_buffer_desc* buf, const char* name, uint32_t dtype,
+                              const pb200_transform* t);
+/* AttributeViewConverting (buffer_views.rs:533-650): materialise attribute `name` as `view_dtype`
+ * into out (len * size(view_dtype) bytes, same memspace as buf) */
+int pb200_view_attribute_with_conversion(pb200_ctx* ctx, const pb200_buffer_desc* buf, const char* name,
+                                         uint32_t view_dtype, void* out);
+
+/* ---- reductions ----------------------------------------------------------------------------------- */
+/* calculate_bounds, pasture-algorithms/src/bounds.rs:11-85. is_some=0 <=> None. All-NaN input ->
+ * PB200_ERR_INVALID (AABB::from_min_max panics). */
+int pb200_calculate_bounds(pb200_ctx* ctx, const pb200_buffer_desc* buf, double out_min[3], double out_max[3],
+                           int* is_some);
+/* minmax_attribute<T>, pasture-algorithms/src/minmax.rs:13-51; out_min/out_max hold one value of `dtype`.
+ * (name, dtype) must be in the layout (the reference's converting branch always panics, buffer_views.rs:549). */
+int pb200_minmax_attribute(pb200_ctx* ctx, const pb200_buffer_desc* buf, const char* name, uint32_t dtype,
+                           void* out_min, void* out_max, int* is_some);
+/* expand_bits_by_3, pasture-core/src/math/bitmanip.rs:2-10 (host) and 63-bit Morton codes of positions
+ * quantised to 21 bits/axis inside [bmin,bmax] (device; codes_out: len u64 in buf's memspace) */
+uint64_t pb200_expand_bits_by_3(uint64_t v);
+int pb200_morton_codes(pb200_ctx* ctx, const pb200_buffer_desc* buf, const double bmin[3], const double bmax[3],
+                       uint64_t* codes_out);
+
+/* ---- voxel grid, pasture-algorithms/src/voxel_grid.rs:109-165 ------------------------------------- */
+/* Result: a library-owned buffer with `dst_layout`, one point per occupied voxel in (ix,iy,iz)
+ * lexicographic order. Mode ties (nondeterministic in the reference, :320-328) resolve to the smallest
+ * value. PB200_ERR_UNSUPPORTED for waveform / non-builtin target attributes (:452-459,:682-687). */
+int pb200_voxelgrid_filter(pb200_ctx* ctx, const pb200_buffer_desc* src, double leaf_x, double leaf_y,
+                           double leaf_z, const pb200_layout* dst_layout, int32_t dst_kind, int32_t dst_memspace,
+                           pb200_result_buffer** out);
+int pb200_result_buffer_desc(const pb200_result_buffer* r, pb200_buffer_desc* out);
+/* per-voxel (ix,iy,iz) keys as 3 x u64, host memory, output order */
+int pb200_result_buffer_voxel_keys(const pb200_result_buffer* r, uint64_t* keys_out);
+void pb200_result_buffer_destroy(pb200_result_buffer* r);
+
+/* ---- kNN / radius / normals ------------------------------------------------------------------------ */
+/* KdTree::nearests(q, k) for every point of the buffer against the buffer itself
+ * (normal_estimation.rs:103,108): k nearest by squared distance including the point itself, ascending.
+ * idx_out: len*k u32, d2_out: len*k f64 (nullable), in buf's memspace; if len < k the tail is 0xFFFFFFFF/inf. */
+int pb200_knn(pb200_ctx* ctx, const pb200_buffer_desc* buf, uint32_t k, uint32_t* idx_out, double* d2_out);
+/* all neighbours with d2 <= r*r, at most max_neighbors per point (nearest first); counts_out: len u32 */
+int pb200_radius_search(pb200_ctx* ctx, const pb200_buffer_desc* buf, double radius, uint32_t max_neighbors,
+                        uint32_t* idx_out, uint32_t* counts_out);
+/* compute_normals, normal_estimation.rs:79-130: normals_out len*3 f64 (un-normalised, un-oriented, as the
+ * reference), curvature_out len f64. PB200_ERR_TOO_FEW_POINTS if len < 3, PB200_ERR_INVALID if k < 3. */
+int pb200_compute_normals(pb200_ctx* ctx, const pb200_buffer_desc* buf, uint32_t k, double* normals_out,
+                          double* curvature_out);
+
+/* ---- reprojection, pasture-algorithms/src/reprojection.rs:132-146,201-227 -------------------------- */
+/* PROJ is a closed-source-to-us dependency here; the GPU path takes an enumerated operation pipeline. */
+enum pb200_proj_kind {
+    PB200_PROJ_AFFINE = 1, PB200_PROJ_GEODETIC_TO_ECEF = 2, PB200_PROJ_ECEF_TO_GEODETIC = 3,
+    PB200_PROJ_ALBERS_FWD = 4, PB200_PROJ_SET_Z = 5, PB200_PROJ_WEBMERC_FWD = 6, PB200_PROJ_TMERC_FWD = 7
+};
+typedef struct pb200_proj_op {
+    uint32_t kind;
+    uint32_t _pad;
+    double p[12];
+} pb200_proj_op;
+/* fills ops (capacity >= 8) for a known CRS pair ("EPSG:4326" -> "EPSG:3309", "EPSG:4326" -> "EPSG:3857");
+ * returns the op count or PB200_ERR_UNSUPPORTED */
+int pb200_proj_pipeline_for_crs(const char* source_crs, const char* target_crs, pb200_proj_op* ops, uint32_t cap);
+/* reproject_point_cloud_within (dst == NULL) / _between (PB200_ERR_RANGE if lengths differ) on POSITION_3D */
+int pb200_reproject(pb200_ctx* ctx, const pb200_buffer_desc* src, const pb200_buffer_desc* dst_or_null,
+                    const pb200_proj_op* ops, uint32_t n_ops);
+
+#ifdef __cplusplus
+}
+#endif
+#endif

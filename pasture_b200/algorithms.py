@@ -1,0 +1,183 @@
+"""Per-point algorithm sweeps -- host-side mirror of pasture-algorithms (bounds.rs, minmax.rs, voxel_grid.rs,
+normal_estimation.rs, reprojection.rs) and pasture-core/src/math (bounds.rs AABB, bitmanip.rs)."""
+import ctypes as C
+
+import numpy as np
+import torch
+
+from ._lib import BufferDesc, ProjOp, check, lib
+from .containers import _NP, _VEC3, HashMapBuffer, VectorBuffer
+from .context import get_context
+from .layout import DT
+
+
+class AABB:
+    """math/bounds.rs:9"""
+
+    def __init__(self, mn, mx):
+        self._min, self._max = tuple(mn), tuple(mx)
+
+    def min(self):
+        return self._min
+
+    def max(self):
+        return self._max
+
+    def extent(self):
+        return tuple(b - a for a, b in zip(self._min, self._max))
+
+    @staticmethod
+    def union(a, b):
+        return AABB([min(x, y) for x, y in zip(a._min, b._min)], [max(x, y) for x, y in zip(a._max, b._max)])
+
+    def __eq__(self, o):
+        return isinstance(o, AABB) and self._min == o._min and self._max == o._max
+
+    def __repr__(self):
+        return f"AABB(min={self._min}, max={self._max})"
+
+
+def calculate_bounds(buffer, ctx=None):
+    """bounds.rs:11-28 -> AABB or None"""
+    ctx = ctx or get_context()
+    d = buffer.desc()
+    mn, mx, some = (C.c_double * 3)(), (C.c_double * 3)(), C.c_int(0)
+    check(lib().pb200_calculate_bounds(ctx._h, C.byref(d), mn, mx, C.byref(some)))
+    return AABB(mn, mx) if some.value else None
+
+
+def minmax_attribute(buffer, attribute, ctx=None):
+    """minmax.rs:13-51 -> (min, max) of attribute.datatype() or None"""
+    ctx = ctx or get_context()
+    d = buffer.desc()
+    mn, mx, some = np.zeros(32, np.uint8), np.zeros(32, np.uint8), C.c_int(0)
+    check(lib().pb200_minmax_attribute(ctx._h, C.byref(d), attribute.name().encode(), int(attribute.datatype()),
+                                       C.c_void_p(mn.ctypes.data), C.c_void_p(mx.ctypes.data), C.byref(some)))
+    if not some.value:
+        return None
+    dt = attribute.datatype()
+    comp = _NP.get(dt) or _NP[_VEC3[dt]]
+    sz = attribute.size()
+    a, b = mn[:sz].view(comp).copy(), mx[:sz].view(comp).copy()
+    return (a[0], b[0]) if dt in _NP else (a, b)
+
+
+def expand_bits_by_3(v):
+    """math/bitmanip.rs:2-10"""
+    return int(lib().pb200_expand_bits_by_3(int(v) & 0xFFFFFFFFFFFFFFFF))
+
+
+def morton_codes(buffer, bmin, bmax, ctx=None):
+    ctx = ctx or get_context()
+    d = buffer.desc()
+    out = torch.zeros(max(1, buffer.len()), dtype=torch.int64, device=buffer.device)
+    check(lib().pb200_morton_codes(ctx._h, C.byref(d), (C.c_double * 3)(*bmin), (C.c_double * 3)(*bmax),
+                                   C.c_void_p(out.data_ptr())))
+    return out[: buffer.len()]
+
+
+def voxelgrid_filter(buffer, leafsize_x, leafsize_y, leafsize_z, filtered_layout=None, out_buffer_type=HashMapBuffer,
+                     device=None, ctx=None, return_keys=False):
+    """voxel_grid.rs:109-165. Returns the filtered buffer (library result copied into a buffer of out_buffer_type)."""
+    ctx = ctx or get_context()
+    layout = filtered_layout or buffer.point_layout()
+    dev = torch.device(device) if device is not None else buffer.device
+    kind = 0 if out_buffer_type is VectorBuffer else 1
+    memspace = 1 if dev.type == "cuda" else 0
+    d = buffer.desc()
+    h = C.c_void_p()
+    check(lib().pb200_voxelgrid_filter(ctx._h, C.byref(d), leafsize_x, leafsize_y, leafsize_z, layout._h, kind, memspace,
+                                       C.byref(h)))
+    try:
+        rd = BufferDesc()
+        check(lib().pb200_result_buffer_desc(h, C.byref(rd)))
+        n = int(rd.len)
+        out = out_buffer_type(layout, n, dev)
+        od = out.desc()
+        if n:
+            if kind == 0:
+                _copy(ctx, od.aos, rd.aos, n * layout.size_of_point_entry(), memspace)
+            else:
+                for i, a in enumerate(layout.attributes()):
+                    _copy(ctx, od.columns[i], rd.columns[i], n * a.size(), memspace)
+        keys = None
+        if return_keys:
+            keys = np.zeros((max(1, n), 3), dtype=np.uint64)
+            check(lib().pb200_result_buffer_voxel_keys(h, C.c_void_p(keys.ctypes.data)))
+            keys = keys[:n]
+    finally:
+        lib().pb200_result_buffer_destroy(h)
+    return (out, keys) if return_keys else out
+
+
+def _copy(ctx, dst, src, nbytes, memspace):
+    if nbytes == 0:
+        return
+    if memspace == 1:
+        import ctypes
+        cudart = torch.cuda.cudart()
+        err = cudart.cudaMemcpy(dst, src, nbytes, 3)  # cudaMemcpyDeviceToDevice
+        if int(err) != 0:
+            raise RuntimeError(f"cudaMemcpy failed: {err}")
+    else:
+        C.memmove(dst, src, nbytes)
+
+
+def knn(buffer, k, with_distances=True, ctx=None):
+    """KdTree::nearests for every point against the cloud (normal_estimation.rs:103,108) -> (idx [n,k] int64-view of u32, d2 [n,k])"""
+    ctx = ctx or get_context()
+    n = buffer.len()
+    dev = buffer.device
+    idx = torch.zeros((max(1, n), k), dtype=torch.int32, device=dev)
+    d2 = torch.zeros((max(1, n), k), dtype=torch.float64, device=dev) if with_distances else None
+    d = buffer.desc()
+    check(lib().pb200_knn(ctx._h, C.byref(d), k, C.c_void_p(idx.data_ptr()),
+                          C.c_void_p(d2.data_ptr()) if with_distances else None))
+    return (idx[:n], d2[:n]) if with_distances else idx[:n]
+
+
+def radius_search(buffer, radius, max_neighbors, ctx=None):
+    ctx = ctx or get_context()
+    n = buffer.len()
+    dev = buffer.device
+    idx = torch.zeros((max(1, n), max_neighbors), dtype=torch.int32, device=dev)
+    cnt = torch.zeros(max(1, n), dtype=torch.int32, device=dev)
+    d = buffer.desc()
+    check(lib().pb200_radius_search(ctx._h, C.byref(d), radius, max_neighbors, C.c_void_p(idx.data_ptr()),
+                                    C.c_void_p(cnt.data_ptr())))
+    return idx[:n], cnt[:n]
+
+
+def compute_normals(point_cloud, k_nn, ctx=None):
+    """normal_estimation.rs:79-130 -> (normals [n,3] f64, curvature [n] f64) tensors on the buffer's device"""
+    ctx = ctx or get_context()
+    n = point_cloud.len()
+    dev = point_cloud.device
+    normals = torch.zeros((max(1, n), 3), dtype=torch.float64, device=dev)
+    curv = torch.zeros(max(1, n), dtype=torch.float64, device=dev)
+    d = point_cloud.desc()
+    check(lib().pb200_compute_normals(ctx._h, C.byref(d), k_nn, C.c_void_p(normals.data_ptr()), C.c_void_p(curv.data_ptr())))
+    return normals[:n], curv[:n]
+
+
+class Projection:
+    """reprojection.rs:10-70 with an enumerated operation pipeline instead of a PROJ string"""
+
+    def __init__(self, source_crs, target_crs):
+        ops = (ProjOp * 8)()
+        n = check(lib().pb200_proj_pipeline_for_crs(source_crs.encode(), target_crs.encode(), ops, 8))
+        self.ops, self.n_ops = ops, n
+
+
+def reproject_point_cloud_within(point_cloud, source_crs, target_crs, ctx=None):  # reprojection.rs:132-146
+    ctx = ctx or get_context()
+    p = Projection(source_crs, target_crs)
+    d = point_cloud.desc()
+    check(lib().pb200_reproject(ctx._h, C.byref(d), None, p.ops, p.n_ops))
+
+
+def reproject_point_cloud_between(source_point_cloud, target_point_cloud, source_crs, target_crs, ctx=None):  # :201-227
+    ctx = ctx or get_context()
+    p = Projection(source_crs, target_crs)
+    sd, dd = source_point_cloud.desc(), target_point_cloud.desc()
+    check(lib().pb200_reproject(ctx._h, C.byref(sd), C.byref(dd), p.ops, p.n_ops))

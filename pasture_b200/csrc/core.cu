@@ -1,0 +1,430 @@
+// core.cu -- errors, context, memory helpers and the PointLayout descriptor (host side)
+#include "internal.h"
+
+namespace pb200 {
+
+std::atomic<uint64_t> g_launches{0};
+static thread_local char g_err[512] = "";
+
+int set_error(int code, const char* fmt, ...) {
+    va_list ap;
+    va_start(ap, fmt);
+    vsnprintf(g_err, sizeof g_err, fmt, ap);
+    va_end(ap);
+    return code;
+}
+
+int cuda_error(cudaError_t e, const char* what) {
+    int code = (e == cudaErrorNoDevice || e == cudaErrorInsufficientDriver || e == cudaErrorInvalidDevice)
+                   ? PB200_ERR_NO_DEVICE
+                   : (e == cudaErrorMemoryAllocation ? PB200_ERR_OOM : PB200_ERR_CUDA);
+    cudaGetLastError();
+    return set_error(code, "CUDA error %d (%s) in %s", (int)e, cudaGetErrorString(e), what);
+}
+
+int ensure_device(pb200_ctx* ctx) {
+    if (!ctx) return set_error(PB200_ERR_INVALID, "null context");
+    PB_CUDA(cudaSetDevice(ctx->device));
+    return PB200_OK;
+}
+
+int scratch(pb200_ctx* ctx, size_t bytes, void** out) {
+    if (bytes > ctx->d_scratch_bytes) {
+        if (ctx->d_scratch) {
+            PB_CUDA(cudaStreamSynchronize(ctx->stream));
+            PB_CUDA(cudaFree(ctx->d_scratch));
+            ctx->d_scratch = nullptr;
+            ctx->d_scratch_bytes = 0;
+        }
+        size_t want = bytes < (1u << 20) ? (1u << 20) : bytes;
+        PB_CUDA(cudaMalloc(&ctx->d_scratch, want));
+        ctx->d_scratch_bytes = want;
+    }
+    *out = ctx->d_scratch;
+    return PB200_OK;
+}
+
+int validate_desc(const pb200_buffer_desc* d, const char* what) {
+    if (!d || !d->layout) return set_error(PB200_ERR_INVALID, "%s: null buffer descriptor/layout", what);
+    if (d->kind != PB200_INTERLEAVED && d->kind != PB200_COLUMNAR)
+        return set_error(PB200_ERR_INVALID, "%s: buffer must be interleaved or columnar", what);
+    if (d->memspace != PB200_HOST && d->memspace != PB200_DEVICE)
+        return set_error(PB200_ERR_INVALID, "%s: bad memspace", what);
+    if (d->len > 0) {
+        if (d->kind == PB200_INTERLEAVED && !d->aos && d->layout->size > 0)
+            return set_error(PB200_ERR_INVALID, "%s: interleaved buffer without memory", what);
+        if (d->kind == PB200_COLUMNAR && !d->columns && !d->layout->attrs.empty())
+            return set_error(PB200_ERR_INVALID, "%s: columnar buffer without columns", what);
+    }
+    return PB200_OK;
+}
+
+static uint64_t align_to(uint64_t v, uint64_t a) {  // math/arithmetic.rs Alignable::align_to
+    if (a == 0) return v;
+    uint64_t r = v % a;
+    return r == 0 ? v : v + (a - r);
+}
+
+}  // namespace pb200
+
+using namespace pb200;
+
+extern "C" {
+
+int pb200_abi_version(void) { return PB200_ABI_VERSION; }
+const char* pb200_last_error(void) { return g_err; }
+uint64_t pb200_kernel_launch_count(void) { return g_launches.load(); }
+
+int pb200_ctx_create(int device, pb200_ctx** out) {
+    if (!out) return set_error(PB200_ERR_INVALID, "pb200_ctx_create: out is null");
+    *out = nullptr;
+    int n = 0;
+    cudaError_t e = cudaGetDeviceCount(&n);
+    if (e != cudaSuccess || n == 0) {
+        cudaGetLastError();
+        return set_error(PB200_ERR_NO_DEVICE,
+                         "no CUDA device available (%s); pasture_b200 has no CPU fallback",
+                         e == cudaSuccess ? "device count 0" : cudaGetErrorString(e));
+    }
+    if (device < 0 || device >= n) return set_error(PB200_ERR_NO_DEVICE, "device %d out of range (%d devices)", device, n);
+    PB_CUDA(cudaSetDevice(device));
+    pb200_ctx* c = new pb200_ctx();
+    c->device = device;
+    cudaDeviceProp prop;
+    PB_CUDA(cudaGetDeviceProperties(&prop, device));
+    if (prop.major < 10) {
+        delete c;
+        return set_error(PB200_ERR_NO_DEVICE, "device %d is sm_%d%d; this library is built for sm_100a only", device,
+                         prop.major, prop.minor);
+    }
+    c->sm_count = prop.multiProcessorCount;
+    c->smem_optin = prop.sharedMemPerBlockOptin;
+    PB_CUDA(cudaStreamCreateWithFlags(&c->stream, cudaStreamNonBlocking));
+    c->owns_stream = true;
+    PB_CUDA(cudaStreamCreateWithFlags(&c->copy_in, cudaStreamNonBlocking));
+    PB_CUDA(cudaStreamCreateWithFlags(&c->copy_out, cudaStreamNonBlocking));
+    PB_CUDA(cudaHostAlloc(&c->h_scratch, 4096, cudaHostAllocDefault));
+    *out = c;
+    return PB200_OK;
+}
+
+int pb200_ctx_set_stream(pb200_ctx* ctx, void* s) {
+    PB_TRY(ensure_device(ctx));
+    if (ctx->owns_stream && ctx->stream) {
+        cudaStreamSynchronize(ctx->stream);
+        cudaStreamDestroy(ctx->stream);
+    }
+    ctx->stream = (cudaStream_t)s;
+    ctx->owns_stream = false;
+    return PB200_OK;
+}
+
+void* pb200_ctx_get_stream(pb200_ctx* ctx) { return ctx ? (void*)ctx->stream : nullptr; }
+
+int pb200_ctx_synchronize(pb200_ctx* ctx) {
+    PB_TRY(ensure_device(ctx));
+    PB_CUDA(cudaStreamSynchronize(ctx->stream));
+    return PB200_OK;
+}
+
+int pb200_ctx_set_param(pb200_ctx* ctx, const char* key, int64_t v) {
+    if (!ctx || !key) return set_error(PB200_ERR_INVALID, "pb200_ctx_set_param: null argument");
+    std::string k(key);
+    if (k == "convert.tile_points") ctx->tile_points = v;
+    else if (k == "convert.threads") ctx->threads = v;
+    else if (k == "convert.stages") ctx->stages = v;
+    else if (k == "convert.ctas_per_sm") ctx->ctas_per_sm = v;
+    else if (k == "convert.force_direct") ctx->force_direct = v;
+    else return set_error(PB200_ERR_INVALID, "unknown parameter %s", key);
+    return PB200_OK;
+}
+
+void pb200_ctx_destroy(pb200_ctx* ctx) {
+    if (!ctx) return;
+    cudaSetDevice(ctx->device);
+    if (ctx->stream) cudaStreamSynchronize(ctx->stream);
+    if (ctx->d_scratch) cudaFree(ctx->d_scratch);
+    if (ctx->h_scratch) cudaFreeHost(ctx->h_scratch);
+    if (ctx->owns_stream && ctx->stream) cudaStreamDestroy(ctx->stream);
+    if (ctx->copy_in) cudaStreamDestroy(ctx->copy_in);
+    if (ctx->copy_out) cudaStreamDestroy(ctx->copy_out);
+    delete ctx;
+}
+
+int pb200_host_alloc(uint64_t bytes, void** out) {
+    if (!out) return set_error(PB200_ERR_INVALID, "null out");
+    PB_CUDA(cudaHostAlloc(out, bytes ? bytes : 1, cudaHostAllocDefault));
+    return PB200_OK;
+}
+int pb200_host_free(void* p) {
+    if (p) PB_CUDA(cudaFreeHost(p));
+    return PB200_OK;
+}
+int pb200_device_alloc(pb200_ctx* ctx, uint64_t bytes, void** out) {
+    PB_TRY(ensure_device(ctx));
+    PB_CUDA(cudaMalloc(out, bytes ? bytes : 1));
+    return PB200_OK;
+}
+int pb200_device_free(pb200_ctx* ctx, void* p) {
+    PB_TRY(ensure_device(ctx));
+    if (p) {
+        PB_CUDA(cudaStreamSynchronize(ctx->stream));
+        PB_CUDA(cudaFree(p));
+    }
+    return PB200_OK;
+}
+int pb200_memcpy_h2d(pb200_ctx* ctx, void* d, const void* s, uint64_t bytes) {
+    PB_TRY(ensure_device(ctx));
+    PB_CUDA(cudaMemcpyAsync(d, s, bytes, cudaMemcpyHostToDevice, ctx->stream));
+    PB_CUDA(cudaStreamSynchronize(ctx->stream));
+    return PB200_OK;
+}
+int pb200_memcpy_d2h(pb200_ctx* ctx, void* d, const void* s, uint64_t bytes) {
+    PB_TRY(ensure_device(ctx));
+    PB_CUDA(cudaMemcpyAsync(d, s, bytes, cudaMemcpyDeviceToHost, ctx->stream));
+    PB_CUDA(cudaStreamSynchronize(ctx->stream));
+    return PB200_OK;
+}
+int pb200_memset_device(pb200_ctx* ctx, void* d, int value, uint64_t bytes) {
+    PB_TRY(ensure_device(ctx));
+    PB_CUDA(cudaMemsetAsync(d, value, bytes, ctx->stream));
+    return PB200_OK;
+}
+
+// ---- PointLayout ---------------------------------------------------------------------------------
+
+uint64_t pb200_dtype_size(uint32_t dtype, uint64_t extra_size) {  // point_layout.rs:72-97
+    switch (dtype) {
+        case PB200_U8: case PB200_I8: return 1;
+        case PB200_U16: case PB200_I16: return 2;
+        case PB200_U32: case PB200_I32: case PB200_F32: return 4;
+        case PB200_U64: case PB200_I64: case PB200_F64: return 8;
+        case PB200_VEC3U8: return 3;
+        case PB200_VEC3U16: return 6;
+        case PB200_VEC3I32: case PB200_VEC3F32: return 12;
+        case PB200_VEC3F64: return 24;
+        case PB200_VEC4U8: return 4;
+        case PB200_BYTEARRAY: case PB200_CUSTOM: return extra_size;
+        default: return 0;
+    }
+}
+
+uint64_t pb200_dtype_min_alignment(uint32_t dtype, uint64_t extra_align) {  // point_layout.rs:100-126
+    switch (dtype) {
+        case PB200_U16: case PB200_I16: case PB200_VEC3U16: return 2;
+        case PB200_U32: case PB200_I32: case PB200_F32: case PB200_VEC3I32: case PB200_VEC3F32: return 4;
+        case PB200_U64: case PB200_I64: case PB200_F64: case PB200_VEC3F64: return 8;
+        case PB200_CUSTOM: return extra_align ? extra_align : 1;
+        default: return 1;
+    }
+}
+
+int pb200_layout_create(pb200_layout** out) {
+    if (!out) return set_error(PB200_ERR_INVALID, "null out");
+    *out = new pb200_layout();
+    return PB200_OK;
+}
+
+int pb200_layout_index_by_name(const pb200_layout* l, const char* name) {
+    if (!l || !name) return -1;
+    for (size_t i = 0; i < l->attrs.size(); ++i)
+        if (strcmp(l->attrs[i].name, name) == 0) return (int)i;
+    return -1;
+}
+
+int pb200_layout_index_of(const pb200_layout* l, const char* name, uint32_t dtype) {
+    if (!l || !name) return -1;
+    for (size_t i = 0; i < l->attrs.size(); ++i)
+        if (strcmp(l->attrs[i].name, name) == 0 && l->attrs[i].dtype == dtype) return (int)i;
+    return -1;
+}
+
+int pb200_layout_add_attribute(pb200_layout* l, const char* name, uint32_t dtype, uint64_t extra_size,
+                               uint64_t extra_align, uint64_t packed_n) {
+    if (!l || !name) return set_error(PB200_ERR_INVALID, "add_attribute: null argument");
+    if (dtype > PB200_CUSTOM) return set_error(PB200_ERR_INVALID, "add_attribute: unknown dtype %u", dtype);
+    if (strlen(name) >= PB200_MAX_NAME) return set_error(PB200_ERR_INVALID, "attribute name too long");
+    if (l->attrs.size() >= PB200_MAX_ATTRIBUTES) return set_error(PB200_ERR_INVALID, "too many attributes");
+    if (pb200_layout_index_by_name(l, name) >= 0)
+        return set_error(PB200_ERR_DUPLICATE_ATTR, "Point attribute %s is already present in this PointLayout!", name);
+    uint64_t min_align = pb200_dtype_min_alignment(dtype, extra_align);
+    uint64_t field_align = packed_n ? (packed_n < min_align ? packed_n : min_align) : min_align;
+    uint64_t next = l->attrs.empty() ? 0 : l->attrs.back().offset + l->attrs.back().size;
+    uint64_t offset = align_to(next, field_align);
+    uint64_t new_max = packed_n ? (packed_n < l->align ? packed_n : l->align) : (l->align > min_align ? l->align : min_align);
+    pb200_attr a;
+    memset(&a, 0, sizeof a);
+    strncpy(a.name, name, PB200_MAX_NAME - 1);
+    a.dtype = dtype;
+    a.extra_size = extra_size;
+    a.extra_align = extra_align;
+    a.offset = offset;
+    a.size = pb200_dtype_size(dtype, extra_size);
+    l->attrs.push_back(a);
+    uint64_t end = offset + a.size;
+    uint64_t unaligned = l->size > end ? l->size : end;
+    l->size = align_to(unaligned, new_max);
+    l->align = new_max;
+    return PB200_OK;
+}
+
+int pb200_layout_from_members_and_alignment(const pb200_attr* members, uint32_t n, uint64_t type_alignment,
+                                            pb200_layout** out) {
+    if (!out || (n && !members)) return set_error(PB200_ERR_INVALID, "null argument");
+    if (n > PB200_MAX_ATTRIBUTES) return set_error(PB200_ERR_INVALID, "too many attributes");
+    if (type_alignment == 0 || (type_alignment & (type_alignment - 1)))
+        return set_error(PB200_ERR_INVALID, "Could not create memory layout for PointLayout (alignment %llu)",
+                         (unsigned long long)type_alignment);
+    for (uint32_t i = 0; i < n; ++i)
+        for (uint32_t j = i + 1; j < n; ++j)
+            if (strncmp(members[i].name, members[j].name, PB200_MAX_NAME) == 0)
+                return set_error(PB200_ERR_DUPLICATE_ATTR, "All attributes must have unique names!");
+    std::vector<std::pair<uint64_t, uint64_t>> ranges;
+    for (uint32_t i = 0; i < n; ++i)
+        ranges.push_back({members[i].offset, members[i].offset + pb200_dtype_size(members[i].dtype, members[i].extra_size)});
+    for (size_t i = 1; i < ranges.size(); ++i) {  // stable insertion sort by start
+        auto r = ranges[i];
+        size_t j = i;
+        while (j > 0 && ranges[j - 1].first > r.first) { ranges[j] = ranges[j - 1]; --j; }
+        ranges[j] = r;
+    }
+    for (size_t i = 1; i < ranges.size(); ++i)
+        if (ranges[i - 1].second > ranges[i].first)
+            return set_error(PB200_ERR_OVERLAP, "All attributes must span non-overlapping memory regions!");
+    pb200_layout* l = new pb200_layout();
+    uint64_t unaligned = 0, max_off = 0;
+    bool have = false;
+    for (uint32_t i = 0; i < n; ++i) {
+        pb200_attr a = members[i];
+        a.name[PB200_MAX_NAME - 1] = 0;
+        a.size = pb200_dtype_size(a.dtype, a.extra_size);
+        if (!have || a.offset >= max_off) { max_off = a.offset; unaligned = a.offset + a.size; have = true; }
+        l->attrs.push_back(a);
+    }
+    l->size = align_to(unaligned, type_alignment);
+    l->align = type_alignment;
+    *out = l;
+    return PB200_OK;
+}
+
+int pb200_layout_clone(const pb200_layout* l, pb200_layout** out) {
+    if (!l || !out) return set_error(PB200_ERR_INVALID, "null argument");
+    *out = new pb200_layout(*l);
+    return PB200_OK;
+}
+uint32_t pb200_layout_num_attributes(const pb200_layout* l) { return l ? (uint32_t)l->attrs.size() : 0; }
+int pb200_layout_get_attribute(const pb200_layout* l, uint32_t i, pb200_attr* out) {
+    if (!l || !out || i >= l->attrs.size()) return set_error(PB200_ERR_INVALID, "attribute index out of bounds");
+    *out = l->attrs[i];
+    return PB200_OK;
+}
+uint64_t pb200_layout_size_of_point_entry(const pb200_layout* l) { return l ? l->size : 0; }
+uint64_t pb200_layout_alignment(const pb200_layout* l) { return l ? l->align : 0; }
+
+int pb200_layout_equal(const pb200_layout* a, const pb200_layout* b) {
+    if (!a || !b) return 0;
+    if (a->attrs.size() != b->attrs.size() || a->size != b->size || a->align != b->align) return 0;
+    for (size_t i = 0; i < a->attrs.size(); ++i) {
+        const pb200_attr &x = a->attrs[i], &y = b->attrs[i];
+        if (strcmp(x.name, y.name) != 0 || !dtype_equal(x, y) || x.offset != y.offset || x.size != y.size) return 0;
+    }
+    return 1;
+}
+
+int pb200_layout_compare_without_offsets(const pb200_layout* a, const pb200_layout* b) {
+    if (!a || !b || a->attrs.size() != b->attrs.size()) return 0;
+    for (const auto& x : a->attrs) {
+        int j = pb200_layout_index_by_name(b, x.name);
+        if (j < 0 || !dtype_equal(x, b->attrs[(size_t)j])) return 0;
+    }
+    return 1;
+}
+
+void pb200_layout_destroy(pb200_layout* l) { delete l; }
+
+// ---- LAS layouts (pasture-io/src/las/las_layout.rs:64-125, las_types.rs) ------------------------------
+
+struct LasFormat { bool extended, gps, color, nir, waveform; };
+static int las_format_of(int n, LasFormat* f) {
+    if (n < 0 || n > 10) return set_error(PB200_ERR_INVALID, "Unsupported LAS point format %d", n);
+    f->extended = n >= 6;
+    f->gps = (n == 1 || n == 3 || n == 4 || n == 5 || n >= 6);
+    f->color = (n == 2 || n == 3 || n == 5 || n == 7 || n == 8 || n == 10);
+    f->nir = (n == 8 || n == 10);
+    f->waveform = (n == 4 || n == 5 || n == 9 || n == 10);
+    return PB200_OK;
+}
+static void add_tail(pb200_layout* l, const LasFormat& f) {
+    if (f.gps) pb200_layout_add_attribute(l, "GpsTime", PB200_F64, 0, 0, 1);
+    if (f.color) pb200_layout_add_attribute(l, "ColorRGB", PB200_VEC3U16, 0, 0, 1);
+    if (f.nir) pb200_layout_add_attribute(l, "NIR", PB200_U16, 0, 0, 1);
+    if (f.waveform) {
+        pb200_layout_add_attribute(l, "WavePacketDescriptorIndex", PB200_U8, 0, 0, 1);
+        pb200_layout_add_attribute(l, "WaveformDataOffset", PB200_U64, 0, 0, 1);
+        pb200_layout_add_attribute(l, "WaveformPacketSize", PB200_U32, 0, 0, 1);
+        pb200_layout_add_attribute(l, "ReturnPointWaveformLocation", PB200_F32, 0, 0, 1);
+        pb200_layout_add_attribute(l, "WaveformParameters", PB200_VEC3F32, 0, 0, 1);
+    }
+}
+
+int pb200_las_raw_layout(int format, pb200_layout** out) {
+    LasFormat f;
+    PB_TRY(las_format_of(format, &f));
+    pb200_layout* l = new pb200_layout();
+    pb200_layout_add_attribute(l, "LASLocalPosition", PB200_VEC3I32, 0, 0, 1);
+    pb200_layout_add_attribute(l, "Intensity", PB200_U16, 0, 0, 1);
+    if (f.extended) pb200_layout_add_attribute(l, "LASExtendedFlags", PB200_U16, 0, 0, 1);
+    else pb200_layout_add_attribute(l, "LASBasicFlags", PB200_U8, 0, 0, 1);
+    pb200_layout_add_attribute(l, "Classification", PB200_U8, 0, 0, 1);
+    if (f.extended) {
+        pb200_layout_add_attribute(l, "UserData", PB200_U8, 0, 0, 1);
+        pb200_layout_add_attribute(l, "ScanAngle", PB200_I16, 0, 0, 1);
+    } else {
+        pb200_layout_add_attribute(l, "ScanAngleRank", PB200_I8, 0, 0, 1);
+        pb200_layout_add_attribute(l, "UserData", PB200_U8, 0, 0, 1);
+    }
+    pb200_layout_add_attribute(l, "PointSourceID", PB200_U16, 0, 0, 1);
+    add_tail(l, f);
+    *out = l;
+    return PB200_OK;
+}
+
+int pb200_las_default_layout(int format, pb200_layout** out) {
+    LasFormat f;
+    PB_TRY(las_format_of(format, &f));
+    pb200_layout* l = new pb200_layout();
+    pb200_layout_add_attribute(l, "Position3D", PB200_VEC3F64, 0, 0, 1);
+    pb200_layout_add_attribute(l, "Intensity", PB200_U16, 0, 0, 1);
+    pb200_layout_add_attribute(l, "ReturnNumber", PB200_U8, 0, 0, 1);
+    pb200_layout_add_attribute(l, "NumberOfReturns", PB200_U8, 0, 0, 1);
+    if (f.extended) {
+        pb200_layout_add_attribute(l, "ClassificationFlags", PB200_U8, 0, 0, 1);
+        pb200_layout_add_attribute(l, "ScannerChannel", PB200_U8, 0, 0, 1);
+    }
+    pb200_layout_add_attribute(l, "ScanDirectionFlag", PB200_U8, 0, 0, 1);
+    pb200_layout_add_attribute(l, "EdgeOfFlightLine", PB200_U8, 0, 0, 1);
+    pb200_layout_add_attribute(l, "Classification", PB200_U8, 0, 0, 1);
+    if (f.extended) {
+        pb200_layout_add_attribute(l, "UserData", PB200_U8, 0, 0, 1);
+        pb200_layout_add_attribute(l, "ScanAngle", PB200_I16, 0, 0, 1);
+    } else {
+        pb200_layout_add_attribute(l, "ScanAngleRank", PB200_I8, 0, 0, 1);
+        pb200_layout_add_attribute(l, "UserData", PB200_U8, 0, 0, 1);
+    }
+    pb200_layout_add_attribute(l, "PointSourceID", PB200_U16, 0, 0, 1);
+    add_tail(l, f);
+    *out = l;
+    return PB200_OK;
+}
+
+uint64_t pb200_expand_bits_by_3(uint64_t val) {  // math/bitmanip.rs:2-10
+    val &= 0x1FFFFFull;
+    val = (val | (val << 32)) & 0x00FF00000000FFFFull;
+    val = (val | (val << 16)) & 0x00FF0000FF0000FFull;
+    val = (val | (val << 8)) & 0xF00F00F00F00F00Full;
+    val = (val | (val << 4)) & 0x30C30C30C30C30C3ull;
+    val = (val | (val << 2)) & 0x1249249249249249ull;
+    return val;
+}
+
+}  // extern "C"

@@ -1,0 +1,80 @@
+// internal.h -- shared host-side definitions of libpasture_b200 (not part of the ABI)
+#pragma once
+#include <cuda_runtime.h>
+
+#include <atomic>
+#include <cstdarg>
+#include <cstdint>
+#include <cstdio>
+#include <cstring>
+#include <string>
+#include <vector>
+
+#include "../../include/pasture_b200.h"
+
+struct pb200_layout {
+    std::vector<pb200_attr> attrs;
+    uint64_t size = 0;   // memory_layout.size()
+    uint64_t align = 1;  // memory_layout.align()
+};
+
+struct pb200_ctx {
+    int device = 0;
+    cudaStream_t stream = nullptr;
+    bool owns_stream = false;
+    int sm_count = 148;
+    size_t smem_optin = 0;
+    // tuning knobs (0 = automatic)
+    int64_t tile_points = 0, threads = 0, stages = 0, ctas_per_sm = 0, force_direct = 0;
+    // scratch
+    void* d_scratch = nullptr;  // small device scratch (counters, partials)
+    size_t d_scratch_bytes = 0;
+    void* h_scratch = nullptr;  // pinned host scratch for small readbacks
+    // staging for HOST memspace buffers
+    cudaStream_t copy_in = nullptr, copy_out = nullptr;
+    bool convert_attr_set = false;
+};
+
+namespace pb200 {
+
+extern std::atomic<uint64_t> g_launches;
+int set_error(int code, const char* fmt, ...);
+int cuda_error(cudaError_t e, const char* what);
+
+#define PB_CUDA(x)                                         \
+    do {                                                   \
+        cudaError_t _e = (x);                              \
+        if (_e != cudaSuccess) return pb200::cuda_error(_e, #x); \
+    } while (0)
+#define PB_TRY(x)            \
+    do {                     \
+        int _rc = (x);       \
+        if (_rc < 0) return _rc; \
+    } while (0)
+
+inline bool is_scalar(uint32_t d) { return d <= PB200_F64; }
+inline bool is_cast_vec3(uint32_t d) { return d >= PB200_VEC3U8 && d <= PB200_VEC3F64; }
+inline uint32_t vec3_component(uint32_t d) {
+    switch (d) {
+        case PB200_VEC3U8: return PB200_U8;
+        case PB200_VEC3U16: return PB200_U16;
+        case PB200_VEC3F32: return PB200_F32;
+        case PB200_VEC3I32: return PB200_I32;
+        default: return PB200_F64;
+    }
+}
+inline bool has_conversion(uint32_t from, uint32_t to) {  // attribute_conversion.rs:194-260
+    if (from == to) return false;
+    return (is_scalar(from) && is_scalar(to)) || (is_cast_vec3(from) && is_cast_vec3(to));
+}
+inline bool dtype_equal(const pb200_attr& a, const pb200_attr& b) {
+    if (a.dtype != b.dtype) return false;
+    if (a.dtype == PB200_BYTEARRAY || a.dtype == PB200_CUSTOM) return a.extra_size == b.extra_size;
+    return true;
+}
+int ensure_device(pb200_ctx* ctx);
+// device scratch of at least `bytes` (grown lazily); contents undefined
+int scratch(pb200_ctx* ctx, size_t bytes, void** out);
+int validate_desc(const pb200_buffer_desc* d, const char* what);
+
+}  // namespace pb200

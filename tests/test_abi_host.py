@@ -1,0 +1,108 @@
+"""CPU-only checks of the product's boundary: the shared library loads, exports every symbol that
+include/pasture_b200.h declares, the host-side PointLayout logic equals the oracle, and compute entry points
+fail loudly (no CPU fallback) when there is no CUDA device."""
+import ctypes as C
+import os
+import re
+
+import numpy as np
+import pytest
+import torch
+
+import oracle as O
+import pasture_b200 as pb
+from pasture_b200 import _lib, attributes as A, PointLayout, PointAttributeDefinition, PointAttributeMember, FieldAlignment
+from pasture_b200 import PointAttributeDataType as DT
+from tests import util
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+
+def declared_symbols():
+    text = open(os.path.join(ROOT, "include", "pasture_b200.h")).read()
+    text = re.sub(r"/\*.*?\*/", "", text, flags=re.S)
+    return sorted(set(re.findall(r"\b(pb200_[a-z0-9_]+)\s*\(", text)))
+
+
+def test_library_exports_every_declared_symbol():
+    L = C.CDLL(_lib.SO_PATH)
+    names = declared_symbols()
+    assert len(names) > 50
+    for n in names:
+        assert hasattr(L, n), f"{n} declared in pasture_b200.h but not exported"
+        assert n in _lib.SIGNATURES, f"{n} has no ctypes signature"
+    assert L.pb200_abi_version() == 1
+
+
+def test_layout_doc_asserts():
+    l = PointLayout.from_attributes([A.POSITION_3D, A.INTENSITY])  # point_layout.rs:664-668, 924-927
+    assert len(l) == 2 and l.at(0).offset() == 0 and l.at(1).offset() == A.POSITION_3D.size()
+    assert l.size_of_point_entry() == 32
+    l1 = PointLayout.from_attributes_packed([A.INTENSITY, A.POSITION_3D], 1)  # :684-691
+    assert l1.at(0).offset() == 0 and l1.at(1).offset() == 2
+    assert PointLayout.from_attributes_packed([A.INTENSITY, A.POSITION_3D], 4).at(1).offset() == 4
+    l = PointLayout.from_members_and_alignment([A.INTENSITY.at_offset_in_type(2), A.POSITION_3D.at_offset_in_type(8)], 8)  # :713-717
+    assert l.at(0).offset() == 2 and l.at(1).offset() == 8 and l.size_of_point_entry() == 32
+    l = PointLayout.default()  # :770-776
+    l.add_attribute(A.INTENSITY, FieldAlignment.Default)
+    l.add_attribute(A.POSITION_3D, FieldAlignment.Default)
+    assert l.at(0) == A.INTENSITY.at_offset_in_type(0) and l.at(1) == A.POSITION_3D.at_offset_in_type(8)
+    assert l.has_attribute_with_name("Position3D") and l.has_attribute(A.POSITION_3D)  # :829, :845
+    l.add_attribute(PointAttributeDefinition("X", DT.U32))
+    assert not l.has_attribute(A.INTENSITY.with_custom_datatype(DT.U32))  # :848
+    assert l.get_attribute(A.POSITION_3D.with_custom_datatype(DT.U32)) is None  # :865-866
+    r = PointLayout.from_members_and_alignment([A.INTENSITY.at_offset_in_type(24), A.POSITION_3D.at_offset_in_type(0)], 8)  # :946-949
+    assert r.index_of(A.INTENSITY) == 0 and r.index_of(A.POSITION_3D) == 1 and r.index_of(A.CLASSIFICATION) is None
+
+
+def test_layout_errors():
+    l = PointLayout.from_attributes([A.POSITION_3D])
+    with pytest.raises(pb.PastureB200Error) as e:
+        l.add_attribute(A.POSITION_3D.with_custom_datatype(DT.Vec3f32))
+    assert e.value.code == -6
+    with pytest.raises(pb.PastureB200Error) as e:
+        PointLayout.from_members_and_alignment([PointAttributeMember.custom("a", DT.U32, 0), PointAttributeMember.custom("b", DT.U32, 2)], 4)
+    assert e.value.code == -7
+
+
+def test_las_layouts_match_oracle_and_reference_sizes():
+    for f in range(11):
+        util.las_layouts(f, True)
+        util.las_layouts(f, False)
+    assert [PointLayout.las_raw(f).size_of_point_entry() for f in range(11)] == [20, 28, 26, 34, 57, 63, 30, 36, 38, 59, 67]
+    assert [PointLayout.las_default(f).size_of_point_entry() for f in range(11)] == [35, 43, 41, 49, 72, 78, 46, 52, 54, 75, 83]
+
+
+def test_random_layouts_match_oracle():
+    rng = np.random.default_rng(11)
+    for trial in range(60):
+        n = int(rng.integers(1, 12))
+        attrs = [(f"a{i}", int(rng.integers(0, 16))) for i in range(n)]
+        packed = int(rng.choice([0, 0, 1, 2, 4, 8]))
+        util.layouts(attrs, packed)
+
+
+def test_expand_bits_by_3_matches_oracle():
+    rng = np.random.default_rng(0)
+    for v in list(rng.integers(0, 1 << 63, 200)) + [0, 1, 2, 0x1FFFFF, 0x155555]:
+        assert pb.algorithms.expand_bits_by_3(int(v)) == O.lib().po_expand_bits_by_3(int(v))
+
+
+@pytest.mark.skipif(torch.cuda.is_available(), reason="checks the no-GPU failure mode")
+def test_compute_fails_loudly_without_gpu():
+    with pytest.raises(pb.PastureB200Error) as e:
+        pb.get_context()
+    assert e.value.code == -100
+    h = C.c_void_p()
+    assert _lib.lib().pb200_ctx_create(0, C.byref(h)) == -100
+    assert b"no CPU fallback" in _lib.lib().pb200_last_error()
+
+
+def test_product_does_not_import_oracle():
+    """the product package must never route through oracle/"""
+    pkg = os.path.join(ROOT, "pasture_b200")
+    for dirpath, _, files in os.walk(pkg):
+        for f in files:
+            if f.endswith((".py", ".cu", ".h", ".cpp", ".hpp")) or f == "Makefile":
+                text = open(os.path.join(dirpath, f)).read()
+                assert "import oracle" not in text and "pasture_oracle" not in text, os.path.join(dirpath, f)

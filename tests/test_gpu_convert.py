@@ -1,0 +1,439 @@
+"""GPU parity tests of the conversion path (K0-K4), through the C ABI, against the CPU oracle.
+
+Bit-exact everywhere (integer casts, byte copies and -- with FMA contraction off -- the f64 transforms).
+Mirrors the reference's own tests: buffer_conversion.rs:684-930 (property tests for all four buffer pairs),
+raw_readers.rs:670-1086 (LAS fixtures incl. the different-layout read)."""
+import itertools
+
+import numpy as np
+import pytest
+import torch
+
+import oracle as O
+import pasture_b200 as pb
+from pasture_b200 import attributes as A, PointAttributeDefinition, BufferLayoutConverter, VectorBuffer, HashMapBuffer
+from pasture_b200 import PointAttributeDataType as DT
+from tests import las_expected as E
+from tests import util
+
+pytestmark = pytest.mark.gpu
+
+PAIRS = list(itertools.product([False, True], [False, True]))
+BUF = {False: VectorBuffer, True: HashMapBuffer}
+BIG = [("GpsTime", O.F64), ("ColorRGB", O.VEC3U16), ("Position3D", O.VEC3F64), ("Classification", O.U8), ("Intensity", O.I16)]
+SMALL = [("Position3D", O.VEC3F64), ("Classification", O.U8)]
+
+
+@pytest.fixture(scope="module")
+def ctx():
+    return pb.get_context(0)
+
+
+def run_both(ocv, pcv, osrc, psrc, dst_col, ol_to, pl_to, device="cuda"):
+    odst = ocv.convert(osrc, dst_col)
+    pdst = pcv.convert(psrc, BUF[dst_col], device=device)
+    torch.cuda.synchronize()
+    util.assert_buffers_match(odst, pdst)
+    return odst, pdst
+
+
+# ---- the reference's property tests ----------------------------------------------------------------
+
+@pytest.mark.parametrize("src_col,dst_col", PAIRS)
+def test_buffer_converter_default(ctx, src_col, dst_col):  # buffer_conversion.rs:684-722
+    ol, pl = util.layouts(BIG, packed=1)
+    olt, plt = util.layouts(SMALL, packed=1)
+    osrc, psrc = util.random_bytes_buffers(ol, pl, 16, src_col, seed=1)
+    _, pdst = run_both(O.OConverter(ol, olt), BufferLayoutConverter.for_layouts(pl, plt), osrc, psrc, dst_col, olt, plt)
+    assert np.array_equal(pdst.view_attribute(A.POSITION_3D), psrc.view_attribute(A.POSITION_3D))
+    assert np.array_equal(pdst.view_attribute(A.CLASSIFICATION), psrc.view_attribute(A.CLASSIFICATION))
+
+
+@pytest.mark.parametrize("src_col,dst_col", PAIRS)
+def test_buffer_converter_multiple_attributes_from_one(ctx, src_col, dst_col):  # :724-762
+    ol, pl = util.layouts(BIG, packed=1)
+    olt, plt = util.layouts([("Classification", O.U8), ("ReturnNumber", O.U8)])
+    osrc, psrc = util.random_bytes_buffers(ol, pl, 16, src_col, seed=2)
+    ocv = O.OConverter(ol, olt, with_default=True)
+    ocv.set_custom_mapping(("Classification", O.U8), ("ReturnNumber", O.U8))
+    pcv = BufferLayoutConverter.for_layouts_with_default(pl, plt)
+    pcv.set_custom_mapping(A.CLASSIFICATION, A.RETURN_NUMBER)
+    _, pdst = run_both(ocv, pcv, osrc, psrc, dst_col, olt, plt)
+    assert np.array_equal(pdst.view_attribute(A.RETURN_NUMBER), psrc.view_attribute(A.CLASSIFICATION))
+
+
+@pytest.mark.parametrize("src_col,dst_col", PAIRS)
+@pytest.mark.parametrize("apply_to_source", [True, False])
+def test_buffer_converter_transformed_attribute(ctx, src_col, dst_col, apply_to_source):  # :764-846
+    ol, pl = util.layouts(BIG, packed=1)
+    olt, plt = util.layouts([("Position3D", O.VEC3F64)])
+    osrc, psrc = util.random_bytes_buffers(ol, pl, 16, src_col, seed=3)
+    t = pb.Add(42.0)
+    ocv = O.OConverter(ol, olt, with_default=True)
+    ocv.set_custom_mapping_with_transformation(("Position3D", O.VEC3F64), ("Position3D", O.VEC3F64), O.VEC3F64,
+                                               util.oracle_transform(t), apply_to_source)
+    pcv = BufferLayoutConverter.for_layouts_with_default(pl, plt)
+    pcv.set_custom_mapping_with_transformation(A.POSITION_3D, A.POSITION_3D, t, apply_to_source)
+    _, pdst = run_both(ocv, pcv, osrc, psrc, dst_col, olt, plt)
+    assert np.array_equal(pdst.view_attribute(A.POSITION_3D), psrc.view_attribute(A.POSITION_3D) + 42.0)
+
+
+@pytest.mark.parametrize("src_col,dst_col", PAIRS)
+def test_buffer_converter_identity(ctx, src_col, dst_col):  # :848-873
+    ol, pl = util.layouts(BIG, packed=1)
+    osrc, psrc = util.random_bytes_buffers(ol, pl, 16, src_col, seed=4)
+    run_both(O.OConverter(ol, ol, with_default=True), BufferLayoutConverter.for_layouts_with_default(pl, pl), osrc, psrc,
+             dst_col, ol, pl)
+
+
+def test_buffer_converter_mismatched_len(ctx):  # :912-930 should_panic
+    ol, pl = util.layouts(BIG, packed=1)
+    _, psrc = util.random_bytes_buffers(ol, pl, 16, False, seed=5)
+    dst = VectorBuffer(pl, 8, "cuda")
+    with pytest.raises(pb.PastureB200Error) as e:
+        BufferLayoutConverter.for_layouts_with_default(pl, pl).convert_into(psrc, dst)
+    assert e.value.code == -5
+
+
+def test_contract_violations(ctx):
+    ol, pl = util.layouts(BIG, packed=1)
+    _, plt = util.layouts([("ReturnNumber", O.U8)])
+    with pytest.raises(pb.PastureB200Error) as e:  # :112-116
+        BufferLayoutConverter.for_layouts(pl, plt)
+    assert e.value.code == -1
+    assert BufferLayoutConverter.for_layouts_with_default(pl, plt).num_mappings() == 0
+    _, a = util.layouts([("X", O.VEC4U8)])
+    _, b = util.layouts([("X", O.U32)])
+    with pytest.raises(pb.PastureB200Error) as e:  # :383-388
+        BufferLayoutConverter.for_layouts(a, b)
+    assert e.value.code == -2
+    _, p32 = util.layouts([("Position3D", O.VEC3F32)])
+    cv = BufferLayoutConverter.for_layouts_with_default(pl, p32)
+    with pytest.raises(pb.PastureB200Error) as e:  # :209-213 transform after the cast must be typed as the target
+        cv.set_custom_mapping_with_transformation(A.POSITION_3D, A.POSITION_3D.with_custom_datatype(DT.Vec3f32),
+                                                  pb.Add(1.0, datatype=DT.Vec3f64), False)
+    assert e.value.code == -3
+    with pytest.raises(pb.PastureB200Error) as e:  # layout mismatch :302-303
+        _, other = util.layouts(BIG)
+        BufferLayoutConverter.for_layouts_with_default(pl, pl).convert_into(VectorBuffer(pl, 4, "cuda"), VectorBuffer(other, 4, "cuda"))
+    assert e.value.code == -4
+
+
+# ---- LAS fixtures (golden vectors of the reference) ---------------------------------------------------
+
+@pytest.mark.parametrize("fmt", range(11))
+@pytest.mark.parametrize("kind", ["plain", "extra_bytes"])
+@pytest.mark.parametrize("columnar", [False, True])
+@pytest.mark.parametrize("device", ["cuda", "cpu"])
+def test_las_fixture_read_default_layout(ctx, las_fixtures, fmt, kind, columnar, device):
+    entry = las_fixtures[kind][str(fmt)]
+    ol_raw, pl_raw = util.las_layouts(fmt, True)
+    if kind == "extra_bytes":
+        ol_raw.add_attribute("ExtraBytesU32", O.U32, packed=1)
+        pl_raw.add_attribute(PointAttributeDefinition("ExtraBytesU32", DT.U32), pb.FieldAlignment.Packed(1))
+    assert pl_raw.size_of_point_entry() == entry["record_length"]
+    raw = np.frombuffer(bytes.fromhex(entry["records_hex"]), dtype=np.uint8)
+    src = VectorBuffer.from_bytes(pl_raw, raw, device)
+    _, pl_def = util.las_layouts(fmt, False)
+    cv = pb.get_default_las_converter(pl_raw, pl_def, entry["scale"], entry["offset"])
+    dst = cv.convert(src, BUF[columnar])
+    torch.cuda.synchronize()
+    for name, expect in E.expected_default_layout_values(fmt).items():
+        got = dst.view_attribute(name)
+        assert got.dtype == expect.dtype and np.array_equal(got, expect), (name, got, expect)
+
+
+@pytest.mark.parametrize("fmt", range(11))
+@pytest.mark.parametrize("columnar", [False, True])
+def test_las_fixture_read_different_layout(ctx, las_fixtures, fmt, columnar):  # raw_readers.rs:815-911
+    entry = las_fixtures["plain"][str(fmt)]
+    _, pl_raw = util.las_layouts(fmt, True)
+    src = VectorBuffer.from_bytes(pl_raw, np.frombuffer(bytes.fromhex(entry["records_hex"]), dtype=np.uint8), "cuda")
+    target = pb.PointLayout.from_attributes([
+        A.POSITION_3D.with_custom_datatype(DT.Vec3f32), A.CLASSIFICATION.with_custom_datatype(DT.U32),
+        A.COLOR_RGB.with_custom_datatype(DT.Vec3u8), A.POINT_SOURCE_ID, A.WAVEFORM_PARAMETERS])
+    cv = pb.get_default_las_converter(pl_raw, target, entry["scale"], entry["offset"])
+    dst = cv.convert(src, BUF[columnar])
+    fl = E.fmt_flags(fmt)
+    assert np.array_equal(dst.view_attribute("Position3D"), E.POSITIONS.astype(np.float32))
+    assert np.array_equal(dst.view_attribute("Classification"), E.CLASSIFICATIONS.astype(np.uint32))
+    assert np.array_equal(dst.view_attribute("ColorRGB"), E.COLORS.astype(np.uint8) if fl["color"] else np.zeros((10, 3), np.uint8))
+    assert np.array_equal(dst.view_attribute("PointSourceID"), E.POINT_SOURCE_IDS)
+    assert np.array_equal(dst.view_attribute("WaveformParameters"),
+                          E.WAVEPACKET_PARAMETERS if fl["waveform"] else np.zeros((10, 3), np.float32))
+
+
+def test_las_invalid_position_type(ctx):  # raw_readers.rs:56
+    _, raw = util.las_layouts(0, True)
+    _, t = util.layouts([("Position3D", O.VEC3I32)])
+    with pytest.raises(pb.PastureB200Error) as e:
+        pb.get_default_las_converter(raw, t, (1, 1, 1), (0, 0, 0))
+    assert e.value.code == -10
+
+
+# ---- every cast of the table, incl. the Rust `as` edge cases ---------------------------------------
+
+EDGE_F = [0.0, -0.0, 0.5, -0.5, 0.99, -0.99, 1.5, -1.5, 2.9, -2.9, 127.0, 127.9, 128.0, -128.0, -128.9, -129.0, 255.0, 255.9,
+          256.0, 300.7, 32767.5, 32768.0, -32768.9, 65535.9, 65536.0, 2147483647.0, 2147483648.0, -2147483648.0,
+          -2147483649.0, 4294967295.0, 4294967296.0, 9.223372036854775e18, 9.223372036854776e18, -9.223372036854776e18,
+          -9.3e18, 1.8446744073709550e19, 1.8446744073709552e19, 1e20, -1e20, 1e40, -1e40, 1e-50, 16777217.0, 3.4028235e38,
+          3.5e38, float("inf"), float("-inf"), float("nan"), 5e-324, 1.1754942e-38, 0.1, 1 / 3]
+
+
+def edge_values(comp, n):
+    rng = np.random.default_rng(int(comp) + 100)
+    if np.issubdtype(comp, np.floating):
+        with np.errstate(over="ignore"):
+            base = np.array(EDGE_F, dtype=np.float64).astype(comp)
+        rnd = rng.integers(0, 256, (n - len(base), np.dtype(comp).itemsize), dtype=np.uint8).view(comp).reshape(-1)
+        return np.concatenate([base, rnd])
+    info = np.iinfo(comp)
+    base = np.array([0, 1, info.max, info.min, info.max - 1, info.min + 1 if info.min < 0 else 2, 127, 128, 255, 256 % (int(info.max) + 1),
+                     16777217 % (int(info.max) + 1)], dtype=np.uint64).astype(comp)
+    rnd = rng.integers(info.min, info.max, n - len(base), dtype=comp, endpoint=True)
+    return np.concatenate([base, rnd])
+
+
+@pytest.mark.parametrize("src_col,dst_col", [(True, True), (False, False)])
+def test_all_scalar_casts_bit_exact(ctx, src_col, dst_col):
+    """all 90 directed scalar pairs (attribute_conversion.rs:194-246) in one layout pair per source type"""
+    n = 1000
+    for sdt in range(10):
+        src_attrs = [("v", sdt)]
+        dst_types = [d for d in range(10) if d != sdt]
+        ol, pl = util.layouts(src_attrs, packed=1)
+        olt, plt = util.layouts([(f"t{d}", d) for d in dst_types], packed=1)
+        osrc = O.OBuffer(ol, n, src_col)
+        osrc.set_attribute("v", edge_values(O.NP_DTYPES[sdt], n))
+        psrc = util.to_pb(osrc, pl)
+        ocv = O.OConverter(ol, olt, with_default=True)
+        pcv = BufferLayoutConverter.for_layouts_with_default(pl, plt)
+        for d in dst_types:
+            ocv.set_custom_mapping(("v", sdt), (f"t{d}", d))
+            pcv.set_custom_mapping(PointAttributeDefinition("v", sdt), PointAttributeDefinition(f"t{d}", d))
+        run_both(ocv, pcv, osrc, psrc, dst_col, olt, plt)
+
+
+def test_all_vec3_casts_bit_exact(ctx):
+    """all 20 directed Vec3 pairs (attribute_conversion.rs:248-260)"""
+    n = 999
+    vec3 = [O.VEC3U8, O.VEC3U16, O.VEC3F32, O.VEC3I32, O.VEC3F64]
+    for sdt in vec3:
+        ol, pl = util.layouts([("v", sdt)], packed=1)
+        dts = [d for d in vec3 if d != sdt]
+        olt, plt = util.layouts([(f"t{d}", d) for d in dts], packed=1)
+        for src_col, dst_col in PAIRS:
+            osrc = O.OBuffer(ol, n, src_col)
+            osrc.set_attribute("v", edge_values(O.NP_DTYPES[O.VEC3_COMPONENT[sdt]], 3 * n).reshape(n, 3))
+            psrc = util.to_pb(osrc, pl)
+            ocv = O.OConverter(ol, olt, with_default=True)
+            pcv = BufferLayoutConverter.for_layouts_with_default(pl, plt)
+            for d in dts:
+                ocv.set_custom_mapping(("v", sdt), (f"t{d}", d))
+                pcv.set_custom_mapping(PointAttributeDefinition("v", sdt), PointAttributeDefinition(f"t{d}", d))
+            run_both(ocv, pcv, osrc, psrc, dst_col, olt, plt)
+
+
+# ---- random layouts, ranges, ragged sizes, both kernels ---------------------------------------------
+
+@pytest.mark.parametrize("seed", range(12))
+def test_random_layout_conversion(ctx, seed):
+    rng = np.random.default_rng(1000 + seed)
+    n_src = int(rng.integers(1, 9))
+    src_attrs = [(f"a{i}", int(rng.choice(list(range(16)) + [O.BYTEARRAY])), int(rng.integers(1, 9))) for i in range(n_src)]
+    src_attrs = [(a, d, e if d == O.BYTEARRAY else 0) for a, d, e in src_attrs]
+    ol, pl = util.layouts(src_attrs, packed=int(rng.choice([0, 1, 2])))
+    dst_attrs = []
+    for (a, d, e) in src_attrs:
+        if rng.random() < 0.25:
+            continue
+        if d <= O.F64 and rng.random() < 0.6:
+            d = int(rng.integers(0, 10))
+        elif O.VEC3U8 <= d <= O.VEC3F64 and rng.random() < 0.6:
+            d = int(rng.integers(O.VEC3U8, O.VEC3F64 + 1))
+        dst_attrs.append((a, d, e))
+    if rng.random() < 0.5:
+        dst_attrs.append(("missing_in_source", O.U32, 0))
+    if not dst_attrs:
+        dst_attrs = [src_attrs[0]]
+    order = rng.permutation(len(dst_attrs))
+    dst_attrs = [dst_attrs[i] for i in order]
+    olt, plt = util.layouts(dst_attrs, packed=int(rng.choice([0, 1, 4])))
+    n = int(rng.choice([1, 7, 100, 1000, 4097, 20011]))
+    for src_col, dst_col in PAIRS:
+        osrc, psrc = util.random_bytes_buffers(ol, pl, n, src_col, seed=seed, finite_floats=bool(seed % 2))
+        ocv = O.OConverter(ol, olt, with_default=True)
+        pcv = BufferLayoutConverter.for_layouts_with_default(pl, plt)
+        # target pre-filled with a pattern: unmapped bytes / padding must survive
+        odst = O.OBuffer(olt, n, dst_col)
+        pdst = BUF[dst_col](plt, n, "cuda")
+        if dst_col:
+            for c in odst.columns:
+                c[:] = 0xA5
+            for c in pdst.columns:
+                c.fill_(0xA5)
+        else:
+            odst.aos[:] = 0xA5
+            pdst.data.fill_(0xA5)
+        ocv.convert_into(osrc, odst)
+        pcv.convert_into(psrc, pdst)
+        torch.cuda.synchronize()
+        util.assert_buffers_match(odst, pdst, f"seed {seed} {src_col}->{dst_col}")
+        if not dst_col:
+            assert np.array_equal(odst.aos[: n * olt.size], pdst.raw_bytes()), "padding / unmapped bytes changed"
+
+
+@pytest.mark.parametrize("src_col,dst_col", PAIRS)
+def test_ranges_with_unaligned_offsets(ctx, src_col, dst_col):
+    """convert_into_range (buffer_conversion.rs:292): arbitrary sub-ranges, neighbours untouched"""
+    ol, pl = util.las_layouts(0, True)
+    olt, plt = util.las_layouts(0, False)
+    n = 5000
+    osrc = O.OBuffer(ol, n, False)
+    osrc.aos[:] = O.gen_las_fmt0_records(0, n)
+    if src_col:
+        osrc = O.OConverter(ol, ol, with_default=True).convert(osrc, True)
+    psrc = util.to_pb(osrc, pl)
+    ocv = O.OConverter.las_default(ol, olt, (0.001,) * 3, (500000.0, 5400000.0, 100.0))
+    pcv = pb.get_default_las_converter(pl, plt, (0.001,) * 3, (500000.0, 5400000.0, 100.0))
+    odst = O.OBuffer(olt, n + 13, dst_col)
+    pdst = BUF[dst_col](plt, n + 13, "cuda")
+    for (sb, se, db) in [(0, 1, 0), (3, 1003, 7), (1001, 4998, 1010), (4999, 5000, 5012), (17, 17, 3)]:
+        ocv.convert_into_range(osrc, sb, se, odst, db, db + (se - sb))
+        pcv.convert_into_range(psrc, range(sb, se), pdst, range(db, db + (se - sb)))
+    torch.cuda.synchronize()
+    util.assert_buffers_match(odst, pdst)
+
+
+@pytest.mark.parametrize("n", [0, 1, 15, 16, 17, 767, 768, 769, 100003])
+def test_c2_sizes_tile_and_direct_kernels_agree(ctx, n):
+    """C2 mapping at ragged sizes; the tile pipeline (K1) and the direct kernel (K0) give identical bytes"""
+    ol, pl = util.las_layouts(0, True)
+    olt, plt = util.las_layouts(0, False)
+    osrc = O.OBuffer(ol, n, False)
+    if n:
+        osrc.aos[: 20 * n] = O.gen_las_fmt0_records(0, n)
+    psrc = util.to_pb(osrc, pl)
+    scale, offset = (0.001,) * 3, (500000.0, 5400000.0, 100.0)
+    odst = O.OConverter.las_default(ol, olt, scale, offset).convert(osrc, True)
+    pcv = pb.get_default_las_converter(pl, plt, scale, offset)
+    a = pcv.convert(psrc, HashMapBuffer)
+    ctx.set_param("convert.force_direct", 1)
+    try:
+        b = pcv.convert(psrc, HashMapBuffer)
+    finally:
+        ctx.set_param("convert.force_direct", 0)
+    torch.cuda.synchronize()
+    util.assert_buffers_match(odst, a, "tile kernel")
+    util.assert_buffers_match(odst, b, "direct kernel")
+
+
+@pytest.mark.parametrize("tile,threads,stages,cps", [(16, 32, 1, 1), (128, 64, 2, 4), (2048, 512, 4, 1), (640, 256, 3, 2)])
+def test_pipeline_shapes(ctx, tile, threads, stages, cps):
+    """every tile/stage/thread shape of the pipeline produces the same bytes"""
+    ol, pl = util.las_layouts(3, True)
+    olt, plt = util.las_layouts(3, False)
+    n = 30011
+    osrc, psrc = util.random_bytes_buffers(ol, pl, n, False, seed=9)
+    odst = O.OConverter.las_default(ol, olt, (0.01, 0.02, 0.03), (1.5, -2.5, 3.5)).convert(osrc, False)
+    pcv = pb.get_default_las_converter(pl, plt, (0.01, 0.02, 0.03), (1.5, -2.5, 3.5))
+    for k, v in (("tile_points", tile), ("threads", threads), ("stages", stages), ("ctas_per_sm", cps)):
+        ctx.set_param("convert." + k, v)
+    try:
+        pdst = pcv.convert(psrc, VectorBuffer)
+        torch.cuda.synchronize()
+    finally:
+        for k in ("tile_points", "threads", "stages", "ctas_per_sm"):
+            ctx.set_param("convert." + k, 0)
+    util.assert_buffers_match(odst, pdst)
+
+
+def test_write_direction_c1_and_out_of_range_count(ctx):
+    """C1: LasPointFormat0 (35 B) -> raw LAS fmt-0 (20 B) with (p - offset) / scale before the cast
+    (write_helpers.rs:15-17: truncation; out-of-range values counted instead of panicking)"""
+    n = 200000
+    offset = (500000.0, 5400000.0, 100.0)
+    ol, pl = util.las_layouts(0, False)
+    olt, plt = util.las_layouts(0, True)
+    osrc = O.OBuffer(ol, n, False)
+    osrc.aos[:] = O.gen_c1_points(0, n, 42, offset)
+    pos = osrc.attribute("Position3D").copy()
+    pos[5] = [3e6 + offset[0], 0, 0]       # > i32::MAX mm
+    pos[6] = [np.nan, np.inf, -np.inf]     # NaN -> 0 (no panic), +-inf out of range
+    osrc.set_attribute("Position3D", pos)
+    psrc = util.to_pb(osrc, pl)
+    t = pb.InvScaleOffset(0.001, offset)
+    ocv = O.OConverter(ol, olt, with_default=True)
+    ocv.set_custom_mapping_with_transformation(("Position3D", O.VEC3F64), ("LASLocalPosition", O.VEC3I32), O.VEC3F64,
+                                               util.oracle_transform(t), True)
+    pcv = BufferLayoutConverter.for_layouts_with_default(pl, plt)
+    pcv.set_custom_mapping_with_transformation(A.POSITION_3D, pb.ATTRIBUTE_LOCAL_LAS_POSITION, t, True)
+    odst = ocv.convert(osrc, False)
+    pdst = VectorBuffer(plt, n, "cuda")
+    oor = pcv.convert_into(psrc, pdst, count_out_of_range=True)
+    util.assert_buffers_match(odst, pdst)
+    assert oor == 4  # x, y of point 5 (y = -5.4e9 mm) and +-inf of point 6
+    got = pdst.view_attribute(pb.ATTRIBUTE_LOCAL_LAS_POSITION)
+    exact = np.trunc((pos[100:] - np.array(offset)) / 0.001)
+    assert np.array_equal(got[100:], exact.astype(np.int32))
+
+
+def test_host_memspace_staged_path(ctx):
+    """HOST buffers: chunks staged through device memory; result lands in caller-owned host memory"""
+    ol, pl = util.las_layouts(1, True)
+    olt, plt = util.las_layouts(1, False)
+    n = 70001
+    osrc, _ = util.random_bytes_buffers(ol, pl, n, False, seed=21, device="cpu")
+    psrc = util.to_pb(osrc, pl, "cpu", pinned=True)
+    for dst_col in (False, True):
+        odst = O.OConverter.las_default(ol, olt, (0.001,) * 3, (1.0, 2.0, 3.0)).convert(osrc, dst_col)
+        pcv = pb.get_default_las_converter(pl, plt, (0.001,) * 3, (1.0, 2.0, 3.0))
+        pdst = BUF[dst_col](plt, n, "cpu", pinned=True)
+        pcv.convert_into(psrc, pdst)
+        util.assert_buffers_match(odst, pdst)
+        # mixed: host source, device target
+        pdev = BUF[dst_col](plt, n, "cuda")
+        pcv.convert_into(psrc, pdev)
+        torch.cuda.synchronize()
+        util.assert_buffers_match(odst, pdev)
+
+
+def test_fused_bounds_equals_oracle_bounds(ctx):
+    ol, pl = util.las_layouts(0, True)
+    olt, plt = util.las_layouts(0, False)
+    n = 123457
+    osrc = O.OBuffer(ol, n, False)
+    osrc.aos[:] = O.gen_las_fmt0_records(0, n)
+    psrc = util.to_pb(osrc, pl)
+    scale, offset = (0.001,) * 3, (500000.0, 5400000.0, 100.0)
+    odst = O.OConverter.las_default(ol, olt, scale, offset).convert(osrc, True)
+    omn, omx = O.calculate_bounds(odst)
+    pcv = pb.get_default_las_converter(pl, plt, scale, offset)
+    pdst = HashMapBuffer(plt, n, "cuda")
+    mn, mx = pcv.convert_into_range_with_bounds(psrc, range(0, n), pdst, range(0, n))
+    assert list(mn) == list(omn) and list(mx) == list(omx)
+    util.assert_buffers_match(odst, pdst)
+    assert pcv.convert_into_range_with_bounds(psrc, range(0, 0), pdst, range(0, 0)) is None
+
+
+def test_transform_attribute_and_converting_view(ctx):
+    ol, pl = util.layouts([("Position3D", O.VEC3F32), ("Intensity", O.U16), ("Position3D64", O.VEC3F64)], packed=1)
+    n = 3001
+    for col in (False, True):
+        osrc, psrc = util.random_bytes_buffers(ol, pl, n, col, seed=33)
+        # pnts_reader.rs:265-277 RTC centre on Vec3f32 and Vec3f64
+        rtc = (1215019.0, -4736339.0, 4081627.0)
+        pb.transform_attribute(psrc, A.POSITION_3D.with_custom_datatype(DT.Vec3f32), pb.Add(rtc))
+        pb.transform_attribute(psrc, PointAttributeDefinition("Position3D64", DT.Vec3f64), pb.Add(rtc))
+        torch.cuda.synchronize()
+        p32 = osrc.attribute("Position3D")
+        assert np.array_equal(psrc.view_attribute("Position3D").view(np.uint32),
+                              (p32.astype(np.float64) + np.array(rtc)).astype(np.float32).view(np.uint32))
+        assert np.array_equal(psrc.view_attribute("Position3D64").view(np.uint64),
+                              (osrc.attribute("Position3D64") + np.array(rtc)).view(np.uint64))
+        assert np.array_equal(psrc.view_attribute("Intensity"), osrc.attribute("Intensity"))
+        # AttributeViewConverting: intensity as f64, positions as Vec3i32
+        v = pb.view_attribute_with_conversion(psrc, A.INTENSITY.with_custom_datatype(DT.F64))
+        assert np.array_equal(v, osrc.attribute("Intensity").astype(np.float64))
+        with pytest.raises(pb.PastureB200Error):
+            pb.view_attribute_with_conversion(psrc, A.INTENSITY.with_custom_datatype(DT.Vec3f64))
