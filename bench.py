@@ -1,0 +1,333 @@
+#!/usr/bin/env python
+"""bench.py -- headline benchmark of the pasture hot path on B200 (contract: see the task statement).
+
+Workload (BASELINE.json configs[1], SURVEY 8d "C2"): 100 M raw LAS format-0 records (interleaved, 20 B)
+-> columnar LasPointFormat0 attributes (10 columns, 35 B/point) with the default LAS read mappings
+(i32 -> f64 cast then v*scale+offset on POSITION_3D, four bit-field extracts, five copies), i.e.
+pasture's BufferLayoutConverter::convert_into_range as configured by get_default_las_converter
+(pasture-io/src/las/raw_readers.rs:31-167).  Algorithmic bytes: 20 read + 35 written = 55 B/point.
+
+  python bench.py --gpus N --steps K --warmup W            our arm (one process per GPU under torchrun for N > 1)
+  python bench.py --impl reference --gpus N ...            the reference algorithm on the host cores (rank 0 only)
+
+N > 1: every rank converts its own 100 M-point shard (weak scaling, shard r = point indices
+r*1e8 ...), the AABB of the produced positions is fused into the convert kernel and one 48-byte NCCL
+all-reduce(min) of [min xyz, -max xyz] gives the global bounds.
+"""
+import argparse
+import json
+import os
+import sys
+import threading
+import time
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+if ROOT not in sys.path:
+    sys.path.insert(0, ROOT)
+
+POINTS_PER_GPU = 100_000_000
+BYTES_IN, BYTES_OUT = 20, 35
+SCALE = (0.001, 0.001, 0.001)
+OFFSET = (500000.0, 5400000.0, 100.0)
+METRIC = "points/sec layout-convert+transform (interleaved LAS fmt0 -> columnar, scale/offset)"
+
+
+def measured_peak_gbs():
+    p = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    try:
+        with open(p) as fh:
+            return float(json.load(fh)["hbm_gbs"]), "measured (MEASURED_PEAKS.json hbm_gbs)"
+    except Exception:
+        return 6650.0, "fallback (B200_PROFILING.md 6.65 TB/s)"
+
+
+def ncu_traffic_bytes():
+    """dram bytes per launch of the convert kernel from the committed ncu --set full capture, if any"""
+    p = os.path.join(ROOT, "profiles", "convert_c2_ncu_summary.json")
+    try:
+        with open(p) as fh:
+            return float(json.load(fh)["dram_bytes_per_launch"])
+    except Exception:
+        return None
+
+
+class ClockSampler:
+    """samples SM clock / throttle reasons during the timed region (pynvml, else nvidia-smi)"""
+
+    def __init__(self, index):
+        self.index, self.samples, self.reasons, self.max_mhz = index, [], set(), None
+        self._stop = threading.Event()
+        self._thread = None
+        self._nvml = None
+        try:
+            import pynvml
+            pynvml.nvmlInit()
+            self._nvml = pynvml
+            self._h = pynvml.nvmlDeviceGetHandleByIndex(index)
+            self.max_mhz = pynvml.nvmlDeviceGetMaxClockInfo(self._h, pynvml.NVML_CLOCK_SM)
+        except Exception:
+            self._nvml = None
+
+    def _loop(self):
+        nv = self._nvml
+        names = {}
+        if nv is not None:
+            for n in ("HwSlowdown", "HwThermalSlowdown", "SwThermalSlowdown", "SwPowerCap", "HwPowerBrakeSlowdown",
+                      "SyncBoost", "ApplicationsClocksSetting", "DisplayClockSetting"):
+                v = getattr(nv, "nvmlClocksThrottleReason" + n, None)
+                if v is not None:
+                    names[int(v)] = n
+        while not self._stop.is_set():
+            try:
+                if nv is not None:
+                    self.samples.append(nv.nvmlDeviceGetClockInfo(self._h, nv.NVML_CLOCK_SM))
+                    r = int(nv.nvmlDeviceGetCurrentClocksThrottleReasons(self._h))
+                    for bit, n in names.items():
+                        if r & bit:
+                            self.reasons.add(n)
+                else:
+                    import subprocess
+                    out = subprocess.run(["nvidia-smi", "-i", str(self.index), "--query-gpu=clocks.sm,clocks.max.sm,"
+                                          "clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
+                                          "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap",
+                                          "--format=csv,noheader,nounits"], capture_output=True, text=True, timeout=5).stdout
+                    f = [x.strip() for x in out.strip().split(",")]
+                    self.samples.append(int(f[0]))
+                    self.max_mhz = int(f[1])
+                    for name, v in zip(("HwSlowdown", "HwThermalSlowdown", "SwThermalSlowdown", "SwPowerCap"), f[2:6]):
+                        if v.lower().startswith("active"):
+                            self.reasons.add(name)
+            except Exception:
+                pass
+            self._stop.wait(0.05)
+
+    def __enter__(self):
+        self._thread = threading.Thread(target=self._loop, daemon=True)
+        self._thread.start()
+        return self
+
+    def __exit__(self, *a):
+        self._stop.set()
+        self._thread.join(timeout=2)
+
+    def summary(self):
+        s = sorted(self.samples)
+        return {"sm_mhz": (s[len(s) // 2] if s else None), "sm_max_mhz": self.max_mhz, "reasons": sorted(self.reasons),
+                "samples": len(s)}
+
+
+def oracle_convert_rate(n_points, threads, repeats=1):
+    """times the CPU restatement of convert_into_range (attribute-outer / point-inner, function-pointer casts,
+    buffer_conversion.rs:546-604) on n_points of the C2 stream; returns (points/s, seconds of the best repeat)"""
+    import oracle as O
+    ol_raw, ol_def = O.OLayout.las_raw(0), O.OLayout.las_default(0)
+    src = O.OBuffer(ol_raw, n_points, False)
+    src.aos[:] = O.gen_las_fmt0_records(0, n_points, 42)
+    dst = O.OBuffer(ol_def, n_points, True)
+    cv = O.OConverter.las_default(ol_raw, ol_def, SCALE, OFFSET)
+    best = None
+    for _ in range(repeats):
+        t0 = time.perf_counter()
+        cv.convert_into_range(src, 0, n_points, dst, 0, n_points, threads=threads)
+        dt = time.perf_counter() - t0
+        best = dt if best is None or dt < best else best
+    return n_points / best, best
+
+
+def run_reference(args):
+    """--impl reference: the reference's algorithm for this path on the host cores. The Rust reference cannot be
+    built in this image (no rustc/cargo), so this is the oracle port (kind "port"): the same per-range routine
+    over all host threads (what wrapping convert_into_range in rayon would give; the reference itself is
+    single-threaded for this path)."""
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return
+    cores = os.cpu_count() or 1
+    sample = 20_000_000
+    import oracle as O
+    ol_raw, ol_def = O.OLayout.las_raw(0), O.OLayout.las_default(0)
+    src = O.OBuffer(ol_raw, sample, False)
+    src.aos[:] = O.gen_las_fmt0_records(0, sample, 42)
+    dst = O.OBuffer(ol_def, sample, True)
+    cv = O.OConverter.las_default(ol_raw, ol_def, SCALE, OFFSET)
+    for _ in range(max(1, args.warmup)):
+        cv.convert_into_range(src, 0, sample, dst, 0, sample, threads=cores)
+    t0 = time.perf_counter()
+    for _ in range(args.steps):
+        cv.convert_into_range(src, 0, sample, dst, 0, sample, threads=cores)
+    dt = time.perf_counter() - t0
+    value = sample * args.steps / dt
+    desc = f"{sample} points of the C2 stream per step, {cores} threads over disjoint point ranges, host memory"
+    print(json.dumps({
+        "impl": "reference", "metric": METRIC, "value": value, "unit": "points/s", "n_gpus": args.gpus,
+        "steps": args.steps, "warmup": args.warmup, "ms_per_step": dt / args.steps * 1e3, "higher_is_better": True,
+        "scaling": "weak", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
+        "config": {"workload": "C2: 100M-point interleaved->columnar convert + scale/offset (bounded CPU sample)",
+                   "points_per_step": sample},
+        "cpu_baseline": {"value": value, "unit": "points/s", "cores": cores, "kind": "port", "sample": desc},
+        "e2e": {"value": value, "unit": "points/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+        "gpu_launches": 0,
+    }))
+
+
+def run_ours(args):
+    import torch
+    import torch.distributed as dist
+
+    import pasture_b200 as pb
+    from pasture_b200.algorithms import synth_las_fmt0_records
+
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    rank = int(os.environ.get("RANK", "0"))
+    local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+    if world > 1:
+        torch.cuda.set_device(local_rank)
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
+    dev = torch.device("cuda", local_rank if world > 1 else 0)
+    torch.cuda.set_device(dev)
+    ctx = pb.get_context(dev.index)
+    n = args.points
+    fused = world > 1 or args.fused_bounds
+
+    pl_raw, pl_def = pb.PointLayout.las_raw(0), pb.PointLayout.las_default(0)
+    src = synth_las_fmt0_records(n, first_index=rank * n, seed=42, device=dev)  # resident in HBM before timing
+    dst = pb.HashMapBuffer(pl_def, n, dev)
+    cv = pb.get_default_las_converter(pl_raw, pl_def, SCALE, OFFSET)
+    minmax6 = torch.zeros(6, dtype=torch.float64, device=dev)
+    rng_all = range(0, n)
+
+    def step():
+        if fused:
+            cv.convert_into_range_with_bounds_device(src, rng_all, dst, rng_all, minmax6)
+            if world > 1:
+                dist.all_reduce(minmax6, op=dist.ReduceOp.MIN)
+        else:
+            cv.convert_into_range(src, rng_all, dst, rng_all)
+
+    for _ in range(max(3, args.warmup)):
+        step()
+    torch.cuda.synchronize()
+    if world > 1:
+        dist.barrier()
+        torch.cuda.synchronize()
+
+    # ---- timed region: exactly K steps, CUDA events on the launching stream (torch's current stream) ----
+    ev = [torch.cuda.Event(enable_timing=True) for _ in range(args.steps + 1)]
+    launches0 = pb.kernel_launch_count()
+    with ClockSampler(dev.index) as clocks:
+        ev[0].record()
+        for i in range(args.steps):
+            step()
+            ev[i + 1].record()
+        torch.cuda.synchronize()
+        if world > 1:
+            dist.barrier()
+            torch.cuda.synchronize()
+    launches = pb.kernel_launch_count() - launches0
+    total_ms = ev[0].elapsed_time(ev[-1])
+    step_ms = [ev[i].elapsed_time(ev[i + 1]) for i in range(args.steps)]
+    if world > 1:
+        t = torch.tensor([total_ms], dtype=torch.float64, device=dev)
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        total_ms = float(t.item())
+    value = world * n * args.steps / (total_ms * 1e-3)
+
+    # ---- sanity: the produced bounds must be the bounds of the shard (cheap device-side check) ----------
+    if fused:
+        mm = minmax6.cpu().numpy()
+        assert mm[0] <= -mm[3] and mm[1] <= -mm[4] and mm[2] <= -mm[5], mm
+
+    if rank != 0:
+        if world > 1:
+            dist.destroy_process_group()
+        return
+
+    # ---- roofline of the dominant kernel (the only kernel in a step at N = 1) -----------------------------
+    peak, peak_src = measured_peak_gbs()
+    avg_kernel_ms = sum(step_ms) / len(step_ms)
+    best_kernel_ms = min(step_ms)
+    achieved = (BYTES_IN + BYTES_OUT) * n / (avg_kernel_ms * 1e-3) / 1e9
+    traffic = ncu_traffic_bytes()
+    roofline = {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
+                "traffic": traffic, "peak_source": peak_src, "algorithmic_bytes_per_launch": (BYTES_IN + BYTES_OUT) * n,
+                "avg_launch_ms": avg_kernel_ms, "best_launch_ms": best_kernel_ms,
+                "frac_of_8TBps_nominal": achieved / 8000.0, "kernel": "convert_tiles_kernel"}
+
+    # ---- end to end through the C ABI with HOST buffers (pinned): H2D + kernel + D2H every step ------------
+    e2e = None
+    if not args.no_e2e:
+        n_e2e = args.e2e_points
+        h_src = pb.VectorBuffer(pl_raw, n_e2e, "cpu", pinned=True)
+        h_src.data[: n_e2e * BYTES_IN].copy_(src.data[: n_e2e * BYTES_IN])
+        h_dst = pb.HashMapBuffer(pl_def, n_e2e, "cpu", pinned=True)
+        torch.cuda.synchronize()
+        r = range(0, n_e2e)
+        cv.convert_into_range(h_src, r, h_dst, r)  # warm-up (allocates the staging buffers)
+        e2e_steps = max(1, min(args.steps, 5))
+        t0 = time.perf_counter()
+        for _ in range(e2e_steps):
+            cv.convert_into_range(h_src, r, h_dst, r)  # returns after the D2H of the last chunk
+        dt = time.perf_counter() - t0
+        e2e = {"value": world * n_e2e * e2e_steps / dt, "unit": "points/s", "h2d_bytes_per_step": n_e2e * BYTES_IN,
+               "d2h_bytes_per_step": n_e2e * BYTES_OUT, "ms_per_step": dt / e2e_steps * 1e3, "points_per_step": n_e2e,
+               "note": "pinned host VectorBuffer -> pb200_converter_convert_into_range (HOST memspace, chunked H2D/kernel/D2H "
+                       "overlap) -> pinned host HashMapBuffer; measured on rank 0" + (" and scaled by n_gpus" if world > 1 else "")}
+        # the host result must equal the device result
+        for i in (0, len(pl_def) - 1):
+            a = h_dst.columns[i][: n_e2e * pl_def.at(i).size()]
+            b = dst.columns[i][: n_e2e * pl_def.at(i).size()].cpu()
+            assert torch.equal(a, b), f"e2e column {i} differs from the device-resident result"
+        del h_src, h_dst
+
+    # ---- CPU baseline: the oracle port on this box's host cores, bounded sample ---------------------------
+    cpu = None
+    if world == 1 and not args.no_cpu_baseline:
+        rate1, secs1 = oracle_convert_rate(2_000_000, 1)
+        sample = int(min(50_000_000, max(2_000_000, rate1 * 12)))  # ~12 s of single-thread work
+        rate, secs = oracle_convert_rate(sample, 1)
+        cores = os.cpu_count() or 1
+        mt_sample = int(min(50_000_000, max(sample, rate * cores * 0.5)))
+        rate_mt, secs_mt = oracle_convert_rate(mt_sample, cores)
+        cpu = {"value": rate, "unit": "points/s", "cores": 1, "kind": "port",
+               "sample": f"{sample} points of the C2 stream, single thread (the reference path is single-threaded), {secs:.1f} s",
+               "mt_value": rate_mt, "mt_cores": cores,
+               "mt_sample": f"{mt_sample} points, {cores} threads over disjoint point ranges, {secs_mt:.1f} s"}
+
+    out = {
+        "metric": METRIC, "value": value, "unit": "points/s", "n_gpus": world, "steps": args.steps, "warmup": max(3, args.warmup),
+        "ms_per_step": total_ms / args.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+        "dtype": "f64", "data": "synthetic",
+        "config": {"workload": ("C5: per-GPU 100M-point shard convert + fused AABB + 48 B NCCL all-reduce(min)" if world > 1 else
+                                "C2: 100M-point interleaved->columnar convert + scale/offset on 1xB200" +
+                                (" + fused AABB" if fused else "")),
+                   "points_per_gpu": n, "source": "VectorBuffer raw LAS fmt0 (20 B/pt)",
+                   "target": "HashMapBuffer LasPointFormat0 (10 columns, 35 B/pt)", "parallelism": f"point-range shards x{world}",
+                   "l2_policy": "inputs (2.0 GB) and outputs (3.5 GB) per step are far larger than the 126 MB L2"},
+        "roofline": roofline, "cpu_baseline": cpu, "e2e": e2e, "gpu_launches": int(launches),
+        "clocks": clocks.summary(),
+    }
+    print(json.dumps(out))
+    if world > 1:
+        dist.destroy_process_group()
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=20)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--points", type=int, default=POINTS_PER_GPU, help="points per GPU (default: the 100 M of C2)")
+    ap.add_argument("--e2e-points", type=int, default=POINTS_PER_GPU)
+    ap.add_argument("--fused-bounds", action="store_true", help="N=1: also fuse the AABB (always on for N>1)")
+    ap.add_argument("--no-e2e", action="store_true")
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    args = ap.parse_args()
+    if args.impl == "reference":
+        run_reference(args)
+    else:
+        run_ours(args)
+
+
+if __name__ == "__main__":
+    main()

@@ -267,6 +267,12 @@ int pb200_proj_pipeline_for_crs(const char* source_crs, const char* target_crs, 
 int pb200_reproject(pb200_ctx* ctx, const pb200_buffer_desc* src, const pb200_buffer_desc* dst_or_null,
                     const pb200_proj_op* ops, uint32_t n_ops);
 
+/* ---- synthetic inputs (bench / test tooling; SURVEY 8d splitmix64 streams, generated in HBM) ---------- */
+/* raw LAS format-0 records (20 B each) of the C2/C5 stream, points first_index .. first_index+n-1 */
+int pb200_synth_las_fmt0_records(pb200_ctx* ctx, void* device_out, uint64_t first_index, uint64_t n, uint64_t seed);
+/* packed Vec3f64 positions of the C3/C4 terrain stream */
+int pb200_synth_terrain_positions(pb200_ctx* ctx, void* device_out, uint64_t first_index, uint64_t n, uint64_t seed);
+
 #ifdef __cplusplus
 }
 #endif

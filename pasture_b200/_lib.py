@@ -98,6 +98,8 @@ SIGNATURES = {
     "pb200_compute_normals": (i32, [vp, BD, u32, vp, vp]),
     "pb200_proj_pipeline_for_crs": (i32, [C.c_char_p, C.c_char_p, C.POINTER(ProjOp), u32]),
     "pb200_reproject": (i32, [vp, BD, BD, C.POINTER(ProjOp), u32]),
+    "pb200_synth_las_fmt0_records": (i32, [vp, vp, u64, u64, u64]),
+    "pb200_synth_terrain_positions": (i32, [vp, vp, u64, u64, u64]),
 }
 
 _lib = None

@@ -181,3 +181,21 @@ def reproject_point_cloud_between(source_point_cloud, target_point_cloud, source
     p = Projection(source_crs, target_crs)
     sd, dd = source_point_cloud.desc(), target_point_cloud.desc()
     check(lib().pb200_reproject(ctx._h, C.byref(sd), C.byref(dd), p.ops, p.n_ops))
+
+
+def synth_las_fmt0_records(n, first_index=0, seed=42, device="cuda", ctx=None):
+    """C2/C5 input stream generated in HBM: VectorBuffer of raw LAS format-0 records"""
+    from .layout import PointLayout
+    ctx = ctx or get_context()
+    buf = VectorBuffer(PointLayout.las_raw(0), n, device)
+    check(lib().pb200_synth_las_fmt0_records(ctx._h, C.c_void_p(buf.data.data_ptr()), first_index, n, seed))
+    return buf
+
+
+def synth_terrain_positions(n, first_index=0, seed=42, device="cuda", ctx=None):
+    """C3/C4 input stream: HashMapBuffer with one packed Vec3f64 POSITION_3D column"""
+    from .layout import PointLayout, attributes
+    ctx = ctx or get_context()
+    buf = HashMapBuffer(PointLayout.from_attributes([attributes.POSITION_3D]), n, device)
+    check(lib().pb200_synth_terrain_positions(ctx._h, C.c_void_p(buf.columns[0].data_ptr()), first_index, n, seed))
+    return buf

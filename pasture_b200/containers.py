@@ -107,7 +107,7 @@ class VectorBuffer(_BufferBase):
         size = layout.size_of_point_entry()
         assert size > 0 and raw.size % size == 0
         b = cls(layout, raw.size // size, "cpu", pinned)
-        b.data[: raw.size] = torch.from_numpy(raw)
+        b.data[: raw.size] = torch.from_numpy(raw.copy())
         return b.to(device) if torch.device(device).type != "cpu" else b
 
     def resize(self, n):

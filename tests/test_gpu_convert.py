@@ -181,15 +181,17 @@ EDGE_F = [0.0, -0.0, 0.5, -0.5, 0.99, -0.99, 1.5, -1.5, 2.9, -2.9, 127.0, 127.9,
 
 
 def edge_values(comp, n):
-    rng = np.random.default_rng(int(comp) + 100)
+    rng = np.random.default_rng(np.dtype(comp).num + 100)
     if np.issubdtype(comp, np.floating):
         with np.errstate(over="ignore"):
             base = np.array(EDGE_F, dtype=np.float64).astype(comp)
         rnd = rng.integers(0, 256, (n - len(base), np.dtype(comp).itemsize), dtype=np.uint8).view(comp).reshape(-1)
         return np.concatenate([base, rnd])
     info = np.iinfo(comp)
-    base = np.array([0, 1, info.max, info.min, info.max - 1, info.min + 1 if info.min < 0 else 2, 127, 128, 255, 256 % (int(info.max) + 1),
-                     16777217 % (int(info.max) + 1)], dtype=np.uint64).astype(comp)
+    bits = 8 * np.dtype(comp).itemsize
+    unsigned = np.dtype(f"u{np.dtype(comp).itemsize}")
+    raw = [0, 1, int(info.max), int(info.min), int(info.max) - 1, int(info.min) + 1, 2, 127, 128, 255, 256, 16777217, -1, -2]
+    base = np.array([v % (1 << bits) for v in raw], dtype=unsigned).view(comp)
     rnd = rng.integers(info.min, info.max, n - len(base), dtype=comp, endpoint=True)
     return np.concatenate([base, rnd])
 
