@@ -186,6 +186,9 @@ def run_ours(args):
     dev = torch.device("cuda", local_rank if world > 1 else 0)
     torch.cuda.set_device(dev)
     ctx = pb.get_context(dev.index)
+    for kv in args.param:
+        k, v = kv.split("=")
+        ctx.set_param(k, int(v))
     n = args.points
     fused = world > 1 or args.fused_bounds
 
@@ -322,6 +325,7 @@ def main():
     ap.add_argument("--fused-bounds", action="store_true", help="N=1: also fuse the AABB (always on for N>1)")
     ap.add_argument("--no-e2e", action="store_true")
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--param", action="append", default=[], help="tuning knob key=value (pb200_ctx_set_param), e.g. convert.threads=512")
     args = ap.parse_args()
     if args.impl == "reference":
         run_reference(args)
