@@ -81,6 +81,7 @@ extern "C" {
     pub fn pb200_device_free(ctx: *mut pb200_ctx, p: *mut c_void) -> c_int;
     pub fn pb200_memcpy_h2d(ctx: *mut pb200_ctx, dst: *mut c_void, src: *const c_void, bytes: u64) -> c_int;
     pub fn pb200_memcpy_d2h(ctx: *mut pb200_ctx, dst: *mut c_void, src: *const c_void, bytes: u64) -> c_int;
+    pub fn pb200_memcpy_d2d(ctx: *mut pb200_ctx, dst: *mut c_void, src: *const c_void, bytes: u64) -> c_int;
     pub fn pb200_memset_device(ctx: *mut pb200_ctx, dst: *mut c_void, value: c_int, bytes: u64) -> c_int;
 
     pub fn pb200_dtype_size(dtype: u32, extra_size: u64) -> u64;

@@ -130,6 +130,7 @@ int pb200_device_alloc(pb200_ctx* ctx, uint64_t bytes, void** out);
 int pb200_device_free(pb200_ctx* ctx, void* p);
 int pb200_memcpy_h2d(pb200_ctx* ctx, void* dst_device, const void* src_host, uint64_t bytes);
 int pb200_memcpy_d2h(pb200_ctx* ctx, void* dst_host, const void* src_device, uint64_t bytes);
+int pb200_memcpy_d2d(pb200_ctx* ctx, void* dst_device, const void* src_device, uint64_t bytes);
 int pb200_memset_device(pb200_ctx* ctx, void* dst_device, int value, uint64_t bytes);
 
 /* ---- PointLayout (pasture-core/src/layout/point_layout.rs:648-997) ------------------------------ */

@@ -54,6 +54,7 @@ SIGNATURES = {
     "pb200_device_free": (i32, [vp, vp]),
     "pb200_memcpy_h2d": (i32, [vp, vp, vp, u64]),
     "pb200_memcpy_d2h": (i32, [vp, vp, vp, u64]),
+    "pb200_memcpy_d2d": (i32, [vp, vp, vp, u64]),
     "pb200_memset_device": (i32, [vp, vp, i32, u64]),
     "pb200_dtype_size": (u64, [u32, u64]),
     "pb200_dtype_min_alignment": (u64, [u32, u64]),

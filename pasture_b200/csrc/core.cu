@@ -185,6 +185,11 @@ int pb200_memcpy_d2h(pb200_ctx* ctx, void* d, const void* s, uint64_t bytes) {
     PB_CUDA(cudaStreamSynchronize(ctx->stream));
     return PB200_OK;
 }
+int pb200_memcpy_d2d(pb200_ctx* ctx, void* d, const void* s, uint64_t bytes) {
+    PB_TRY(ensure_device(ctx));
+    PB_CUDA(cudaMemcpyAsync(d, s, bytes, cudaMemcpyDeviceToDevice, ctx->stream));
+    return PB200_OK;
+}
 int pb200_memset_device(pb200_ctx* ctx, void* d, int value, uint64_t bytes) {
     PB_TRY(ensure_device(ctx));
     PB_CUDA(cudaMemsetAsync(d, value, bytes, ctx->stream));

@@ -3,17 +3,6 @@
 #include "internal.h"
 using namespace pb200;
 extern "C" {
-int pb200_voxelgrid_filter(pb200_ctx*, const pb200_buffer_desc*, double, double, double, const pb200_layout*, int32_t,
-                           int32_t, pb200_result_buffer**) {
-    return set_error(PB200_ERR_UNSUPPORTED, "pb200_voxelgrid_filter: not implemented yet");
-}
-int pb200_result_buffer_desc(const pb200_result_buffer*, pb200_buffer_desc*) {
-    return set_error(PB200_ERR_UNSUPPORTED, "not implemented yet");
-}
-int pb200_result_buffer_voxel_keys(const pb200_result_buffer*, uint64_t*) {
-    return set_error(PB200_ERR_UNSUPPORTED, "not implemented yet");
-}
-void pb200_result_buffer_destroy(pb200_result_buffer*) {}
 int pb200_knn(pb200_ctx*, const pb200_buffer_desc*, uint32_t, uint32_t*, double*) {
     return set_error(PB200_ERR_UNSUPPORTED, "pb200_knn: not implemented yet");
 }

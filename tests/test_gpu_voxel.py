@@ -1,0 +1,128 @@
+"""GPU parity of the voxel-grid filter (K7-K9) against the oracle's faithful restatement of
+pasture-algorithms/src/voxel_grid.rs (voxel ids, voxel count and order bit-exact; centroids bit-exact because
+the stable sort keeps the reference's summation order; integer reductions exact, mode ties -> smallest value)."""
+import numpy as np
+import pytest
+import torch
+
+import oracle as O
+import pasture_b200 as pb
+from pasture_b200 import HashMapBuffer, VectorBuffer
+from pasture_b200.algorithms import voxelgrid_filter
+from tests import util
+from tests.test_oracle_algorithms import COMPLETE, setup_point_cloud
+
+pytestmark = pytest.mark.gpu
+
+
+def to_product(ob, attrs, packed, device="cuda"):
+    _, pl = util.layouts(attrs, packed)
+    return util.to_pb(ob, pl, device), pl
+
+
+@pytest.mark.parametrize("out_type", [HashMapBuffer, VectorBuffer])
+@pytest.mark.parametrize("device", ["cuda", "cpu"])
+def test_reference_voxel_test(out_type, device):  # voxel_grid.rs:906-938
+    ol, ob = setup_point_cloud()
+    pbuf, pl = to_product(ob, COMPLETE, 1, device)
+    out, keys = voxelgrid_filter(pbuf, 1.0, 1.0, 1.0, out_buffer_type=out_type, return_keys=True)
+    assert out.len() == 1000
+    p = out.view_attribute("Position3D")[1]
+    assert 0.59 < p[0] < 0.61 and 0.59 < p[1] < 0.61 and 1.59 < p[2] < 1.61
+    assert out.view_attribute("Intensity")[1] == 4
+    assert out.view_attribute("ReturnNumber")[1] == 42
+    assert out.view_attribute("ClassificationFlags")[1] == 133
+    oout, okeys = O.voxelgrid_filter(ob, (1.0, 1.0, 1.0), ol, columnar=True)
+    assert np.array_equal(keys, okeys)
+    util.assert_buffers_match(oout, out)
+
+
+@pytest.mark.parametrize("seed,n,leaf", [(1, 5000, (0.7, 0.9, 1.1)), (2, 20000, (0.25, 0.25, 0.25)), (3, 777, (5.0, 0.01, 100.0)),
+                                          (4, 1, (1.0, 1.0, 1.0)), (5, 3000, (100.0, 100.0, 100.0))])
+@pytest.mark.parametrize("src_col", [False, True])
+def test_random_clouds_match_faithful_oracle(seed, n, leaf, src_col):
+    rng = np.random.default_rng(seed)
+    attrs = [("Position3D", O.VEC3F64), ("Intensity", O.U16), ("Classification", O.U8), ("GpsTime", O.F64),
+             ("ColorRGB", O.VEC3U16), ("ScanAngleRank", O.I8), ("ScanAngle", O.I16), ("PointSourceID", O.U16),
+             ("PointID", O.U64), ("Normal", O.VEC3F32), ("EdgeOfFlightLine", O.U8), ("ClassificationFlags", O.U8)]
+    ol = O.OLayout.from_attributes(attrs)
+    ob = O.OBuffer(ol, n, src_col)
+    ob.set_attribute("Position3D", rng.random((n, 3)) * [20, 10, 3] - [5, 5, 1])
+    ob.set_attribute("Intensity", rng.integers(0, 65536, n))
+    ob.set_attribute("Classification", rng.integers(0, 4, n))
+    ob.set_attribute("GpsTime", rng.random(n) * 100 - 20)
+    ob.set_attribute("ColorRGB", rng.integers(0, 65536, (n, 3)))
+    ob.set_attribute("ScanAngleRank", rng.integers(-3, 3, n))
+    ob.set_attribute("ScanAngle", rng.integers(-300, 300, n))
+    ob.set_attribute("PointSourceID", rng.integers(0, 3, n))
+    ob.set_attribute("PointID", rng.integers(0, 2**62, n))
+    ob.set_attribute("Normal", rng.random((n, 3)).astype(np.float32) - 0.5)
+    ob.set_attribute("EdgeOfFlightLine", rng.integers(0, 2, n))
+    ob.set_attribute("ClassificationFlags", rng.integers(0, 256, n))
+    pbuf, pl = to_product(ob, attrs, 0)
+    oout, okeys = O.voxelgrid_filter(ob, leaf, ol, columnar=True, use_sort=False)
+    out, keys = voxelgrid_filter(pbuf, *leaf, return_keys=True)
+    assert out.len() == oout.len
+    assert np.array_equal(keys, okeys)
+    util.assert_buffers_match(oout, out)
+
+
+def test_subset_target_layout_and_errors():
+    ol, ob = setup_point_cloud(3)
+    pbuf, pl = to_product(ob, COMPLETE, 1)
+    _, sub = util.layouts([("Intensity", O.U16), ("Position3D", O.VEC3F64)])
+    osub = O.OLayout.from_attributes([("Intensity", O.U16), ("Position3D", O.VEC3F64)])
+    out = voxelgrid_filter(pbuf, 2.0, 2.0, 2.0, filtered_layout=sub)
+    oout, _ = O.voxelgrid_filter(ob, (2.0, 2.0, 2.0), osub)
+    util.assert_buffers_match(oout, out)
+    _, bad = util.layouts([("Position3D", O.VEC3F64), ("WaveformPacketSize", O.U32)])
+    with pytest.raises(pb.PastureB200Error) as e:  # voxel_grid.rs:452-459
+        voxelgrid_filter(pbuf, 1.0, 1.0, 1.0, filtered_layout=bad)
+    assert e.value.code == -10
+    _, bad = util.layouts([("Position3D", O.VEC3F64), ("Custom", O.F32)])
+    with pytest.raises(pb.PastureB200Error):  # :682-687
+        voxelgrid_filter(pbuf, 1.0, 1.0, 1.0, filtered_layout=bad)
+    _, nopos = util.layouts([("Position3D", O.VEC3F32)])
+    with pytest.raises(pb.PastureB200Error) as e:  # :116-121
+        voxelgrid_filter(HashMapBuffer(nopos, 4, "cuda"), 1.0, 1.0, 1.0)
+    assert e.value.code == -1
+    with pytest.raises(pb.PastureB200Error):  # empty buffer: calculate_bounds(..).unwrap()
+        voxelgrid_filter(HashMapBuffer(pl, 0, "cuda"), 1.0, 1.0, 1.0)
+
+
+def test_c3_shape_against_sort_oracle():
+    """C3 stream (terrain positions, 0.1 m leaf) at a size the sort-based oracle restatement finishes in seconds"""
+    n = 300000
+    pts = O.gen_terrain_positions(0, n)
+    ol = O.OLayout.from_attributes([("Position3D", O.VEC3F64)])
+    ob = O.OBuffer(ol, n, True)
+    ob.set_attribute("Position3D", pts)
+    src = pb.algorithms.synth_terrain_positions(n)
+    assert np.array_equal(src.view_attribute("Position3D"), pts)  # device generator == oracle generator, bit for bit
+    oout, okeys = O.voxelgrid_filter(ob, (0.1, 0.1, 0.1), ol, columnar=True, use_sort=True)
+    out, keys = voxelgrid_filter(src, 0.1, 0.1, 0.1, return_keys=True)
+    assert out.len() == oout.len and np.array_equal(keys, okeys)
+    util.assert_buffers_match(oout, out)
+
+
+def test_full_size_properties():
+    """100 M-point C3 cloud: size-independent properties (keys strictly increasing, every point accounted for,
+    centroids inside their voxel's marker neighbourhood, idempotent count)"""
+    n = 100_000_000 if torch.cuda.get_device_properties(0).total_memory > 100e9 else 5_000_000
+    src = pb.algorithms.synth_terrain_positions(n)
+    out, keys = voxelgrid_filter(src, 0.1, 0.1, 0.1, return_keys=True)
+    v = out.len()
+    assert 0 < v <= n
+    k = keys.astype(np.int64)
+    packed = (k[:, 0] << 42) | (k[:, 1] << 21) | k[:, 2]
+    assert np.all(np.diff(packed) > 0)  # lexicographic, unique
+    c = out.view_attribute("Position3D")
+    aabb = pb.algorithms.calculate_bounds(src)
+    mn, mx = np.array(aabb.min()), np.array(aabb.max())
+    assert np.all(c >= mn) and np.all(c <= mx)
+    # nearest-marker rule: centroid index is within one cell of its voxel index
+    approx = (c - mn) / 0.1
+    assert np.all(np.abs(approx - keys.astype(np.float64)) < 1.6)
+    # filtering the centroids again with the same grid origin keeps at most v voxels
+    out2 = voxelgrid_filter(out, 0.1, 0.1, 0.1)
+    assert out2.len() <= v
