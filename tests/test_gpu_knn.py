@@ -1,0 +1,182 @@
+"""GPU parity of kNN / radius search over the LBVH (K10-K12), normal estimation (K13) and reprojection (K14).
+
+kNN: neighbour indices AND squared distances bit-exact vs the brute-force oracle, ordered by (d2, index)
+(tie order of the reference's kd-tree crate is unpinned).  Normals: bit-exact given identical
+neighbour order (no FMA); curvature within 1e-9 relative (device atan2/cos/sin vs glibc).  Reprojection: the 4
+reference KATs at the reference's tolerance (1e-4 m), and 1e-6 m vs the oracle elsewhere."""
+import numpy as np
+import pytest
+import torch
+
+import oracle as O
+import pasture_b200 as pb
+from pasture_b200 import HashMapBuffer, VectorBuffer, attributes as A
+from pasture_b200.algorithms import (compute_normals, knn, radius_search, reproject_point_cloud_between,
+                                     reproject_point_cloud_within)
+from tests import util
+
+pytestmark = pytest.mark.gpu
+
+
+def cloud(pts, columnar=True, device="cuda", extra=False):
+    attrs = [("Position3D", O.VEC3F64)] + ([("Intensity", O.U16)] if extra else [])
+    ol, pl = util.layouts(attrs)
+    ob = O.OBuffer(ol, len(pts), columnar)
+    if len(pts):
+        ob.set_attribute("Position3D", pts)
+    return util.to_pb(ob, pl, device)
+
+
+def clouds():
+    rng = np.random.default_rng(7)
+    yield "uniform", rng.random((4000, 3)) * [10, 10, 2]
+    yield "terrain", O.gen_terrain_positions(0, 6000)
+    yield "clustered", np.concatenate([rng.normal(c, 0.05, (700, 3)) for c in ([0, 0, 0], [5, 5, 5], [5, 0, 1], [-3, 2, 0])])
+    g = np.stack(np.meshgrid(np.arange(12.0), np.arange(12.0), np.arange(6.0)), -1).reshape(-1, 3)
+    yield "lattice_with_ties", g  # many exactly equal distances
+    yield "duplicates", np.repeat(rng.random((300, 3)), 4, axis=0)
+    yield "line", np.stack([np.linspace(0, 1, 1000), np.zeros(1000), np.zeros(1000)], 1)
+
+
+@pytest.mark.parametrize("name,pts", list(clouds()))
+@pytest.mark.parametrize("k", [1, 3, 16])
+def test_knn_matches_bruteforce(name, pts, k):
+    oidx, od2 = O.knn_bruteforce(pts, pts, k)
+    idx, d2 = knn(cloud(pts), k)
+    torch.cuda.synchronize()
+    idx = idx.cpu().numpy().view(np.uint32)
+    d2 = d2.cpu().numpy()
+    assert np.array_equal(d2, od2), name
+    assert np.array_equal(idx, oidx), name
+
+
+@pytest.mark.parametrize("columnar,device", [(True, "cuda"), (False, "cuda"), (True, "cpu"), (False, "cpu")])
+def test_knn_buffer_kinds_and_small_inputs(columnar, device):
+    rng = np.random.default_rng(3)
+    pts = rng.random((1500, 3))
+    oidx, od2 = O.knn_bruteforce(pts, pts, 8)
+    idx, d2 = knn(cloud(pts, columnar, device, extra=True), 8)
+    assert np.array_equal(idx.cpu().numpy().view(np.uint32), oidx) and np.array_equal(d2.cpu().numpy(), od2)
+    for n in (1, 2, 5):  # fewer points than k: the tail is 0xFFFFFFFF / inf
+        p = rng.random((n, 3))
+        idx, d2 = knn(cloud(p, columnar, device), 8)
+        oidx, od2 = O.knn_bruteforce(p, p, 8)
+        assert np.array_equal(idx.cpu().numpy().view(np.uint32), oidx) and np.array_equal(d2.cpu().numpy(), od2)
+
+
+def test_radius_search():
+    rng = np.random.default_rng(11)
+    pts = rng.random((3000, 3))
+    r, m = 0.08, 32
+    idx, cnt = radius_search(cloud(pts), r, m)
+    idx = idx.cpu().numpy().view(np.uint32)
+    cnt = cnt.cpu().numpy()
+    d2 = ((pts[:, None, :] - pts[None, :, :]) ** 2)
+    d2 = (d2[..., 0] + d2[..., 1]) + d2[..., 2]
+    for i in range(0, 3000, 37):
+        inside = np.nonzero(d2[i] <= r * r)[0]
+        order = inside[np.lexsort((inside, d2[i][inside]))][:m]
+        assert cnt[i] == len(order)
+        assert np.array_equal(idx[i, : cnt[i]], order)
+
+
+KAT = np.array([[1.0, 0.0, 0.0], [0.0, 1.0, 0.0], [1.0, 1.0, 0.0], [-1.0, 0.0, 0.0]])
+
+
+def test_compute_normal_kat():  # normal_estimation.rs:580-610
+    normals, curv = compute_normals(cloud(KAT, False, extra=True), 3)
+    normals, curv = normals.cpu().numpy(), curv.cpu().numpy()
+    assert np.all(normals[:, 0] == 0) and np.all(normals[:, 1] == 0) and np.all(normals[:, 2] != 0)
+    assert np.all(curv == 0)
+    on, oc = O.compute_normals(KAT, 3)
+    assert np.array_equal(normals, on) and np.array_equal(curv, oc)
+
+
+def test_compute_normal_panics():  # :612-698
+    with pytest.raises(pb.PastureB200Error) as e:
+        compute_normals(cloud(KAT[:1]), 3)
+    assert e.value.code == -9
+    with pytest.raises(pb.PastureB200Error):
+        compute_normals(cloud(KAT[:2]), 3)
+    for k in (1, 2):
+        with pytest.raises(pb.PastureB200Error) as e:
+            compute_normals(cloud(KAT), k)
+        assert e.value.code == -8
+
+
+@pytest.mark.parametrize("name,pts", [c for c in clouds() if c[0] in ("uniform", "terrain", "clustered")])
+@pytest.mark.parametrize("k", [3, 16])
+def test_normals_match_oracle(name, pts, k):
+    pts = pts[:2500]
+    on, oc = O.compute_normals(pts, k)
+    normals, curv = compute_normals(cloud(pts), k)
+    normals, curv = normals.cpu().numpy(), curv.cpu().numpy()
+    assert np.array_equal(normals, on), name           # bit-exact: same neighbour order, no FMA
+    # curvature = |lambda0 * maxabs(C) / trace(C)| goes through atan2/cos/sin: 1e-9 relative (device libm vs glibc);
+    # for rank-deficient neighbourhoods (k = 3, planar patches) lambda0 is pure cancellation noise ~1e-16 * trace,
+    # hence the absolute floor
+    assert np.allclose(curv, oc, rtol=1e-9, atol=1e-12 * max(1.0, float(np.abs(pts).max()) ** 2)), (name, np.abs(curv - oc).max())
+
+
+def test_normals_c4_shape_properties():
+    """C4 stream at 2 M points: normals of the smooth terrain point mostly upwards, curvature finite and >= 0"""
+    n = 2_000_000
+    src = pb.algorithms.synth_terrain_positions(n)
+    normals, curv = compute_normals(src, 16)
+    torch.cuda.synchronize()
+    assert bool(torch.isfinite(normals).all()) and bool(torch.isfinite(curv).all()) and bool((curv >= 0).all())
+    nz = normals[:, 2].abs() / normals.norm(dim=1).clamp_min(1e-300)
+    assert float((nz > 0.5).double().mean()) > 0.9
+    # spot-check 64 points against the brute-force oracle on the same cloud
+    pts = src.view_attribute(A.POSITION_3D)
+    sel = np.linspace(0, n - 1, 64).astype(np.int64)
+    oidx, od2 = O.knn_bruteforce(pts, pts[sel], 16)
+    for row, i in enumerate(sel):
+        nrm = np.zeros(3)
+        c = np.zeros(1)
+        O.lib().po_normal_estimation(O._ptr(np.ascontiguousarray(pts[oidx[row]])), 16, O._ptr(nrm), O._ptr(c))
+        assert np.array_equal(normals[i].cpu().numpy(), nrm)
+        assert np.isclose(float(curv[i]), c[0], rtol=1e-9, atol=1e-12 * 500.0 ** 2)
+
+
+KATS_IN = np.array([[1.0, 22.0, 0.0], [12.0, 23.0, 0.0], [10.0, 8.0, 2.0], [10.0, 0.0, 1.0]])
+KATS_OUT = np.array([[12185139.590523569, 7420953.944297638, 0.0], [11104667.534080556, 7617693.973680517, 0.0],
+                     [11055663.927418157, 5832081.512011217, 2.0], [10807262.110686881, 4909128.916889962, 1.0]])
+
+
+@pytest.mark.parametrize("columnar,device", [(False, "cuda"), (True, "cuda"), (False, "cpu")])
+def test_reproject_epsg4326_epsg3309_within(columnar, device):  # reprojection.rs:250-291
+    buf = cloud(KATS_IN, columnar, device, extra=True)
+    reproject_point_cloud_within(buf, "EPSG:4326", "EPSG:3309")
+    torch.cuda.synchronize()
+    out = buf.view_attribute(A.POSITION_3D)
+    assert np.all(np.abs(out - KATS_OUT) < 1e-4), out - KATS_OUT
+    assert np.array_equal(buf.view_attribute(A.INTENSITY), np.zeros(4, np.uint16))
+
+
+def test_reproject_between_and_errors():  # reprojection.rs:292-367
+    src = cloud(KATS_IN, False, extra=True)
+    dst = cloud(np.zeros((4, 3)), True, extra=True)
+    reproject_point_cloud_between(src, dst, "EPSG:4326", "EPSG:3309")
+    torch.cuda.synchronize()
+    assert np.all(np.abs(dst.view_attribute(A.POSITION_3D) - KATS_OUT) < 1e-4)
+    assert np.array_equal(src.view_attribute(A.POSITION_3D), KATS_IN)
+    with pytest.raises(pb.PastureB200Error) as e:  # "The point clouds don't have the same size!"
+        reproject_point_cloud_between(src, cloud(np.zeros((2, 3))), "EPSG:4326", "EPSG:3309")
+    assert e.value.code == -5
+    with pytest.raises(pb.PastureB200Error) as e:
+        reproject_point_cloud_within(src, "EPSG:4326", "EPSG:25832")
+    assert e.value.code == -10
+
+
+def test_reproject_matches_oracle_on_random_points():
+    rng = np.random.default_rng(5)
+    pts = np.stack([rng.random(20000) * 60 - 10, rng.random(20000) * 80 - 160, rng.random(20000) * 3000], 1)
+    ops, n = O.pipeline_epsg4326_to_3309()
+    expect = O.reproject(ops, n, pts)
+    buf = cloud(pts)
+    reproject_point_cloud_within(buf, "EPSG:4326", "EPSG:3309")
+    torch.cuda.synchronize()
+    got = buf.view_attribute(A.POSITION_3D)
+    assert np.all(np.abs(got - expect) < 1e-6), np.abs(got - expect).max()
+    assert np.array_equal(got[:, 2], pts[:, 2])  # z passes through
