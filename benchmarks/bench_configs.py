@@ -1,0 +1,101 @@
+#!/usr/bin/env python
+"""Informational timings of the non-headline configs of BASELINE.json (C3: AABB + voxel-grid downsample, C4: kNN
+normals, plus the stand-alone reductions and the other conversion directions). Prints one JSON object per line;
+the headline metric lives in bench.py."""
+import argparse
+import json
+import os
+import sys
+import time
+
+import torch
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+sys.path.insert(0, ROOT)
+import pasture_b200 as pb  # noqa: E402
+from pasture_b200 import algorithms as alg  # noqa: E402
+
+
+def timed(fn, reps=3, warm=1):
+    for _ in range(warm):
+        fn()
+    torch.cuda.synchronize()
+    best = None
+    for _ in range(reps):
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        fn()
+        e1.record()
+        torch.cuda.synchronize()
+        ms = e0.elapsed_time(e1)
+        best = ms if best is None or ms < best else best
+    return best
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--points", type=int, default=100_000_000)
+    ap.add_argument("--knn-points", type=int, default=20_000_000)
+    ap.add_argument("--skip", default="")
+    args = ap.parse_args()
+    n = args.points
+    peak = 6536.4
+    try:
+        peak = json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json")))["hbm_gbs"]
+    except Exception:
+        pass
+
+    def emit(name, ms, npts, bytes_per_pt, extra=None):
+        d = {"config": name, "points": npts, "ms": ms, "points_per_s": npts / (ms * 1e-3),
+             "algorithmic_bytes_per_point": bytes_per_pt, "achieved_GBps": bytes_per_pt * npts / (ms * 1e-3) / 1e9 if bytes_per_pt else None,
+             "frac_of_measured_peak": (bytes_per_pt * npts / (ms * 1e-3) / 1e9 / peak) if bytes_per_pt else None}
+        if extra:
+            d.update(extra)
+        print(json.dumps(d), flush=True)
+
+    if "aabb" not in args.skip:
+        src = alg.synth_terrain_positions(n)
+        ms = timed(lambda: alg.calculate_bounds(src))
+        emit("AABB of packed Vec3f64 column (calculate_bounds, incl. the 48 B readback)", ms, n, 24)
+        del src
+    if "c3" not in args.skip:
+        src = alg.synth_terrain_positions(n)
+        t0 = time.perf_counter()
+        out = alg.voxelgrid_filter(src, 0.1, 0.1, 0.1)
+        torch.cuda.synchronize()
+        first = (time.perf_counter() - t0) * 1e3
+        ms = timed(lambda: alg.voxelgrid_filter(src, 0.1, 0.1, 0.1), reps=2, warm=0)
+        emit("C3: AABB + voxel keys + radix sort + per-voxel centroid, leaf 0.1 m (wall-clock incl. allocations)", ms, n, 232,
+             {"voxels": out.len(), "first_call_ms": first})
+        del src, out
+    if "soa2aos" not in args.skip:
+        raw, tgt = pb.PointLayout.las_raw(0), pb.PointLayout.las_default(0)
+        src = alg.synth_las_fmt0_records(n)
+        col = pb.HashMapBuffer(tgt, n, "cuda")
+        cv = pb.get_default_las_converter(raw, tgt, (0.001,) * 3, (500000.0, 5400000.0, 100.0))
+        cv.convert_into(src, col)
+        del src
+        aos = pb.VectorBuffer(tgt, n, "cuda")
+        ident = pb.BufferLayoutConverter.for_layouts(tgt, tgt)
+        ms = timed(lambda: ident.convert_into(col, aos))
+        emit("columnar -> interleaved (LasPointFormat0 35 B, identity mappings)", ms, n, 70)
+        # write direction (C1 on the GPU): 35 B default layout -> 20 B raw records, (p-o)/s truncation
+        back = pb.VectorBuffer(raw, n, "cuda")
+        wr = pb.BufferLayoutConverter.for_layouts_with_default(tgt, raw)
+        wr.set_custom_mapping_with_transformation(pb.attributes.POSITION_3D, pb.ATTRIBUTE_LOCAL_LAS_POSITION,
+                                                  pb.InvScaleOffset(0.001, (500000.0, 5400000.0, 100.0)), True)
+        ms = timed(lambda: wr.convert_into(aos, back))
+        emit("C1 on GPU: interleaved LasPointFormat0 (35 B) -> raw LAS fmt0 (20 B), (p-o)/s truncating", ms, n, 55)
+        del col, aos, back
+    if "c4" not in args.skip:
+        m = args.knn_points
+        src = alg.synth_terrain_positions(m)
+        t0 = time.perf_counter()
+        normals, curv = alg.compute_normals(src, 16)
+        torch.cuda.synchronize()
+        ms = (time.perf_counter() - t0) * 1e3
+        emit("C4: LBVH build + kNN (k=16) + normals/curvature (wall-clock, single call)", ms, m, 56)
+
+
+if __name__ == "__main__":
+    main()

@@ -24,7 +24,8 @@ struct pb200_result_buffer {
     uint64_t len = 0;
     void* aos = nullptr;
     std::vector<void*> columns;
-    std::vector<uint64_t> keys;  // 3 per voxel
+    void* d_packed_keys = nullptr;  // device, one packed u64 per voxel (unpacked on demand)
+    unsigned bits_y = 0, bits_z = 0;
 };
 
 namespace pb200 {
@@ -376,7 +377,7 @@ int pb200_voxelgrid_filter(pb200_ctx* ctx, const pb200_buffer_desc* src, double 
     const uint64_t V = (uint64_t)last[0] + last[1];
     DeviceBuf d_starts, d_vkeys;
     PB_CUDA(d_starts.alloc((V + 1) * 4));
-    PB_CUDA(d_vkeys.alloc(V * 8));
+    PB_CUDA(d_vkeys.alloc(V * 8 + 8));
     segment_starts_kernel<<<blocks, 256, 0, st>>>((const uint32_t*)d_flags.p, (const uint32_t*)d_excl.p, n, (uint32_t*)d_starts.p,
                                                   (const unsigned long long*)d_keys2.p, (unsigned long long*)d_vkeys.p);
     g_launches++;
@@ -393,6 +394,7 @@ int pb200_voxelgrid_filter(pb200_ctx* ctx, const pb200_buffer_desc* src, double 
     std::vector<void*> d_out(dst_layout->attrs.size(), nullptr);
     auto fail = [&](int rc) {
         for (void* p : d_out) if (p) cudaFree(p);
+        if (res->d_packed_keys) cudaFree(res->d_packed_keys);
         delete res;
         return rc;
     };
@@ -416,20 +418,12 @@ int pb200_voxelgrid_filter(pb200_ctx* ctx, const pb200_buffer_desc* src, double 
         cudaError_t e = cudaGetLastError();
         if (e != cudaSuccess) return fail(cuda_error(e, "voxel reduce"));
     }
-    // voxel keys for the caller (unpacked to ix,iy,iz)
-    std::vector<unsigned long long> packed(V);
-    if (V) {
-        cudaError_t e = cudaMemcpyAsync(packed.data(), d_vkeys.p, V * 8, cudaMemcpyDeviceToHost, st);
-        if (e != cudaSuccess) return fail(cuda_error(e, "D2H voxel keys"));
-    }
-    cudaStreamSynchronize(st);
-    res->keys.resize(3 * V);
-    for (uint64_t v = 0; v < V; ++v) {
-        const unsigned long long k = packed[v];
-        res->keys[3 * v + 2] = k & ((1ull << bits_z) - 1);
-        res->keys[3 * v + 1] = (k >> bits_z) & ((1ull << bits_y) - 1);
-        res->keys[3 * v + 0] = k >> (bits_z + bits_y);
-    }
+    // packed voxel keys stay on the device; pb200_result_buffer_voxel_keys unpacks them on demand
+    res->d_packed_keys = d_vkeys.p;
+    d_vkeys.p = nullptr;
+    res->bits_y = bits_y;
+    res->bits_z = bits_z;
+    cudaStreamSynchronize(st);  // temporaries (sorted keys, indices, staged inputs) are released on return
     // ---- hand the result over in the requested memory layout / space -------------------------------------------
     pb200_buffer_desc stage;
     stage.layout = dst_layout;
@@ -493,13 +487,24 @@ int pb200_result_buffer_desc(const pb200_result_buffer* r, pb200_buffer_desc* ou
 
 int pb200_result_buffer_voxel_keys(const pb200_result_buffer* r, uint64_t* keys_out) {
     if (!r || !keys_out) return set_error(PB200_ERR_INVALID, "null argument");
-    if (!r->keys.empty()) memcpy(keys_out, r->keys.data(), r->keys.size() * sizeof(uint64_t));
+    if (r->len == 0) return PB200_OK;
+    PB_TRY(ensure_device(r->ctx));
+    std::vector<unsigned long long> packed(r->len);
+    PB_CUDA(cudaMemcpyAsync(packed.data(), r->d_packed_keys, r->len * 8, cudaMemcpyDeviceToHost, r->ctx->stream));
+    PB_CUDA(cudaStreamSynchronize(r->ctx->stream));
+    for (uint64_t v = 0; v < r->len; ++v) {
+        const unsigned long long k = packed[v];
+        keys_out[3 * v + 2] = k & ((1ull << r->bits_z) - 1);
+        keys_out[3 * v + 1] = (k >> r->bits_z) & ((1ull << r->bits_y) - 1);
+        keys_out[3 * v + 0] = k >> (r->bits_z + r->bits_y);
+    }
     return PB200_OK;
 }
 
 void pb200_result_buffer_destroy(pb200_result_buffer* r) {
     if (!r) return;
     if (r->ctx) cudaSetDevice(r->ctx->device);
+    if (r->d_packed_keys) cudaFree(r->d_packed_keys);
     if (r->memspace == PB200_DEVICE) {
         if (r->aos) cudaFree(r->aos);
         for (void* p : r->columns) if (p) cudaFree(p);
