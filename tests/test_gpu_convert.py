@@ -439,3 +439,30 @@ def test_transform_attribute_and_converting_view(ctx):
         assert np.array_equal(v, osrc.attribute("Intensity").astype(np.float64))
         with pytest.raises(pb.PastureB200Error):
             pb.view_attribute_with_conversion(psrc, A.INTENSITY.with_custom_datatype(DT.Vec3f64))
+
+
+def test_large_range_matches_direct_kernel_and_torch(ctx):
+    """6 M points (many tiles per CTA): tile pipeline == direct kernel == a torch recomputation of the positions"""
+    n = 6_000_011
+    pl, plt = pb.PointLayout.las_raw(0), pb.PointLayout.las_default(0)
+    src = pb.algorithms.synth_las_fmt0_records(n)
+    scale, offset = (0.001, 0.001, 0.001), (500000.0, 5400000.0, 100.0)
+    cv = pb.get_default_las_converter(pl, plt, scale, offset)
+    a = HashMapBuffer(plt, n, "cuda")
+    bounds = cv.convert_into_range_with_bounds(src, range(0, n), a, range(0, n))
+    a2 = HashMapBuffer(plt, n, "cuda")
+    cv.convert_into(src, a2)                                                    
+    cv.convert_into(src, a2)                                                    
+    ctx.set_param("convert.force_direct", 1)
+    try:
+        b = cv.convert(src, HashMapBuffer)
+    finally:
+        ctx.set_param("convert.force_direct", 0)
+    torch.cuda.synchronize()
+    for i in range(len(plt)):
+        assert torch.equal(a.columns[i], b.columns[i]) and torch.equal(a2.columns[i], b.columns[i]), plt.at(i)
+    xyz = src.data[: 20 * n].view(n, 20)[:, :12].contiguous().view(torch.int32).view(n, 3)
+    pos = xyz.double() * 0.001 + torch.tensor(offset, dtype=torch.float64, device="cuda")  # mul then add: two roundings
+    got = a.columns[0][: 24 * n].view(torch.float64).view(n, 3)
+    assert torch.equal(got, pos)
+    assert list(bounds[0]) == pos.min(0).values.tolist() and list(bounds[1]) == pos.max(0).values.tolist()
