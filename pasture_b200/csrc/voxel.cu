@@ -182,6 +182,72 @@ __global__ void __launch_bounds__(128) voxel_reduce_kernel(ReduceArgs a) {
     }
 }
 
+// ---- sort-based mode for crowded voxels -------------------------------------------------------------------------
+// The per-thread mode above is O(points-in-voxel^2): fine for the usual handful of points per voxel, hopeless for a
+// voxel that swallows a large part of the cloud.  When the most crowded voxel holds more than MODE_THREAD_LIMIT points
+// the mode attributes switch to: composite key (voxel id << 16 | biased value) -> radix sort -> run lengths ->
+// one 64-bit atomicMax per run on (length << 16 | 65535 - biased value): the longest run wins, ties go to the smallest
+// value (the same rule as the per-thread path).
+constexpr uint32_t MODE_THREAD_LIMIT = 64;
+
+__global__ void __launch_bounds__(256) max_occupancy_kernel(const uint32_t* __restrict__ starts, unsigned long long n_voxels,
+                                                            uint32_t* __restrict__ out) {
+    uint32_t m = 0;
+    const unsigned long long step = (unsigned long long)gridDim.x * blockDim.x;
+    for (unsigned long long v = (unsigned long long)blockIdx.x * blockDim.x + threadIdx.x; v < n_voxels; v += step) {
+        const uint32_t c = starts[v + 1] - starts[v];
+        m = c > m ? c : m;
+    }
+    for (int o = 16; o > 0; o >>= 1) { const uint32_t x = __shfl_xor_sync(0xffffffffu, m, o); m = x > m ? x : m; }
+    if ((threadIdx.x & 31) == 0 && m) atomicMax(out, m);
+}
+
+template <class S>
+__global__ void __launch_bounds__(256) mode_keys_kernel(const uint32_t* __restrict__ flags, const uint32_t* __restrict__ excl,
+                                                        const uint32_t* __restrict__ sorted_idx, unsigned long long n,
+                                                        const uint8_t* __restrict__ src, unsigned long long stride, int aligned,
+                                                        unsigned long long* __restrict__ keys) {
+    const unsigned long long step = (unsigned long long)gridDim.x * blockDim.x;
+    for (unsigned long long i = (unsigned long long)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += step) {
+        const unsigned long long voxel = (unsigned long long)excl[i] + flags[i] - 1ull;
+        const long long val = (long long)ld_attr<S>(src + (unsigned long long)sorted_idx[i] * stride, aligned != 0);
+        constexpr long long bias = (S(-1) < S(0)) ? 32768 : 0;  // keeps signed values ordered as unsigned 16-bit fields
+        keys[i] = (voxel << 16) | (unsigned long long)((val + bias) & 0xFFFF);
+    }
+}
+
+__global__ void __launch_bounds__(256) run_heads_kernel(const unsigned long long* __restrict__ keys, unsigned long long n,
+                                                        uint32_t* __restrict__ head_idx) {
+    const unsigned long long step = (unsigned long long)gridDim.x * blockDim.x;
+    for (unsigned long long i = (unsigned long long)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += step)
+        head_idx[i] = (i == 0 || keys[i] != keys[i - 1]) ? (uint32_t)i : 0u;
+}
+
+__global__ void __launch_bounds__(256) run_vote_kernel(const unsigned long long* __restrict__ keys, const uint32_t* __restrict__ head_of,
+                                                       unsigned long long n, unsigned long long* __restrict__ best) {
+    const unsigned long long step = (unsigned long long)gridDim.x * blockDim.x;
+    for (unsigned long long i = (unsigned long long)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += step) {
+        if (i + 1 < n && keys[i + 1] == keys[i]) continue;  // only the last element of a run votes
+        const unsigned long long len = i - head_of[i] + 1ull;
+        const unsigned long long voxel = keys[i] >> 16, biased = keys[i] & 0xFFFFull;
+        atomicMax(&best[voxel], (len << 16) | (65535ull - biased));
+    }
+}
+
+__global__ void __launch_bounds__(256) mode_decode_kernel(const unsigned long long* __restrict__ best, unsigned long long n_voxels,
+                                                          uint8_t* __restrict__ dst, uint32_t dst_size, int as_bool, long long bias) {
+    const unsigned long long step = (unsigned long long)gridDim.x * blockDim.x;
+    for (unsigned long long v = (unsigned long long)blockIdx.x * blockDim.x + threadIdx.x; v < n_voxels; v += step) {
+        const long long val = (long long)(65535ull - (best[v] & 0xFFFFull)) - bias;
+        if (as_bool) dst[v] = val != 0 ? 1 : 0;
+        else memcpy(dst + v * dst_size, &val, dst_size);
+    }
+}
+
+struct MaxU32 {
+    __device__ __forceinline__ uint32_t operator()(uint32_t a, uint32_t b) const { return a > b ? a : b; }
+};
+
 struct Rule { const char* name; uint32_t dtype; ReduceKind kind; };
 static const Rule RULES[] = {  // voxel_grid.rs:461-679, source order
     {"Position3D", PB200_VEC3F64, R_MEAN_VEC_F64}, {"Intensity", PB200_U16, R_MEAN_U16},
@@ -384,6 +450,30 @@ int pb200_voxelgrid_filter(pb200_ctx* ctx, const pb200_buffer_desc* src, double 
     const uint32_t n32 = (uint32_t)n;
     PB_CUDA(cudaMemcpyAsync((uint32_t*)d_starts.p + V, &n32, 4, cudaMemcpyHostToDevice, st));
 
+    // the most crowded voxel decides how the mode attributes are reduced
+    bool any_mode = false;
+    for (const Rule* r : rules) any_mode = any_mode || r->kind == R_MODE || r->kind == R_MODE_BOOL;
+    uint32_t max_occ = 0;
+    DeviceBuf d_mode_keys, d_mode_keys2, d_head, d_head2, d_best, d_mode_tmp;
+    size_t mode_tmp_bytes = 0;
+    if (any_mode) {
+        PB_CUDA(cudaMemsetAsync(d_tmp.p, 0, 4, st));  // d_tmp[0..3] doubles as the max counter (the sort is done)
+        max_occupancy_kernel<<<blocks, 256, 0, st>>>((const uint32_t*)d_starts.p, V, (uint32_t*)d_tmp.p);
+        g_launches++;
+        PB_CUDA(cudaMemcpyAsync(&max_occ, d_tmp.p, 4, cudaMemcpyDeviceToHost, st));
+        PB_CUDA(cudaStreamSynchronize(st));
+        if (max_occ > MODE_THREAD_LIMIT) {
+            PB_CUDA(d_mode_keys.alloc(n * 8)); PB_CUDA(d_mode_keys2.alloc(n * 8));
+            PB_CUDA(d_head.alloc(n * 4)); PB_CUDA(d_head2.alloc(n * 4));
+            PB_CUDA(d_best.alloc((V + 1) * 8));
+            size_t t1 = 0, t2 = 0;
+            cub::DeviceRadixSort::SortKeys(nullptr, t1, (const unsigned long long*)d_mode_keys.p, (unsigned long long*)d_mode_keys2.p, (int)n, 0, 64, st);
+            cub::DeviceScan::InclusiveScan(nullptr, t2, (const uint32_t*)d_head.p, (uint32_t*)d_head2.p, MaxU32(), (int)n, st);
+            mode_tmp_bytes = t1 > t2 ? t1 : t2;
+            PB_CUDA(d_mode_tmp.alloc(mode_tmp_bytes));
+        }
+    }
+
     // ---- per-attribute reductions into a columnar staging result -----------------------------------------------
     pb200_result_buffer* res = new pb200_result_buffer();
     res->ctx = ctx;
@@ -412,7 +502,31 @@ int pb200_voxelgrid_filter(pb200_ctx* ctx, const pb200_buffer_desc* src, double 
         ra.dst_size = (uint32_t)dst_layout->attrs[a].size;
         const uint64_t comp = pb200_dtype_size(is_cast_vec3(rules[a]->dtype) ? vec3_component(rules[a]->dtype) : rules[a]->dtype, 0);
         ra.src_aligned = (((uintptr_t)ra.src % comp) == 0 && (sstride % comp) == 0) ? 1 : 0;
-        launch_reduce(*rules[a], ra, st);
+        const bool is_mode = rules[a]->kind == R_MODE || rules[a]->kind == R_MODE_BOOL;
+        if (is_mode && max_occ > MODE_THREAD_LIMIT) {
+            const uint32_t dt = rules[a]->dtype;
+            unsigned long long* mk = (unsigned long long*)d_mode_keys.p;
+            const uint32_t *fl = (const uint32_t*)d_flags.p, *ex = (const uint32_t*)d_excl.p, *si2 = (const uint32_t*)d_idx2.p;
+            if (dt == PB200_U8) mode_keys_kernel<uint8_t><<<blocks, 256, 0, st>>>(fl, ex, si2, n, ra.src, sstride, ra.src_aligned, mk);
+            else if (dt == PB200_I8) mode_keys_kernel<int8_t><<<blocks, 256, 0, st>>>(fl, ex, si2, n, ra.src, sstride, ra.src_aligned, mk);
+            else if (dt == PB200_I16) mode_keys_kernel<int16_t><<<blocks, 256, 0, st>>>(fl, ex, si2, n, ra.src, sstride, ra.src_aligned, mk);
+            else mode_keys_kernel<uint16_t><<<blocks, 256, 0, st>>>(fl, ex, si2, n, ra.src, sstride, ra.src_aligned, mk);
+            size_t tb = mode_tmp_bytes;
+            cudaError_t e2 = cub::DeviceRadixSort::SortKeys(d_mode_tmp.p, tb, (const unsigned long long*)mk, (unsigned long long*)d_mode_keys2.p,
+                                                            (int)n, 0, 16 + (int)bits_for(V + 1), st);
+            if (e2 != cudaSuccess) return fail(cuda_error(e2, "mode sort"));
+            run_heads_kernel<<<blocks, 256, 0, st>>>((const unsigned long long*)d_mode_keys2.p, n, (uint32_t*)d_head.p);
+            tb = mode_tmp_bytes;
+            e2 = cub::DeviceScan::InclusiveScan(d_mode_tmp.p, tb, (const uint32_t*)d_head.p, (uint32_t*)d_head2.p, MaxU32(), (int)n, st);
+            if (e2 != cudaSuccess) return fail(cuda_error(e2, "mode scan"));
+            cudaMemsetAsync(d_best.p, 0, (V + 1) * 8, st);
+            run_vote_kernel<<<blocks, 256, 0, st>>>((const unsigned long long*)d_mode_keys2.p, (const uint32_t*)d_head2.p, n, (unsigned long long*)d_best.p);
+            mode_decode_kernel<<<blocks, 256, 0, st>>>((const unsigned long long*)d_best.p, V, ra.dst, ra.dst_size, rules[a]->kind == R_MODE_BOOL ? 1 : 0,
+                                                           (dt == PB200_I8 || dt == PB200_I16) ? 32768ll : 0ll);
+            g_launches += 8;
+        } else {
+            launch_reduce(*rules[a], ra, st);
+        }
     }
     {
         cudaError_t e = cudaGetLastError();

@@ -126,3 +126,27 @@ def test_full_size_properties():
     # filtering the centroids again with the same grid origin keeps at most v voxels
     out2 = voxelgrid_filter(out, 0.1, 0.1, 0.1)
     assert out2.len() <= v
+
+
+@pytest.mark.parametrize("leaf", [(50.0, 50.0, 50.0), (4.0, 4.0, 50.0)])
+def test_crowded_voxels_use_the_sort_based_mode(leaf):
+    """voxels with hundreds / thousands of points: the mode attributes take the sort-based path (composite-key radix
+    sort + run-length vote) and must still equal the oracle (ties -> smallest value, signed values ordered)"""
+    rng = np.random.default_rng(17)
+    n = 6000
+    attrs = [("Position3D", O.VEC3F64), ("Classification", O.U8), ("ScanAngleRank", O.I8), ("ScanAngle", O.I16),
+             ("PointSourceID", O.U16), ("EdgeOfFlightLine", O.U8), ("Intensity", O.U16)]
+    ol = O.OLayout.from_attributes(attrs)
+    ob = O.OBuffer(ol, n, True)
+    ob.set_attribute("Position3D", rng.random((n, 3)) * [20, 10, 3])
+    ob.set_attribute("Classification", rng.integers(0, 5, n))
+    ob.set_attribute("ScanAngleRank", rng.integers(-4, 4, n))
+    ob.set_attribute("ScanAngle", rng.integers(-30000, 30000, n) // 10000 * 10000)
+    ob.set_attribute("PointSourceID", rng.choice([0, 1, 40000, 65535], n))
+    ob.set_attribute("EdgeOfFlightLine", rng.integers(0, 2, n))
+    ob.set_attribute("Intensity", rng.integers(0, 65536, n))
+    pbuf, _ = to_product(ob, attrs, 0)
+    oout, okeys = O.voxelgrid_filter(ob, leaf, ol, columnar=True)
+    out, keys = voxelgrid_filter(pbuf, *leaf, return_keys=True)
+    assert np.array_equal(keys, okeys)
+    util.assert_buffers_match(oout, out)
