@@ -62,6 +62,21 @@ pub const PB200_T_ADD: u32 = 3; pub const PB200_T_SHIFT_MASK: u32 = 4;
 pub struct pb200_transform { pub kind: u32, pub shift: u32, pub mask: u64, pub s: [f64; 3], pub o: [f64; 3] }
 
 #[repr(C)] #[derive(Clone, Copy)]
+pub struct pb200_las_header {
+    pub version_major: u8, pub version_minor: u8, pub point_format: u8, pub is_compressed: u8,
+    pub record_length: u16, pub header_size: u16,
+    pub offset_to_point_data: u32, pub number_of_vlrs: u32, pub extra_bytes: u32, pub _pad: u32,
+    pub number_of_points: u64,
+    pub scale: [f64; 3], pub offset: [f64; 3], pub min: [f64; 3], pub max: [f64; 3],
+}
+
+#[repr(C)] #[derive(Clone, Copy)]
+pub struct pb200_las_write_stats {
+    pub out_of_range: u64, pub points_by_return: [u64; 16], pub has_bounds: i32, pub _pad: i32,
+    pub bounds_min: [f64; 3], pub bounds_max: [f64; 3],
+}
+
+#[repr(C)] #[derive(Clone, Copy)]
 pub struct pb200_proj_op { pub kind: u32, pub _pad: u32, pub p: [f64; 12] }
 
 #[link(name = "pasture_b200")]
@@ -113,6 +128,13 @@ extern "C" {
         apply_to_source: c_int) -> c_int;
     pub fn pb200_las_default_converter(ctx: *mut pb200_ctx, raw: *const pb200_layout, target: *const pb200_layout,
                                        scale: *const f64, offset: *const f64, out: *mut *mut pb200_converter) -> c_int;
+    pub fn pb200_converter_set_packed_mapping(cv: *mut pb200_converter, to_name: *const c_char, to_dtype: u32, n_sources: u32,
+        from_names: *const *const c_char, masks: *const u32, shifts: *const u32) -> c_int;
+    pub fn pb200_las_parse_header(file_bytes: *const c_void, size: u64, out: *mut pb200_las_header) -> c_int;
+    pub fn pb200_las_read_points(ctx: *mut pb200_ctx, file_bytes: *const c_void, size: u64, first_point: u64, count: u64,
+                                 dst: *const pb200_buffer_desc, dst_begin: u64) -> c_int;
+    pub fn pb200_las_write_points(ctx: *mut pb200_ctx, src: *const pb200_buffer_desc, begin: u64, end: u64, point_format: c_int,
+        scale: *const f64, offset: *const f64, out_records: *mut c_void, out_memspace: i32, stats: *mut pb200_las_write_stats) -> c_int;
     pub fn pb200_converter_num_mappings(cv: *const pb200_converter) -> u32;
     pub fn pb200_converter_convert_into_range(cv: *mut pb200_converter, src: *const pb200_buffer_desc, src_begin: u64,
         src_end: u64, dst: *const pb200_buffer_desc, dst_begin: u64, dst_end: u64, out_of_range_count: *mut u64) -> c_int;

@@ -173,6 +173,10 @@ int pb200_converter_set_custom_mapping_with_transformation(pb200_converter* cv, 
                                                            uint32_t from_dtype, const char* to_name,
                                                            uint32_t to_dtype, uint32_t transform_dtype,
                                                            const pb200_transform* t, int apply_to_source);
+/* Bit-field packing (extension; the reference packs LAS flags per point in its writer, write_helpers.rs:26-51):
+ * target = OR_k ((source_k & mask_k) << shift_k); sources are U8 attributes of the source layout, target is U8/U16. */
+int pb200_converter_set_packed_mapping(pb200_converter* cv, const char* to_name, uint32_t to_dtype, uint32_t n_sources,
+                                       const char* const* from_names, const uint32_t* masks, const uint32_t* shifts);
 /* get_default_las_converter, pasture-io/src/las/raw_readers.rs:31-167 */
 int pb200_las_default_converter(pb200_ctx* ctx, const pb200_layout* raw_las_layout, const pb200_layout* target,
                                 const double scale[3], const double offset[3], pb200_converter** out);
@@ -267,6 +271,31 @@ int pb200_proj_pipeline_for_crs(const char* source_crs, const char* target_crs, 
 /* reproject_point_cloud_within (dst == NULL) / _between (PB200_ERR_RANGE if lengths differ) on POSITION_3D */
 int pb200_reproject(pb200_ctx* ctx, const pb200_buffer_desc* src, const pb200_buffer_desc* dst_or_null,
                     const pb200_proj_op* ops, uint32_t n_ops);
+
+/* ---- LAS point-block ingest / egress (the callers on either side of the conversion path) ---- */
+typedef struct pb200_las_header {       /* the public-header fields the point path needs (LAS 1.0-1.4) */
+    uint8_t version_major, version_minor, point_format, is_compressed;
+    uint16_t record_length, header_size;
+    uint32_t offset_to_point_data, number_of_vlrs, extra_bytes, _pad;
+    uint64_t number_of_points;
+    double scale[3], offset[3], min[3], max[3];
+} pb200_las_header;
+typedef struct pb200_las_write_stats {
+    uint64_t out_of_range;              /* != 0: write_position_as_las_position would panic (write_helpers.rs:15-17) */
+    uint64_t points_by_return[16];      /* [r] = points with ReturnNumber == r, r = 1..15 (raw_writers.rs:221-229,259-263) */
+    int32_t has_bounds, _pad;
+    double bounds_min[3], bounds_max[3];/* bounds of the written world-space positions (raw_writers.rs:28-47) */
+} pb200_las_write_stats;
+int pb200_las_parse_header(const void* file_bytes, uint64_t size, pb200_las_header* out);
+/* RawLASReader::read_into (pasture-io/src/las/raw_readers.rs:366-383): points [first, first+count) of an uncompressed
+ * LAS file image in HOST memory -> dst[dst_begin ..] in dst's own layout (default mappings of get_default_las_converter) */
+int pb200_las_read_points(pb200_ctx* ctx, const void* file_bytes, uint64_t size, uint64_t first_point, uint64_t count,
+                          const pb200_buffer_desc* dst, uint64_t dst_begin);
+/* RawLASWriter::write_points_default_layout (raw_writers.rs:203-362): points [begin,end) of `src` (the LasPointFormatN
+ * attributes by name; missing ones are written as 0) -> (end-begin) raw records of `point_format` in out_records */
+int pb200_las_write_points(pb200_ctx* ctx, const pb200_buffer_desc* src, uint64_t begin, uint64_t end, int point_format,
+                           const double scale[3], const double offset[3], void* out_records, int32_t out_memspace,
+                           pb200_las_write_stats* stats);
 
 /* ---- synthetic inputs (bench / test tooling; SURVEY 8d splitmix64 streams, generated in HBM) ---------- */
 /* raw LAS format-0 records (20 B each) of the C2/C5 stream, points first_index .. first_index+n-1 */

@@ -102,6 +102,7 @@ def lib():
         "po_las_default_layout": (i32, [i32, LP]),
         "po_las_default_converter": (i32, [CP, LP, LP, C.POINTER(dbl), C.POINTER(dbl)]),
         "po_las_write_position": (i32, [C.POINTER(dbl), C.POINTER(dbl), C.POINTER(dbl), C.POINTER(C.c_int32)]),
+        "po_las_write_points": (i32, [BP, i32, C.POINTER(dbl), C.POINTER(dbl), vp, vp, C.POINTER(dbl), C.POINTER(dbl), C.POINTER(u64)]),
         "po_calculate_bounds": (i32, [BP, C.POINTER(dbl), C.POINTER(dbl)]),
         "po_minmax_attribute": (i32, [BP, C.c_char_p, u32, u32, vp, vp]),
         "po_expand_bits_by_3": (u64, [u64]),
@@ -339,6 +340,17 @@ def convert_value(from_dtype, to_dtype, value_bytes):
     dst = np.zeros(32, dtype=np.uint8)
     _check(lib().po_convert_value(from_dtype, to_dtype, _ptr(src), _ptr(dst)), "convert_value")
     return dst[: lib().po_dtype_size(to_dtype, 0)].tobytes()
+
+
+def las_write_points(src, fmt, scale, offset):
+    """-> (records uint8 (n, record_size), counts16, bmin, bmax, panics)"""
+    raw = OLayout.las_raw(fmt)
+    out = np.zeros(max(1, src.len * raw.size), dtype=np.uint8)
+    counts = np.zeros(16, dtype=np.uint64)
+    mn, mx, panics = (C.c_double * 3)(), (C.c_double * 3)(), C.c_uint64(0)
+    _check(lib().po_las_write_points(C.byref(src.c), fmt, (C.c_double * 3)(*scale), (C.c_double * 3)(*offset), _ptr(out),
+                                     _ptr(counts), mn, mx, C.byref(panics)), "las_write_points")
+    return out[: src.len * raw.size].reshape(src.len, raw.size), counts, np.array(mn[:]), np.array(mx[:]), int(panics.value)
 
 
 def calculate_bounds(buf):

@@ -669,6 +669,65 @@ int po_las_write_position(const double world[3], const double scale[3], const do
     return panic;
 }
 
+/* RawLASWriter::write_points_default_layout, pasture-io/src/las/raw_writers.rs:203-362. `src` must have the default
+ * layout of `format` (LasPointFormatN). out: n raw records. counts16[r] = points with return number r (r = 1..15; the
+ * reference keeps 1..=5 or 1..=15 depending on the header, :221-229). Returns the number of points for which
+ * write_position_as_las_position would panic (write_helpers.rs:15-17); bounds as update_bounds_in_las_header (:28-47)
+ * starting from (+MAX, -MAX). */
+int po_las_write_points(const po_buffer* src, int format, const double scale[3], const double offset[3], uint8_t* out,
+                        uint64_t counts16[16], double bmin[3], double bmax[3], uint64_t* panics) {
+    po_layout def, raw;
+    int rc = po_las_default_layout(format, &def);
+    if (rc) return rc;
+    if (!po_layout_equal(src->layout, &def)) return PO_ERR_LAYOUT_MISMATCH;
+    po_las_raw_layout(format, &raw);
+    las_format f;
+    las_format_of(format, &f);
+    for (int b = 0; b < 16; ++b) counts16[b] = 0;
+    for (int c = 0; c < 3; ++c) { bmin[c] = 1.7976931348623157e308; bmax[c] = -1.7976931348623157e308; }
+    *panics = 0;
+    for (uint64_t i = 0; i < src->len; ++i) {
+        uint8_t rec[128];
+        /* get_point_range: gather the point in default-layout order (:237-240) */
+        for (uint32_t a = 0; a < def.n; ++a) {
+            raw_view v = view_attr(src, (int)a);
+            memcpy(rec + def.m[a].offset, view_at(&v, i), def.m[a].size);
+        }
+        const uint8_t* r = rec;
+        uint8_t* w = out + i * raw.size;
+        double pos[3];
+        memcpy(pos, r, 24); r += 24;
+        int32_t local[3];
+        if (po_las_write_position(pos, scale, offset, local)) (*panics)++;
+        memcpy(w, local, 12); w += 12;
+        for (int c = 0; c < 3; ++c) { if (pos[c] < bmin[c]) bmin[c] = pos[c]; if (pos[c] > bmax[c]) bmax[c] = pos[c]; }
+        memcpy(w, r, 2); w += 2; r += 2; /* intensity */
+        if (f.extended) {
+            uint8_t rn = r[0], nr = r[1], cf = r[2], sc = r[3], sd = r[4], ef = r[5];
+            r += 6;
+            if (rn >= 1 && rn <= 15) counts16[rn]++;
+            w[0] = (uint8_t)((rn & 0xF) | ((nr & 0xF) << 4));                                   /* write_helpers.rs:39-47 */
+            w[1] = (uint8_t)((cf & 0xF) | ((sc & 0x3) << 4) | ((sd & 0x1) << 6) | ((ef & 0x1) << 7));
+            w += 2;
+        } else {
+            uint8_t rn = r[0], nr = r[1], sd = r[2], ef = r[3];
+            r += 4;
+            if (rn >= 1 && rn <= 15) counts16[rn]++;
+            w[0] = (uint8_t)((rn & 0x7) | ((nr & 0x7) << 3) | ((sd & 0x1) << 6) | ((ef & 0x1) << 7)); /* :32-37 */
+            w += 1;
+        }
+        *w++ = *r++; /* classification */
+        if (f.extended) { *w++ = r[0]; memcpy(w, r + 1, 2); w += 2; r += 3; } /* user data, scan angle i16 */
+        else { *w++ = r[0]; *w++ = r[1]; r += 2; }                              /* scan angle rank, user data */
+        memcpy(w, r, 2); w += 2; r += 2; /* point source id */
+        if (f.gps) { memcpy(w, r, 8); w += 8; r += 8; }
+        if (f.color) { memcpy(w, r, 6); w += 6; r += 6; }
+        if (f.nir) { memcpy(w, r, 2); w += 2; r += 2; }
+        if (f.waveform) { memcpy(w, r, 29); w += 29; r += 29; }
+    }
+    return PO_OK;
+}
+
 /* ------------------------------------------------------------------------------------------------
  * A / M: bounds and min-max
  * ---------------------------------------------------------------------------------------------- */

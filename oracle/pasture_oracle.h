@@ -153,6 +153,10 @@ int po_las_default_converter(po_converter* cv, const po_layout* raw, const po_la
 /* returns 0, or 1 if the point would make the reference writer panic (try_into::<i32> overflow) */
 int po_las_write_position(const double world[3], const double scale[3], const double offset[3], int32_t out[3]);
 
+/* raw_writers.rs:203-362 (default-layout writer) */
+int po_las_write_points(const po_buffer* src, int format, const double scale[3], const double offset[3], uint8_t* out,
+                        uint64_t counts16[16], double bmin[3], double bmax[3], uint64_t* panics);
+
 /* bounds.rs:11-85 ; returns 1 = Some, 0 = None */
 int po_calculate_bounds(const po_buffer* buf, double out_min[3], double out_max[3]);
 /* minmax.rs:13-51 with T = view_dtype; returns 1 = Some, 0 = None, <0 error */

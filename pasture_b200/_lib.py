@@ -28,6 +28,19 @@ class Transform(C.Structure):
                 ("o", C.c_double * 3)]
 
 
+class LasHeader(C.Structure):
+    _fields_ = [("version_major", C.c_uint8), ("version_minor", C.c_uint8), ("point_format", C.c_uint8),
+                ("is_compressed", C.c_uint8), ("record_length", C.c_uint16), ("header_size", C.c_uint16),
+                ("offset_to_point_data", C.c_uint32), ("number_of_vlrs", C.c_uint32), ("extra_bytes", C.c_uint32),
+                ("_pad", C.c_uint32), ("number_of_points", C.c_uint64), ("scale", C.c_double * 3),
+                ("offset", C.c_double * 3), ("min", C.c_double * 3), ("max", C.c_double * 3)]
+
+
+class LasWriteStats(C.Structure):
+    _fields_ = [("out_of_range", C.c_uint64), ("points_by_return", C.c_uint64 * 16), ("has_bounds", C.c_int32),
+                ("_pad", C.c_int32), ("bounds_min", C.c_double * 3), ("bounds_max", C.c_double * 3)]
+
+
 class ProjOp(C.Structure):
     _fields_ = [("kind", C.c_uint32), ("_pad", C.c_uint32), ("p", C.c_double * 12)]
 
@@ -78,6 +91,10 @@ SIGNATURES = {
     "pb200_converter_set_custom_mapping_with_transformation":
         (i32, [vp, C.c_char_p, u32, C.c_char_p, u32, u32, C.POINTER(Transform), i32]),
     "pb200_las_default_converter": (i32, [vp, vp, vp, PD, PD, PVP]),
+    "pb200_converter_set_packed_mapping": (i32, [vp, C.c_char_p, u32, u32, C.POINTER(C.c_char_p), C.POINTER(u32), C.POINTER(u32)]),
+    "pb200_las_parse_header": (i32, [vp, u64, C.POINTER(LasHeader)]),
+    "pb200_las_read_points": (i32, [vp, vp, u64, u64, u64, BD, u64]),
+    "pb200_las_write_points": (i32, [vp, BD, u64, u64, i32, PD, PD, vp, C.c_int32, C.POINTER(LasWriteStats)]),
     "pb200_converter_num_mappings": (u32, [vp]),
     "pb200_converter_convert_into_range": (i32, [vp, BD, u64, u64, BD, u64, u64, C.POINTER(u64)]),
     "pb200_converter_convert_into": (i32, [vp, BD, BD, C.POINTER(u64)]),

@@ -33,6 +33,7 @@ def parse(path):
         "format": fmt & 0x3F, "record_length": rec_len, "count": count, "scale": list(scale),
         "offset": list(offset), "header_max_min": list(maxmin), "n_vlrs": n_vlrs,
         "records_hex": records.hex(),
+        "file_hex": b.hex(),  # the whole (tiny) file: header + VLRs + records, for the ingest tests
     }
 
 
