@@ -152,6 +152,16 @@ extern "C" {
     pub fn pb200_view_attribute_with_conversion(ctx: *mut pb200_ctx, buf: *const pb200_buffer_desc, name: *const c_char,
                                                 view_dtype: u32, out: *mut c_void) -> c_int;
 
+    pub fn pb200_ransac_rank_samples(ctx: *mut pb200_ctx, buf: *const pb200_buffer_desc, kind: c_int, samples: *const u64, n_models: u64,
+                                     distance_threshold: f64, models_out: *mut f64, rankings_out: *mut u64) -> c_int;
+    pub fn pb200_ransac_rank_models(ctx: *mut pb200_ctx, buf: *const pb200_buffer_desc, kind: c_int, models: *const f64, n_models: u64,
+                                    distance_threshold: f64, rankings_out: *mut u64) -> c_int;
+    pub fn pb200_ransac_inliers(ctx: *mut pb200_ctx, buf: *const pb200_buffer_desc, kind: c_int, model: *const f64, distance_threshold: f64,
+                                indices_out: *mut u64, capacity: u64, num_inliers: *mut u64) -> c_int;
+    pub fn pb200_ransac(ctx: *mut pb200_ctx, buf: *const pb200_buffer_desc, kind: c_int, distance_threshold: f64, num_of_iterations: u64,
+                        seed: u64, model_out: *mut f64, ranking_out: *mut u64, indices_out: *mut u64, capacity: u64) -> c_int;
+    pub fn pb200_filter_into(ctx: *mut pb200_ctx, src: *const pb200_buffer_desc, mask: *const u8, dst: *const pb200_buffer_desc,
+                             num_matches: *mut u64) -> c_int;
     pub fn pb200_calculate_bounds(ctx: *mut pb200_ctx, buf: *const pb200_buffer_desc, out_min: *mut f64,
                                   out_max: *mut f64, is_some: *mut c_int) -> c_int;
     pub fn pb200_minmax_attribute(ctx: *mut pb200_ctx, buf: *const pb200_buffer_desc, name: *const c_char, dtype: u32,

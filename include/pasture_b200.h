@@ -214,6 +214,13 @@ int pb200_transform_attribute(pb200_ctx* ctx, const pb200_buffer_desc* buf, cons
 int pb200_view_attribute_with_conversion(pb200_ctx* ctx, const pb200_buffer_desc* buf, const char* name,
                                          uint32_t view_dtype, void* out);
 
+/* HashMapBuffer::filter_into (pasture-core/src/containers/point_buffer.rs:1086-1136) with the index predicate given as
+ * a byte mask (len entries, non-zero = keep, same memory space as `src`). Keeps the order of the points. Writes the
+ * number of kept points to *num_matches; PB200_ERR_RANGE if dst->len is smaller, PB200_ERR_LAYOUT_MISMATCH if the
+ * layouts differ. Works for interleaved and columnar buffers on both sides. */
+int pb200_filter_into(pb200_ctx* ctx, const pb200_buffer_desc* src, const uint8_t* mask, const pb200_buffer_desc* dst,
+                      uint64_t* num_matches);
+
 /* ---- reductions ----------------------------------------------------------------------------------- */
 /* calculate_bounds, pasture-algorithms/src/bounds.rs:11-85. is_some=0 <=> None. All-NaN input ->
  * PB200_ERR_INVALID (AABB::from_min_max panics). */
@@ -253,6 +260,31 @@ int pb200_radius_search(pb200_ctx* ctx, const pb200_buffer_desc* buf, double rad
  * reference), curvature_out len f64. PB200_ERR_TOO_FEW_POINTS if len < 3, PB200_ERR_INVALID if k < 3. */
 int pb200_compute_normals(pb200_ctx* ctx, const pb200_buffer_desc* buf, uint32_t k, double* normals_out,
                           double* curvature_out);
+
+/* ---- RANSAC segmentation (pasture-algorithms/src/segmentation.rs) ------------------------------------------
+ * kind: plane = ransac_plane_{par,serial} (:180-199, :240-255), model = a,b,c,d of ax+by+cz+d=0 (4 doubles, 3 sample
+ * points per model); line = ransac_line_{par,serial} (:291-310, :350-368), model = first xyz, second xyz (6 doubles,
+ * 2 sample points). A point is an inlier iff distance_point_plane / distance_point_line (:31-44) < threshold,
+ * evaluated in f64 exactly as written there. Requires a Vec3f64 POSITION_3D like view_attribute::<Vector3<f64>>.
+ * The reference draws its samples from rand::thread_rng(); that draw is the only part that is not reproduced. */
+enum { PB200_RANSAC_PLANE = 0, PB200_RANSAC_LINE = 1 };
+/* generate_{plane,line}_model (:98-138) for n_models given draws: samples = n_models x 3|2 point indices (host),
+ * models_out = n_models x 4|6 doubles (host), rankings_out = n_models inlier counts (host). All models are ranked in
+ * one pass over the positions per 256 models. PB200_ERR_TOO_FEW_POINTS if len < 3|2, PB200_ERR_RANGE for a bad index. */
+int pb200_ransac_rank_samples(pb200_ctx* ctx, const pb200_buffer_desc* buf, int kind, const uint64_t* samples, uint64_t n_models,
+                              double distance_threshold, double* models_out, uint64_t* rankings_out);
+/* the same for caller-supplied models (host) */
+int pb200_ransac_rank_models(pb200_ctx* ctx, const pb200_buffer_desc* buf, int kind, const double* models, uint64_t n_models,
+                             double distance_threshold, uint64_t* rankings_out);
+/* the Vec<usize> of inlier indices of one model, ascending; indices_out (capacity entries) lives in buf's memory
+ * space. *num_inliers is always set; PB200_ERR_RANGE if capacity is too small. */
+int pb200_ransac_inliers(pb200_ctx* ctx, const pb200_buffer_desc* buf, int kind, const double* model, double distance_threshold,
+                         uint64_t* indices_out, uint64_t capacity, uint64_t* num_inliers);
+/* ransac_*_serial / _par in one call: draw j is splitmix64(seed, j) % len with the reference's redraw loops, the best
+ * model is the LAST one with the maximal ranking (Iterator::max_by). model_out: 4|6 doubles (host); indices_out may be
+ * NULL (ranking only) or hold `capacity` >= ranking entries in buf's memory space. */
+int pb200_ransac(pb200_ctx* ctx, const pb200_buffer_desc* buf, int kind, double distance_threshold, uint64_t num_of_iterations,
+                 uint64_t seed, double* model_out, uint64_t* ranking_out, uint64_t* indices_out, uint64_t capacity);
 
 /* ---- reprojection, pasture-algorithms/src/reprojection.rs:132-146,201-227 -------------------------- */
 /* PROJ is a closed-source-to-us dependency here; the GPU path takes an enumerated operation pipeline. */

@@ -120,6 +120,11 @@ def lib():
         "po_reproject": (None, [C.POINTER(ProjOp), u32, vp, vp, u64]),
         "po_pipeline_epsg4326_to_3309": (u32, [C.POINTER(ProjOp)]),
         "po_splitmix64": (u64, [u64, u64]),
+        "po_ransac_model_from_samples": (None, [i32, vp, vp, vp]),
+        "po_ransac_distance": (dbl, [i32, vp, vp]),
+        "po_ransac_rank_models": (None, [i32, vp, u64, vp, u64, dbl, vp]),
+        "po_ransac_inliers": (u64, [i32, vp, u64, vp, dbl, vp]),
+        "po_ransac_draw_samples": (None, [i32, u64, u64, u64, vp]),
         "po_gen_las_fmt0_records": (None, [vp, u64, u64, u64]),
         "po_gen_c1_points": (None, [vp, u64, u64, u64, C.POINTER(dbl)]),
         "po_gen_terrain_positions": (None, [vp, u64, u64, u64]),
@@ -353,6 +358,26 @@ def las_write_points(src, fmt, scale, offset):
     return out[: src.len * raw.size].reshape(src.len, raw.size), counts, np.array(mn[:]), np.array(mx[:]), int(panics.value)
 
 
+def filter_into(src, predicate, dst):
+    """HashMapBuffer::filter_into (pasture-core/src/containers/point_buffer.rs:1086-1136): for every attribute, the
+    values of the points whose index satisfies `predicate` are written, in order, to the front of `dst`.
+    -> number of matches. Raises like the reference panics (layout mismatch, target too small)."""
+    if [m[:2] + m[3:] for m in src.layout.members()] != [m[:2] + m[3:] for m in dst.layout.members()] or \
+            src.layout.size != dst.layout.size:
+        raise OracleError(-4, "PointLayouts must match")  # :1092
+    keep = [i for i in range(src.len) if predicate(i)]
+    if dst.len < len(keep):
+        raise OracleError(-5, "buffer.len() must be at least as large as the number of predicate matches")  # :1097
+    for a, (_, _, off, sz) in enumerate(src.layout.members()):
+        vals = src.attribute_bytes(a)[keep] if keep else np.zeros((0, sz), np.uint8)
+        if dst.columnar:  # :1104-1119
+            dst.columns[a][: len(keep) * sz] = vals.reshape(-1)
+        else:  # :1120-1134
+            rec = dst.aos[: dst.len * dst.layout.size].reshape(dst.len, dst.layout.size)
+            rec[: len(keep), off:off + sz] = vals
+    return len(keep)
+
+
 def calculate_bounds(buf):
     mn = (C.c_double * 3)()
     mx = (C.c_double * 3)()
@@ -446,6 +471,49 @@ def reproject(ops, n_ops, xyz):
     out = np.zeros_like(xyz)
     lib().po_reproject(ops, n_ops, _ptr(xyz), _ptr(out), len(xyz))
     return out
+
+
+def ransac_draw_samples(kind, n, n_models, seed):
+    s = np.zeros((n_models, 3 if kind == 0 else 2), dtype=np.uint64)
+    lib().po_ransac_draw_samples(kind, n, n_models, seed, _ptr(s))
+    return s
+
+
+def ransac_models(kind, pts, samples):
+    pts = np.ascontiguousarray(pts, dtype=np.float64)
+    samples = np.ascontiguousarray(samples, dtype=np.uint64)
+    w = 4 if kind == 0 else 6
+    m = np.zeros((len(samples), w))
+    for h in range(len(samples)):
+        row = np.zeros(w)
+        lib().po_ransac_model_from_samples(kind, _ptr(pts), _ptr(samples[h].copy()), _ptr(row))
+        m[h] = row
+    return m
+
+
+def ransac_rank_models(kind, pts, models, threshold):
+    pts = np.ascontiguousarray(pts, dtype=np.float64)
+    models = np.ascontiguousarray(models, dtype=np.float64)
+    r = np.zeros(len(models), dtype=np.uint64)
+    lib().po_ransac_rank_models(kind, _ptr(pts), len(pts), _ptr(models), len(models), C.c_double(threshold), _ptr(r))
+    return r
+
+
+def ransac_inliers(kind, pts, model, threshold):
+    pts = np.ascontiguousarray(pts, dtype=np.float64)
+    model = np.ascontiguousarray(model, dtype=np.float64)
+    idx = np.zeros(max(1, len(pts)), dtype=np.uint64)
+    k = lib().po_ransac_inliers(kind, _ptr(pts), len(pts), _ptr(model), C.c_double(threshold), _ptr(idx))
+    return idx[:k].copy()
+
+
+def ransac(kind, pts, threshold, n_models, seed):
+    """ransac_{plane,line}_serial (segmentation.rs:240-255, :350-368) with the seeded draw: (model, ranking, indices)"""
+    samples = ransac_draw_samples(kind, len(pts), n_models, seed)
+    models = ransac_models(kind, pts, samples)
+    ranks = ransac_rank_models(kind, pts, models, threshold)
+    best = len(ranks) - 1 - int(np.argmax(ranks[::-1]))  # Iterator::max_by returns the last maximum
+    return models[best], int(ranks[best]), ransac_inliers(kind, pts, models[best], threshold)
 
 
 def gen_las_fmt0_records(first, n, seed=42):

@@ -1383,6 +1383,76 @@ uint32_t po_pipeline_epsg4326_to_3309(po_proj_op* ops) {
 }
 
 /* ------------------------------------------------------------------------------------------------
+ * RANSAC segmentation, pasture-algorithms/src/segmentation.rs
+ * ---------------------------------------------------------------------------------------------- */
+
+void po_ransac_model_from_samples(int kind, const double* pts, const uint64_t* s, double* m) {
+    if (kind == 0) { /* generate_rng_plane :60-76 */
+        const double* pa = pts + 3 * s[0]; const double* pb = pts + 3 * s[1]; const double* pc = pts + 3 * s[2];
+        double v1[3], v2[3], nrm[3];
+        for (int c = 0; c < 3; ++c) { v1[c] = pb[c] - pa[c]; v2[c] = pc[c] - pa[c]; }
+        nrm[0] = v1[1] * v2[2] - v1[2] * v2[1]; /* nalgebra cross */
+        nrm[1] = v1[2] * v2[0] - v1[0] * v2[2];
+        nrm[2] = v1[0] * v2[1] - v1[1] * v2[0];
+        double dot = (nrm[0] * pa[0] + nrm[1] * pa[1]) + nrm[2] * pa[2]; /* nalgebra dot, 3 rows: a + b + c */
+        m[0] = nrm[0]; m[1] = nrm[1]; m[2] = nrm[2]; m[3] = -dot;
+    } else { /* generate_rng_line :91-95 */
+        for (int c = 0; c < 3; ++c) { m[c] = pts[3 * s[0] + c]; m[3 + c] = pts[3 * s[1] + c]; }
+    }
+}
+
+double po_ransac_distance(int kind, const double* m, const double p[3]) {
+    if (kind == 0) { /* distance_point_plane :31-35 */
+        double d = fabs(((m[0] * p[0] + m[1] * p[1]) + m[2] * p[2]) + m[3]);
+        double e = sqrt((m[0] * m[0] + m[1] * m[1]) + m[2] * m[2]);
+        return d / e;
+    }
+    /* distance_point_line :39-44 */
+    double v[3], w[3], cr[3];
+    for (int c = 0; c < 3; ++c) { v[c] = m[3 + c] - m[c]; w[c] = m[c] - p[c]; }
+    cr[0] = v[1] * w[2] - v[2] * w[1];
+    cr[1] = v[2] * w[0] - v[0] * w[2];
+    cr[2] = v[0] * w[1] - v[1] * w[0];
+    double num = sqrt((cr[0] * cr[0] + cr[1] * cr[1]) + cr[2] * cr[2]);
+    double den = sqrt((v[0] * v[0] + v[1] * v[1]) + v[2] * v[2]);
+    return num / den;
+}
+
+void po_ransac_rank_models(int kind, const double* pts, uint64_t n, const double* models, uint64_t n_models,
+                           double threshold, uint64_t* rankings) {
+    const int w = kind == 0 ? 4 : 6;
+    for (uint64_t h = 0; h < n_models; ++h) { /* generate_plane_model :119-138 / generate_line_model :98-117 */
+        uint64_t r = 0;
+        for (uint64_t i = 0; i < n; ++i)
+            if (po_ransac_distance(kind, models + w * h, pts + 3 * i) < threshold) r++;
+        rankings[h] = r;
+    }
+}
+
+uint64_t po_ransac_inliers(int kind, const double* pts, uint64_t n, const double* model, double threshold, uint64_t* indices) {
+    uint64_t r = 0;
+    for (uint64_t i = 0; i < n; ++i)
+        if (po_ransac_distance(kind, model, pts + 3 * i) < threshold) indices[r++] = i;
+    return r;
+}
+
+void po_ransac_draw_samples(int kind, uint64_t n, uint64_t n_models, uint64_t seed, uint64_t* samples) {
+    uint64_t j = 0;
+    for (uint64_t h = 0; h < n_models; ++h) {
+        uint64_t r1 = po_splitmix64(seed, j++) % n;
+        uint64_t r2 = po_splitmix64(seed, j++) % n;
+        while (r1 == r2) r2 = po_splitmix64(seed, j++) % n; /* :52-54, :85-89 */
+        if (kind == 0) {
+            uint64_t r3 = po_splitmix64(seed, j++) % n;
+            while (r2 == r3 || r1 == r3) r3 = po_splitmix64(seed, j++) % n; /* :55-59 */
+            samples[3 * h] = r1; samples[3 * h + 1] = r2; samples[3 * h + 2] = r3;
+        } else {
+            samples[2 * h] = r1; samples[2 * h + 1] = r2;
+        }
+    }
+}
+
+/* ------------------------------------------------------------------------------------------------
  * Synthetic inputs: identical streams on CPU and GPU
  * ---------------------------------------------------------------------------------------------- */
 

@@ -216,6 +216,23 @@ uint32_t po_pipeline_epsg4326_to_3309(po_proj_op* ops);
 
 /* deterministic synthetic generators, SURVEY 8(d) */
 uint64_t po_splitmix64(uint64_t seed, uint64_t j);
+
+/* ---- RANSAC segmentation (pasture-algorithms/src/segmentation.rs) --------------------------------------
+ * The reference draws its sample indices from rand::thread_rng() (:49-59, :82-89), so WHICH models are tried is not
+ * reproducible there; what is deterministic -- and restated here -- is everything after the draw: the model from the
+ * sampled points (:60-76, :91-95), the point/model distance (:31-44), the strict `<` inlier test with the ranking
+ * and index list (:98-138) and the choice of the best model (max_by ranking: the LAST maximum, :192-199).
+ * kind 0 = plane (3 samples per model, model = a,b,c,d), kind 1 = line (2 samples, model = first xyz, second xyz). */
+void po_ransac_model_from_samples(int kind, const double* pts, const uint64_t* samples, double* model);
+double po_ransac_distance(int kind, const double* model, const double p[3]);
+/* rankings[h] = number of points with distance < threshold for model h (models: 4 or 6 doubles each) */
+void po_ransac_rank_models(int kind, const double* pts, uint64_t n, const double* models, uint64_t n_models,
+                           double threshold, uint64_t* rankings);
+/* indices of the inliers of one model, ascending; returns their number */
+uint64_t po_ransac_inliers(int kind, const double* pts, uint64_t n, const double* model, double threshold, uint64_t* indices);
+/* the draw used by the GPU library's convenience entry point: draw j = splitmix64(seed, j) % n, redrawn like the
+ * reference's `while` loops until the 3 (2) indices differ. Fills samples (n_models x 3|2). */
+void po_ransac_draw_samples(int kind, uint64_t n, uint64_t n_models, uint64_t seed, uint64_t* samples);
 void po_gen_las_fmt0_records(uint8_t* out20, uint64_t first_index, uint64_t n, uint64_t seed);
 void po_gen_c1_points(uint8_t* out35, uint64_t first_index, uint64_t n, uint64_t seed, const double offset[3]);
 void po_gen_terrain_positions(double* out_xyz, uint64_t first_index, uint64_t n, uint64_t seed);

@@ -13,7 +13,7 @@ _lib.lib()  # fail at import time, not at first use
 from .layout import (ATTRIBUTE_BASIC_FLAGS, ATTRIBUTE_EXTENDED_FLAGS, ATTRIBUTE_LOCAL_LAS_POSITION,  # noqa: E402
                      FieldAlignment, PointAttributeDataType, PointAttributeDefinition, PointAttributeMember,
                      PointLayout, attributes)
-from .containers import HashMapBuffer, VectorBuffer, buffers_equal  # noqa: E402
+from .containers import HashMapBuffer, VectorBuffer, buffers_equal, filter, filter_into  # noqa: E402
 from .context import Context, get_context, kernel_launch_count  # noqa: E402
 from .conversion import (Add, BufferLayoutConverter, InvScaleOffset, ScaleOffset, ShiftMask, Transform,  # noqa: E402
                          get_default_las_converter, transform_attribute, view_attribute_with_conversion)
@@ -24,7 +24,7 @@ from . import las  # noqa: E402
 __all__ = [
     "PastureB200Error", "PointAttributeDataType", "PointAttributeDefinition", "PointAttributeMember", "PointLayout",
     "FieldAlignment", "attributes", "ATTRIBUTE_BASIC_FLAGS", "ATTRIBUTE_EXTENDED_FLAGS",
-    "ATTRIBUTE_LOCAL_LAS_POSITION", "VectorBuffer", "HashMapBuffer", "buffers_equal", "Context", "get_context",
+    "ATTRIBUTE_LOCAL_LAS_POSITION", "VectorBuffer", "HashMapBuffer", "buffers_equal", "filter", "filter_into", "Context", "get_context",
     "kernel_launch_count", "BufferLayoutConverter", "Transform", "ScaleOffset", "InvScaleOffset", "Add", "ShiftMask",
     "get_default_las_converter", "transform_attribute", "view_attribute_with_conversion", "algorithms", "sharding", "las",
 ]

@@ -103,6 +103,11 @@ SIGNATURES = {
     "pb200_converter_destroy": (None, [vp]),
     "pb200_transform_attribute": (i32, [vp, BD, C.c_char_p, u32, C.POINTER(Transform)]),
     "pb200_view_attribute_with_conversion": (i32, [vp, BD, C.c_char_p, u32, vp]),
+    "pb200_ransac_rank_samples": (i32, [vp, BD, i32, vp, u64, C.c_double, vp, vp]),
+    "pb200_ransac_rank_models": (i32, [vp, BD, i32, vp, u64, C.c_double, vp]),
+    "pb200_ransac_inliers": (i32, [vp, BD, i32, vp, C.c_double, vp, u64, C.POINTER(u64)]),
+    "pb200_ransac": (i32, [vp, BD, i32, C.c_double, u64, u64, vp, C.POINTER(u64), vp, u64]),
+    "pb200_filter_into": (i32, [vp, BD, vp, BD, C.POINTER(u64)]),
     "pb200_calculate_bounds": (i32, [vp, BD, PD, PD, C.POINTER(i32)]),
     "pb200_minmax_attribute": (i32, [vp, BD, C.c_char_p, u32, vp, vp, C.POINTER(i32)]),
     "pb200_expand_bits_by_3": (u64, [u64]),

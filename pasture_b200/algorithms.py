@@ -157,6 +157,95 @@ def compute_normals(point_cloud, k_nn, ctx=None):
     return normals[:n], curv[:n]
 
 
+# ---- segmentation (pasture-algorithms/src/segmentation.rs) --------------------------------------------------
+RANSAC_PLANE, RANSAC_LINE = 0, 1
+
+
+class Plane:
+    """segmentation.rs:19-28: ax + by + cz + d = 0 and the number of inliers"""
+
+    def __init__(self, a, b, c, d, ranking):
+        self.a, self.b, self.c, self.d, self.ranking = a, b, c, d, ranking
+
+    def __repr__(self):
+        return f"Plane {{ a: {self.a}, b: {self.b}, c: {self.c}, d: {self.d}, ranking: {self.ranking} }}"
+
+
+class Line:
+    """segmentation.rs:10-17"""
+
+    def __init__(self, first, second, ranking):
+        self.first, self.second, self.ranking = first, second, ranking
+
+    def __repr__(self):
+        return f"Line {{ first: {self.first}, second: {self.second}, ranking: {self.ranking} }}"
+
+
+def ransac_rank_samples(buffer, kind, samples, distance_threshold, ctx=None):
+    """generate_{plane,line}_model (:98-138) for given draws -> (models [m, 4|6] f64, rankings [m] u64) numpy"""
+    ctx = ctx or get_context()
+    s = np.ascontiguousarray(samples, dtype=np.uint64)
+    m = s.shape[0]
+    models = np.zeros((m, 4 if kind == RANSAC_PLANE else 6), dtype=np.float64)
+    ranks = np.zeros(m, dtype=np.uint64)
+    d = buffer.desc()
+    check(lib().pb200_ransac_rank_samples(ctx._h, C.byref(d), kind, s.ctypes.data, m, float(distance_threshold),
+                                          models.ctypes.data, ranks.ctypes.data))
+    return models, ranks
+
+
+def ransac_rank_models(buffer, kind, models, distance_threshold, ctx=None):
+    ctx = ctx or get_context()
+    mm = np.ascontiguousarray(models, dtype=np.float64)
+    ranks = np.zeros(mm.shape[0], dtype=np.uint64)
+    d = buffer.desc()
+    check(lib().pb200_ransac_rank_models(ctx._h, C.byref(d), kind, mm.ctypes.data, mm.shape[0], float(distance_threshold),
+                                         ranks.ctypes.data))
+    return ranks
+
+
+def ransac_inliers(buffer, kind, model, distance_threshold, ctx=None):
+    """indices (int64 tensor on the buffer's device, ascending) of the points within the threshold of `model`"""
+    ctx = ctx or get_context()
+    mm = np.ascontiguousarray(model, dtype=np.float64)
+    n = buffer.len()
+    idx = torch.zeros(max(1, n), dtype=torch.int64, device=buffer.device)
+    cnt = C.c_uint64(0)
+    d = buffer.desc()
+    check(lib().pb200_ransac_inliers(ctx._h, C.byref(d), kind, mm.ctypes.data, float(distance_threshold),
+                                     C.c_void_p(idx.data_ptr()), n, C.byref(cnt)))
+    return idx[: int(cnt.value)]
+
+
+def _ransac(buffer, kind, distance_threshold, num_of_iterations, seed, ctx):
+    ctx = ctx or get_context()
+    if seed is None:  # the reference draws from thread_rng(): every call tries different models
+        seed = int.from_bytes(__import__("os").urandom(8), "little")
+    n = buffer.len()
+    model = np.zeros(4 if kind == RANSAC_PLANE else 6, dtype=np.float64)
+    rank = C.c_uint64(0)
+    idx = torch.zeros(max(1, n), dtype=torch.int64, device=buffer.device)
+    d = buffer.desc()
+    check(lib().pb200_ransac(ctx._h, C.byref(d), kind, float(distance_threshold), int(num_of_iterations), int(seed),
+                             model.ctypes.data, C.byref(rank), C.c_void_p(idx.data_ptr()), n))
+    r = int(rank.value)
+    if kind == RANSAC_PLANE:
+        return Plane(*model.tolist(), r), idx[:r]
+    return Line(model[:3].copy(), model[3:].copy(), r), idx[:r]
+
+
+def ransac_plane_par(buffer, distance_threshold, num_of_iterations, seed=None, ctx=None):  # segmentation.rs:180
+    return _ransac(buffer, RANSAC_PLANE, distance_threshold, num_of_iterations, seed, ctx)
+
+
+def ransac_line_par(buffer, distance_threshold, num_of_iterations, seed=None, ctx=None):  # :291
+    return _ransac(buffer, RANSAC_LINE, distance_threshold, num_of_iterations, seed, ctx)
+
+
+ransac_plane_serial = ransac_plane_par  # :240 -- one implementation: all iterations are ranked in the same pass
+ransac_line_serial = ransac_line_par  # :350
+
+
 class Projection:
     """reprojection.rs:10-70 with an enumerated operation pipeline instead of a PROJ string"""
 

@@ -247,6 +247,36 @@ class HashMapBuffer(_BufferBase):
         return d
 
 
+def _mask_tensor(mask, n, device):
+    m = mask if isinstance(mask, torch.Tensor) else torch.from_numpy(np.ascontiguousarray(np.asarray(mask)))
+    m = (m != 0).to(torch.uint8).reshape(-1)
+    assert m.numel() == n, "one predicate value per point"
+    return m.to(device).contiguous()
+
+
+def filter_into(source, target, mask, ctx=None):
+    """HashMapBuffer::filter_into (point_buffer.rs:1086): the predicate `Fn(usize) -> bool` is given as a mask over
+    the point indices. Returns the number of matches."""
+    from ._lib import check, lib
+    from .context import get_context
+    ctx = ctx or get_context()
+    m = _mask_tensor(mask, source.len(), source.device)
+    sd, dd = source.desc(), target.desc()
+    count = C.c_uint64(0)
+    check(lib().pb200_filter_into(ctx._h, C.byref(sd), C.c_void_p(m.data_ptr()), C.byref(dd), C.byref(count)))
+    return int(count.value)
+
+
+def filter(source, mask, out_buffer_type=None, device=None, ctx=None):
+    """HashMapBuffer::filter (point_buffer.rs:1064): new buffer holding the points whose mask entry is non-zero"""
+    m = _mask_tensor(mask, source.len(), source.device)
+    n = int(m.sum().item())
+    out_type = out_buffer_type or type(source)
+    target = out_type(source.point_layout(), n, device if device is not None else source.device)
+    filter_into(source, target, m, ctx)
+    return target
+
+
 def buffers_equal(a, b):
     """attribute-wise byte equality of two buffers with the same attributes (any memory layout)"""
     la, lb = a.point_layout(), b.point_layout()

@@ -151,3 +151,17 @@ def test_mt_variant_equals_single_thread():
     assert np.array_equal(a.attribute("ScanDirectionFlag"), (flags >> 6) & 1)
     assert np.array_equal(a.attribute("EdgeOfFlightLine"), (flags >> 7) & 1)
     assert np.array_equal(a.attribute("ScanAngleRank"), rec[:, 16].view(np.int8))
+
+
+def test_oracle_filter_into_like_reference_test():  # point_buffer.rs:2296-2329 (every second point survives)
+    ol = O.OLayout.from_attributes([("Position3D", O.VEC3F64), ("Classification", O.U8)])
+    src = O.OBuffer(ol, 8, True)
+    src.set_attribute("Position3D", np.arange(24, dtype=np.float64).reshape(8, 3))
+    src.set_attribute("Classification", np.arange(8))
+    for columnar in (True, False):
+        dst = O.OBuffer(ol, 4, columnar)
+        assert O.filter_into(src, lambda i: i % 2 == 0, dst) == 4
+        assert np.array_equal(dst.attribute("Classification"), [0, 2, 4, 6])
+        assert np.array_equal(dst.attribute("Position3D"), np.arange(24, dtype=np.float64).reshape(8, 3)[::2])
+    with pytest.raises(O.OracleError):
+        O.filter_into(src, lambda i: True, O.OBuffer(ol, 4, True))
