@@ -152,6 +152,11 @@ extern "C" {
     pub fn pb200_view_attribute_with_conversion(ctx: *mut pb200_ctx, buf: *const pb200_buffer_desc, name: *const c_char,
                                                 view_dtype: u32, out: *mut c_void) -> c_int;
 
+    pub fn pb200_pnts_compatible_layout(point_layout: *const pb200_layout, num_points: u64, out_attrs: *mut pb200_attr, n_out: *mut u32,
+                                        body_bytes: *mut u64) -> c_int;
+    pub fn pb200_pnts_read_points(ctx: *mut pb200_ctx, body: *const c_void, attrs: *const pb200_attr, n_attrs: u32, first_point: u64,
+                                  count: u64, dst: *const pb200_buffer_desc, rtc_center: *const f64) -> c_int;
+    pub fn pb200_pnts_write_points(ctx: *mut pb200_ctx, src: *const pb200_buffer_desc, body_out: *mut c_void, body_capacity: u64) -> c_int;
     pub fn pb200_ransac_rank_samples(ctx: *mut pb200_ctx, buf: *const pb200_buffer_desc, kind: c_int, samples: *const u64, n_models: u64,
                                      distance_threshold: f64, models_out: *mut f64, rankings_out: *mut u64) -> c_int;
     pub fn pb200_ransac_rank_models(ctx: *mut pb200_ctx, buf: *const pb200_buffer_desc, kind: c_int, models: *const f64, n_models: u64,

@@ -199,7 +199,8 @@ int pb200_converter_convert_into_range_with_bounds(pb200_converter* cv, const pb
                                                    uint64_t dst_end, double out_min[3], double out_max[3],
                                                    int* is_some);
 /* same, but leaves [minx,miny,minz,-maxx,-maxy,-maxz] in a device array (6 doubles) without synchronising,
- * ready for one ncclAllReduce(min) across point-range shards. Empty range: +MAX / +MAX. */
+ * ready for one ncclAllReduce(min) across point-range shards. Empty range: +MAX / +MAX.
+ * Returns 1 if bounds were tracked (the target has a mapped Vec3f64 "Position3D"), 0 if not, < 0 on error. */
 int pb200_converter_convert_into_range_with_bounds_device(pb200_converter* cv, const pb200_buffer_desc* src,
                                                           uint64_t src_begin, uint64_t src_end,
                                                           const pb200_buffer_desc* dst, uint64_t dst_begin,
@@ -260,6 +261,26 @@ int pb200_radius_search(pb200_ctx* ctx, const pb200_buffer_desc* buf, double rad
  * reference), curvature_out len f64. PB200_ERR_TOO_FEW_POINTS if len < 3, PB200_ERR_INVALID if k < 3. */
 int pb200_compute_normals(pb200_ctx* ctx, const pb200_buffer_desc* buf, uint32_t k, double* normals_out,
                           double* curvature_out);
+
+/* ---- 3D-Tiles .pnts FeatureTable body (pasture-io/src/tiles3d) --------------------------------------------
+ * The binary body is one packed array per semantic. `attrs` describes the file's layout like PntsReader::layout +
+ * attribute_offsets do: name (pasture attribute name, e.g. "Position3D"), dtype, offset = byte offset of the array in
+ * the body. Header and JSON stay with the caller. */
+/* PntsWriter::make_compatible_layout (pnts_writer.rs:104-150) + the array offsets of create_feature_table (:234-246):
+ * the supported semantics of `point_layout` (Position3D->Vec3f32, ColorRGB->Vec3u8, ColorRGBA->Vec4u8, Normal->Vec3f32,
+ * everything else is dropped) in source order; *body_bytes = calc_feature_table_body_length (:300-308).
+ * out_attrs must have room for 4 entries. */
+int pb200_pnts_compatible_layout(const pb200_layout* point_layout, uint64_t num_points, pb200_attr* out_attrs, uint32_t* n_out,
+                                 uint64_t* body_bytes);
+/* PntsReader::read_into (pnts_reader.rs:294-367): points [first_point, first_point+count) of the body (same memory
+ * space as dst) go to dst[0, count); file attributes the target does not have are skipped, target attributes the file
+ * does not have are left alone, differing datatypes are cast. rtc_center (nullable, 3 doubles) = PntsReadPositionsMode::
+ * Absolute: added to POSITION_3D of every point of dst (Vec3f32 via f64, or Vec3f64; else PB200_ERR_UNSUPPORTED, :247-283). */
+int pb200_pnts_read_points(pb200_ctx* ctx, const void* body, const pb200_attr* attrs, uint32_t n_attrs, uint64_t first_point,
+                           uint64_t count, const pb200_buffer_desc* dst, const double* rtc_center);
+/* PntsWriter::write + write_feature_table_body (pnts_writer.rs:353-401, :310-341): all points of src, converted to
+ * the compatible layout, as the FeatureTable body (zero padded arrays) at body_out (src's memory space). */
+int pb200_pnts_write_points(pb200_ctx* ctx, const pb200_buffer_desc* src, void* body_out, uint64_t body_capacity);
 
 /* ---- RANSAC segmentation (pasture-algorithms/src/segmentation.rs) ------------------------------------------
  * kind: plane = ransac_plane_{par,serial} (:180-199, :240-255), model = a,b,c,d of ax+by+cz+d=0 (4 doubles, 3 sample

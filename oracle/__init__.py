@@ -378,6 +378,70 @@ def filter_into(src, predicate, dst):
     return len(keep)
 
 
+def _set_attribute_bytes(buf, idx, rows, raw):
+    _, _, off, sz = buf.layout.members()[idx]
+    if buf.columnar:
+        buf.columns[idx][: buf.len * sz].reshape(buf.len, sz)[rows] = raw
+    else:
+        buf.aos[: buf.len * buf.layout.size].reshape(buf.len, buf.layout.size)[rows, off:off + sz] = raw
+
+
+def _convert_column(name, raw, from_dtype, to_dtype):
+    """(n, size(from)) uint8 -> (n, size(to)) uint8 through get_converter_for_attributes (attribute_conversion.rs:160-271)"""
+    n = raw.shape[0]
+    if from_dtype == to_dtype or n == 0:
+        return raw
+    sl, tl = OLayout.from_attributes([(name, from_dtype)]), OLayout.from_attributes([(name, to_dtype)])
+    src = OBuffer(sl, n, True)
+    src.columns[0][: raw.size] = raw.reshape(-1)
+    return OConverter(sl, tl).convert(src, True).attribute_bytes(0)
+
+
+PNTS_SEMANTIC_DTYPES = {"Position3D": VEC3F32, "ColorRGB": VEC3U8, "ColorRGBA": VEC4U8, "Normal": VEC3F32}  # pnts_writer.rs:110-117
+
+
+def pnts_read_into(body, file_attrs, first, count, dst, rtc_center=None):
+    """PntsReader::read_into (pasture-io/src/tiles3d/pnts_reader.rs:294-367). body: uint8 array holding the file,
+    file_attrs: [(name, dtype, byte offset of the array)]; points [first, first+count) -> dst[0, count).
+    rtc_center: apply_rtc_center_offset (:247-283) over the WHOLE buffer."""
+    body = np.frombuffer(bytes(body), dtype=np.uint8)
+    for name, dtype, off in file_attrs:
+        ti = dst.layout.index_by_name(name)
+        if ti < 0:
+            continue  # :308
+        ssz = lib().po_dtype_size(dtype, 0)
+        raw = body[off + first * ssz: off + (first + count) * ssz].reshape(count, ssz)
+        _set_attribute_bytes(dst, ti, slice(0, count), _convert_column(name, raw, dtype, dst.layout.members()[ti][1]))
+    pi = dst.layout.index_by_name("Position3D")
+    if rtc_center is not None and pi >= 0:
+        dtype = dst.layout.members()[pi][1]
+        c = np.asarray(rtc_center, dtype=np.float64)
+        p = dst.attribute("Position3D")
+        if dtype == VEC3F32:
+            p = (p.astype(np.float64) + c).astype(np.float32)  # :265-273
+        elif dtype == VEC3F64:
+            p = p + c  # :275-278
+        else:
+            raise OracleError(-10, "Unsupported datatype for POSITION_3D attribute")
+        dst.set_attribute("Position3D", p)
+
+
+def pnts_feature_table_body(src):
+    """PntsWriter::write + write_feature_table_body (pnts_writer.rs:353-401, :310-341) for one buffer:
+    -> ([(name, dtype, byte offset)], body bytes)"""
+    attrs, parts, off = [], [], 0
+    for i, (name, dtype, _, _) in enumerate(src.layout.members()):
+        if name not in PNTS_SEMANTIC_DTYPES:
+            continue
+        to = PNTS_SEMANTIC_DTYPES[name]
+        raw = _convert_column(name, src.attribute_bytes(i), dtype, to).reshape(-1)
+        attrs.append((name, to, off))
+        pad = (-raw.size) % 8
+        parts += [raw, np.zeros(pad, np.uint8)]
+        off += raw.size + pad
+    return attrs, (np.concatenate(parts) if parts else np.zeros(0, np.uint8)).tobytes()
+
+
 def calculate_bounds(buf):
     mn = (C.c_double * 3)()
     mx = (C.c_double * 3)()

@@ -20,11 +20,12 @@ from .conversion import (Add, BufferLayoutConverter, InvScaleOffset, ScaleOffset
 from . import algorithms  # noqa: E402
 from . import sharding  # noqa: E402
 from . import las  # noqa: E402
+from . import tiles3d  # noqa: E402
 
 __all__ = [
     "PastureB200Error", "PointAttributeDataType", "PointAttributeDefinition", "PointAttributeMember", "PointLayout",
     "FieldAlignment", "attributes", "ATTRIBUTE_BASIC_FLAGS", "ATTRIBUTE_EXTENDED_FLAGS",
     "ATTRIBUTE_LOCAL_LAS_POSITION", "VectorBuffer", "HashMapBuffer", "buffers_equal", "filter", "filter_into", "Context", "get_context",
     "kernel_launch_count", "BufferLayoutConverter", "Transform", "ScaleOffset", "InvScaleOffset", "Add", "ShiftMask",
-    "get_default_las_converter", "transform_attribute", "view_attribute_with_conversion", "algorithms", "sharding", "las",
+    "get_default_las_converter", "transform_attribute", "view_attribute_with_conversion", "algorithms", "sharding", "las", "tiles3d",
 ]

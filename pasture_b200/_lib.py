@@ -103,6 +103,9 @@ SIGNATURES = {
     "pb200_converter_destroy": (None, [vp]),
     "pb200_transform_attribute": (i32, [vp, BD, C.c_char_p, u32, C.POINTER(Transform)]),
     "pb200_view_attribute_with_conversion": (i32, [vp, BD, C.c_char_p, u32, vp]),
+    "pb200_pnts_compatible_layout": (i32, [vp, u64, vp, C.POINTER(u32), C.POINTER(u64)]),
+    "pb200_pnts_read_points": (i32, [vp, vp, vp, u32, u64, u64, BD, vp]),
+    "pb200_pnts_write_points": (i32, [vp, BD, vp, u64]),
     "pb200_ransac_rank_samples": (i32, [vp, BD, i32, vp, u64, C.c_double, vp, vp]),
     "pb200_ransac_rank_models": (i32, [vp, BD, i32, vp, u64, C.c_double, vp]),
     "pb200_ransac_inliers": (i32, [vp, BD, i32, vp, C.c_double, vp, u64, C.POINTER(u64)]),
