@@ -87,6 +87,50 @@ def main():
         ms = timed(lambda: wr.convert_into(aos, back))
         emit("C1 on GPU: interleaved LasPointFormat0 (35 B) -> raw LAS fmt0 (20 B), (p-o)/s truncating", ms, n, 55)
         del col, aos, back
+    if "filter" not in args.skip:
+        src = alg.synth_las_fmt0_records(n)
+        rec = src.data[: 20 * n].view(n, 20)
+        mask = ((rec[:, 15] & 1) == 1).to(torch.uint8)
+        kept = int(mask.sum().item())
+        dst = pb.VectorBuffer(src.point_layout(), kept, "cuda")
+        ms = timed(lambda: pb.filter_into(src, dst, mask))
+        emit("filter_into: raw LAS fmt0 records (20 B, interleaved), ~50% kept (mask scan + gather)", ms, n, 1 + 20 + 20 * kept / n,
+             {"kept": kept})
+        del src, dst, mask, rec
+    if "ransac" not in args.skip:
+        import numpy as np
+        m = args.knn_points
+        src = alg.synth_terrain_positions(m)
+        rng = np.random.default_rng(1)
+        for kind, name in ((0, "plane"), (1, "line")):
+            samples = rng.integers(0, m, (300, 3 if kind == 0 else 2)).astype(np.uint64)
+            ms = timed(lambda: alg.ransac_rank_samples(src, kind, samples, 0.5), reps=2)
+            emit(f"RANSAC {name}: 300 models ranked over the cloud (2 launches of <=256 models, 24 B/pt each)", ms, m, 48,
+                 {"point_model_tests_per_s": 300 * m / (ms * 1e-3)})
+        del src
+    if "las" not in args.skip:
+        from pasture_b200 import las
+        raw, tgt = pb.PointLayout.las_raw(0), pb.PointLayout.las_default(0)
+        src = alg.synth_las_fmt0_records(n)
+        col = pb.HashMapBuffer(tgt, n, "cuda")
+        cv = pb.get_default_las_converter(raw, tgt, (0.001,) * 3, (500000.0, 5400000.0, 100.0))
+        cv.convert_into(src, col)
+        del src
+        ms = timed(lambda: las.write_points(col, 0, (0.001,) * 3, (500000.0, 5400000.0, 100.0)), reps=2)
+        emit("LAS egress: columnar default layout (35 B) -> fmt0 records (20 B) + counts by return + bounds", ms, n, 55)
+        del col
+    if "pnts" not in args.skip:
+        from pasture_b200 import tiles3d
+        _l = pb.PointLayout.from_attributes([pb.attributes.POSITION_3D, pb.attributes.COLOR_RGB])
+        src = pb.HashMapBuffer(_l, n, "cuda")
+        src.columns[0][: 24 * n].view(torch.float64).uniform_(-1000.0, 1000.0)
+        w = tiles3d.PntsWriter(_l)
+        def wr():
+            w._chunks.clear()
+            w.write(src)
+        ms = timed(wr, reps=2)
+        emit(".pnts egress: Vec3f64 + Vec3u16 columns -> FeatureTable body (Vec3f32 + Vec3u8)", ms, n, 30 + 15)
+        del src
     if "c4" not in args.skip:
         m = args.knn_points
         src = alg.synth_terrain_positions(m)

@@ -16,9 +16,10 @@ BIG = [("GpsTime", O.F64), ("ColorRGB", O.VEC3U16), ("Position3D", O.VEC3F64), (
 @pytest.mark.parametrize("src_col", [True, False])
 @pytest.mark.parametrize("dst_type", [HashMapBuffer, VectorBuffer])
 @pytest.mark.parametrize("device", ["cuda", "cpu"])
-@pytest.mark.parametrize("n,keep", [(1, 1.0), (17, 0.5), (5000, 0.3), (100003, 0.9), (4096, 0.0)])
-def test_filter_matches_boolean_indexing(src_col, dst_type, device, n, keep):
-    ol, pl = util.layouts(BIG, packed=1)
+@pytest.mark.parametrize("packed", [0, 1])
+@pytest.mark.parametrize("n,keep", [(1, 1.0), (17, 0.5), (5000, 0.3), (100003, 0.9), (4096, 0.0), (8192, 1.0)])
+def test_filter_matches_boolean_indexing(src_col, dst_type, device, packed, n, keep):
+    ol, pl = util.layouts(BIG, packed=packed)
     ob, pbuf = util.random_bytes_buffers(ol, pl, n, src_col, seed=n, device=device)
     rng = np.random.default_rng(n + 1)
     mask = rng.random(n) < keep
@@ -58,6 +59,19 @@ def test_filter_into_contract():
     assert k == int(mask.sum())
     raw = dst.raw_bytes().reshape(120, pl.size_of_point_entry())
     assert np.all(raw[k:] == 0xEE)
+    # a layout with padding: the padding bytes of the written records are not touched either (the reference copies
+    # attribute by attribute)
+    ol2, pl2 = util.layouts(BIG)
+    assert pl2.size_of_point_entry() > sum(m.size() for m in pl2.attributes())
+    _, src2 = util.random_bytes_buffers(ol2, pl2, 100, False, seed=5)
+    dst2 = VectorBuffer(pl2, 100, "cuda")
+    dst2.data.fill_(0xEE)
+    k2 = pb.filter_into(src2, dst2, mask)
+    raw2 = dst2.raw_bytes().reshape(100, pl2.size_of_point_entry())
+    covered = np.zeros(pl2.size_of_point_entry(), bool)
+    for m in pl2.attributes():
+        covered[m.offset():m.offset() + m.size()] = True
+    assert np.all(raw2[:k2][:, ~covered] == 0xEE) and not np.all(raw2[:k2][:, covered] == 0xEE)
 
 
 def test_filter_full_size():
