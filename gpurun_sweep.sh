@@ -1,6 +1,8 @@
-python -m pytest tests/test_gpu_convert.py -x -q 2>&1 | tail -3
-B="python bench.py --steps 10 --warmup 3 --no-e2e --no-cpu-baseline"
-for cfg in "" "--param convert.threads=512 --param convert.ctas_per_sm=1" "--param convert.threads=512 --param convert.ctas_per_sm=1 --param convert.stages=3" "--param convert.threads=384 --param convert.ctas_per_sm=1"  "--param convert.threads=512 --param convert.ctas_per_sm=2" "--param convert.threads=384 --param convert.ctas_per_sm=2" "--param convert.threads=256 --param convert.ctas_per_sm=3" "--param convert.threads=512 --param convert.ctas_per_sm=1 --fused-bounds"; do
-  echo "== $cfg"; $B $cfg 2>&1 | python -c "import sys,json; d=json.loads(sys.stdin.readlines()[-1]); print(d['ms_per_step'], d['roofline']['best_launch_ms'], d['roofline']['achieved'], d['roofline']['frac'])"
-done
-ncu --set full --clock-control none --import-source on -k regex:convert_tiles -s 3 -c 1 -o gpurun_out/prof_convert_r1d python bench.py --steps 3 --warmup 3 --no-e2e --no-cpu-baseline --param convert.threads=512 --param convert.ctas_per_sm=1 > /dev/null 2>&1
+#!/bin/bash
+# round-1 evidence run: full GPU suite, default bench, ncu launch list of the bench command, one full capture of the top kernel
+python -m pytest tests -m gpu -x -q 2>&1 | tail -4 > gpurun_out/pytest_gpu_r1.txt
+python bench.py > gpurun_out/bench_r1.json 2> gpurun_out/bench_r1.err
+python bench.py --impl reference > gpurun_out/bench_r1_reference.json 2>> gpurun_out/bench_r1.err
+ncu --metrics gpu__time_duration.sum --clock-control none -c 400 --csv --log-file gpurun_out/launches_r1.csv python bench.py --steps 3 --warmup 3 --no-cpu-baseline > gpurun_out/bench_under_ncu.json 2>&1
+ncu --set full --clock-control none --import-source on -k regex:convert_tiles -s 3 -c 1 -o gpurun_out/prof_convert_r1e python bench.py --steps 3 --warmup 3 --no-e2e --no-cpu-baseline > /dev/null 2>&1
+cat gpurun_out/pytest_gpu_r1.txt; cat gpurun_out/bench_r1.json; cat gpurun_out/bench_r1_reference.json
