@@ -88,6 +88,7 @@ extern "C" {
     pub fn pb200_ctx_set_stream(ctx: *mut pb200_ctx, cuda_stream: *mut c_void) -> c_int;
     pub fn pb200_ctx_get_stream(ctx: *mut pb200_ctx) -> *mut c_void;
     pub fn pb200_ctx_synchronize(ctx: *mut pb200_ctx) -> c_int;
+    pub fn pb200_ctx_trim(ctx: *mut pb200_ctx) -> c_int;
     pub fn pb200_ctx_set_param(ctx: *mut pb200_ctx, key: *const c_char, value: i64) -> c_int;
     pub fn pb200_ctx_destroy(ctx: *mut pb200_ctx);
     pub fn pb200_host_alloc(bytes: u64, out: *mut *mut c_void) -> c_int;

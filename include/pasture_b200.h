@@ -118,6 +118,8 @@ int pb200_ctx_create(int device, pb200_ctx** out);
 int pb200_ctx_set_stream(pb200_ctx* ctx, void* cuda_stream);
 void* pb200_ctx_get_stream(pb200_ctx* ctx);
 int pb200_ctx_synchronize(pb200_ctx* ctx);
+/* hand the temporaries cached between calls (sort buffers, trees; stream-ordered pool) back to the driver */
+int pb200_ctx_trim(pb200_ctx* ctx);
 /* tuning knobs of the tile pipeline: "convert.tile_points", "convert.threads", "convert.stages",
  * "convert.ctas_per_sm", "convert.force_direct" */
 int pb200_ctx_set_param(pb200_ctx* ctx, const char* key, int64_t value);

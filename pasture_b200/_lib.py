@@ -59,6 +59,7 @@ SIGNATURES = {
     "pb200_ctx_set_stream": (i32, [vp, vp]),
     "pb200_ctx_get_stream": (vp, [vp]),
     "pb200_ctx_synchronize": (i32, [vp]),
+    "pb200_ctx_trim": (i32, [vp]),
     "pb200_ctx_set_param": (i32, [vp, C.c_char_p, i64]),
     "pb200_ctx_destroy": (None, [vp]),
     "pb200_host_alloc": (i32, [u64, PVP]),

@@ -25,6 +25,10 @@ class Context:
     def synchronize(self):
         check(lib().pb200_ctx_synchronize(self._h))
 
+    def trim(self):
+        """release the temporaries cached between calls (sort buffers, trees) back to the driver"""
+        check(lib().pb200_ctx_trim(self._h))
+
     def set_param(self, key, value):
         check(lib().pb200_ctx_set_param(self._h, key.encode(), int(value)))
 

@@ -104,6 +104,14 @@ int pb200_ctx_create(int device, pb200_ctx** out) {
     PB_CUDA(cudaStreamCreateWithFlags(&c->copy_in, cudaStreamNonBlocking));
     PB_CUDA(cudaStreamCreateWithFlags(&c->copy_out, cudaStreamNonBlocking));
     PB_CUDA(cudaHostAlloc(&c->h_scratch, 4096, cudaHostAllocDefault));
+    {   // keep freed temporaries (DevTmp) in the pool between calls; pb200_ctx_trim hands them back
+        cudaMemPool_t pool;
+        if (cudaDeviceGetDefaultMemPool(&pool, device) == cudaSuccess) {
+            uint64_t keep = UINT64_MAX;
+            cudaMemPoolSetAttribute(pool, cudaMemPoolAttrReleaseThreshold, &keep);
+        }
+        cudaGetLastError();
+    }
     *out = c;
     return PB200_OK;
 }
@@ -127,6 +135,15 @@ int pb200_ctx_synchronize(pb200_ctx* ctx) {
     return PB200_OK;
 }
 
+int pb200_ctx_trim(pb200_ctx* ctx) {
+    PB_TRY(ensure_device(ctx));
+    PB_CUDA(cudaStreamSynchronize(ctx->stream));
+    cudaMemPool_t pool;
+    PB_CUDA(cudaDeviceGetDefaultMemPool(&pool, ctx->device));
+    PB_CUDA(cudaMemPoolTrimTo(pool, 0));
+    return PB200_OK;
+}
+
 int pb200_ctx_set_param(pb200_ctx* ctx, const char* key, int64_t v) {
     if (!ctx || !key) return set_error(PB200_ERR_INVALID, "pb200_ctx_set_param: null argument");
     std::string k(key);
@@ -135,6 +152,9 @@ int pb200_ctx_set_param(pb200_ctx* ctx, const char* key, int64_t v) {
     else if (k == "convert.stages") ctx->stages = v;
     else if (k == "convert.ctas_per_sm") ctx->ctas_per_sm = v;
     else if (k == "convert.force_direct") ctx->force_direct = v;
+    else if (k == "knn.init_radius") ctx->knn_init_radius = v;
+    else if (k == "knn.stats") ctx->knn_stats = v;
+    else if (k == "knn.per_axis_codes") ctx->knn_per_axis_codes = v;
     else return set_error(PB200_ERR_INVALID, "unknown parameter %s", key);
     return PB200_OK;
 }

@@ -26,6 +26,7 @@ struct pb200_ctx {
     size_t smem_optin = 0;
     // tuning knobs (0 = automatic)
     int64_t tile_points = 0, threads = 0, stages = 0, ctas_per_sm = 0, force_direct = 0;
+    int64_t knn_init_radius = -1, knn_stats = 0, knn_per_axis_codes = 0;  // experiments / diagnostics
     // scratch
     void* d_scratch = nullptr;  // small device scratch (counters, partials)
     size_t d_scratch_bytes = 0;
@@ -76,5 +77,23 @@ int ensure_device(pb200_ctx* ctx);
 // device scratch of at least `bytes` (grown lazily); contents undefined
 int scratch(pb200_ctx* ctx, size_t bytes, void** out);
 int validate_desc(const pb200_buffer_desc* d, const char* what);
+
+// Stream-ordered temporary (cudaMallocAsync from the device's default pool, whose release threshold the context raises
+// so that the multi-GB sort / tree buffers of repeated calls are recycled instead of going back to the driver).
+// Freed behind the work already queued on the stream: no host synchronisation is needed before it goes out of scope.
+struct DevTmp {
+    void* p = nullptr;
+    cudaStream_t st = nullptr;
+    DevTmp() = default;
+    DevTmp(const DevTmp&) = delete;
+    DevTmp& operator=(const DevTmp&) = delete;
+    ~DevTmp() { release(); }
+    void release() { if (p) cudaFreeAsync(p, st); p = nullptr; }
+    cudaError_t alloc(cudaStream_t s, size_t bytes) {
+        release();
+        st = s;
+        return cudaMallocAsync(&p, bytes ? bytes : 1, s);
+    }
+};
 
 }  // namespace pb200

@@ -5,13 +5,18 @@
 // `nearests(point, k)` per point (:108).  Tree shape is not part of the contract; the RESULT is: the k points with the
 // smallest squared distance ((dx*dx + dy*dy) + dz*dz in f64), the query itself included, ascending.  Here:
 //   K10  63-bit Morton codes inside the global AABB (expand_bits_by_3, math/bitmanip.rs:2-10)
-//   K8   radix sort of (code, index)
-//   K11  Karras-style hierarchy from the sorted codes (ties broken by position in the sorted array) + bottom-up
-//        refit of conservative f32 boxes with per-node arrival counters
-//   K12  one thread per query in Morton order, stack traversal nearest-child-first, exact f64 distances, a sorted
-//        k-list ordered by (d2, original index); a subtree is skipped only if its box distance is > the current worst
+//   K8   radix sort of (code, index); positions gathered into Morton order (padded with +inf to whole buckets)
+//   K11  BUCKETS of 8 consecutive sorted points are the leaves; a Karras-style radix hierarchy is built over the first
+//        code of every bucket (ties broken by bucket number).  One 64-byte record per internal node holds BOTH child
+//        boxes (conservative f32, rounded outwards) and the split, so a visit is four 16-byte loads and decides on both
+//        children at once; boxes are refitted bottom-up with per-node arrival counters.
+//   K12  one thread per query, queries in Morton order (a warp walks neighbouring buckets, so node and bucket loads hit
+//        L1).  The k-list lives in REGISTERS (template KMAX, worst element in slot 0, fully unrolled insertion) ordered
+//        by (d2, original index); it is primed from the query's own and adjacent buckets before the top-down,
+//        nearest-child-first traversal, so the pruning bound is tight from the first node on.  A subtree is skipped
+//        only if its box distance (same f64 association as the point distance, hence monotone) is > the current worst.
 //   K13  centroid -> covariance (neighbour order) -> closed-form cubic -> cross products, as written in the reference
-//        (the eigenvalue shift at :446-449 is a no-op there)
+//        (the eigenvalue shift at :446-449 is a no-op there); fused into the query kernel.
 #include <cub/device/device_radix_sort.cuh>
 
 #include <cfloat>
@@ -21,19 +26,24 @@
 
 namespace pb200 {
 
-constexpr uint32_t LEAF_FLAG = 0x80000000u;
+constexpr int BUCKET = 8;                 // points per leaf
+constexpr uint32_t LEFT_LEAF = 0x80000000u, RIGHT_LEAF = 0x40000000u, SPLIT_MASK = 0x3FFFFFFFu;
+constexpr uint32_t NONE = 0xFFFFFFFFu;
 constexpr int MAX_K = 64;
-constexpr int STACK_DEPTH = 128;  // >= 63 code bits + 32 tie-break bits + slack
+constexpr int STACK_DEPTH = 128;          // >= 63 code bits + 28 tie-break bits + slack
 
-struct DBuf {
-    void* p = nullptr;
-    ~DBuf() { if (p) cudaFree(p); }
-    cudaError_t alloc(size_t bytes) { return cudaMalloc(&p, bytes ? bytes : 1); }
+struct alignas(16) Node {                 // 64 B: what one traversal step needs
+    float l[6];                           // left child box: lo xyz, hi xyz
+    float r[6];                           // right child box
+    uint32_t split;                       // gamma | LEFT_LEAF | RIGHT_LEAF; children are gamma and gamma + 1
+    uint32_t first, last;                 // bucket range covered by this node
+    uint32_t pad;
 };
+static_assert(sizeof(Node) == 64, "node record is one 64-byte line");
 
 struct Lbvh {
-    uint32_t n = 0;
-    DBuf codes, codes2, idx, idx2, tmp, spos, left, right, parent, leaf_parent, boxes, counters;
+    uint32_t n = 0, nb = 0;
+    DevTmp codes, codes2, idx, idx2, tmp, spos, nodes, parent, leaf_parent, counters;
     const double* sorted_pos() const { return (const double*)spos.p; }
 };
 
@@ -62,93 +72,95 @@ __global__ void __launch_bounds__(256) lbvh_codes_kernel(const uint8_t* __restri
     }
 }
 
+// positions in Morton order; the tail of the last bucket is +inf (such a point is never accepted: d2 = inf)
 __global__ void __launch_bounds__(256) gather_positions_kernel(const uint8_t* __restrict__ base, unsigned long long stride,
-                                                               const uint32_t* __restrict__ idx, uint32_t n, double* __restrict__ out) {
-    for (uint32_t i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x) {
-        const double* p = reinterpret_cast<const double*>(base + (unsigned long long)idx[i] * stride);
-        out[3 * (size_t)i] = p[0];
-        out[3 * (size_t)i + 1] = p[1];
-        out[3 * (size_t)i + 2] = p[2];
+                                                               const uint32_t* __restrict__ idx, uint32_t n, uint32_t n_padded,
+                                                               double* __restrict__ out) {
+    for (uint32_t i = blockIdx.x * blockDim.x + threadIdx.x; i < n_padded; i += gridDim.x * blockDim.x) {
+        double x = INFINITY, y = INFINITY, z = INFINITY;
+        if (i < n) {
+            const double* p = reinterpret_cast<const double*>(base + (unsigned long long)idx[i] * stride);
+            x = p[0]; y = p[1]; z = p[2];
+        }
+        out[3 * (size_t)i] = x;
+        out[3 * (size_t)i + 1] = y;
+        out[3 * (size_t)i + 2] = z;
     }
 }
 
-__device__ __forceinline__ int delta(const unsigned long long* __restrict__ codes, uint32_t n, long long i, long long j) {
-    if (j < 0 || j >= (long long)n) return -1;
-    const unsigned long long a = codes[i], b = codes[j];
-    if (a == b) return 64 + __clz((unsigned)i ^ (unsigned)j);  // duplicates: fall back to the position in the sorted array
+// common-prefix length of the keys of buckets i and j (key = code of the bucket's first point)
+__device__ __forceinline__ int delta(const unsigned long long* __restrict__ codes, uint32_t nb, long long i, long long j) {
+    if (j < 0 || j >= (long long)nb) return -1;
+    const unsigned long long a = codes[(size_t)i * BUCKET], b = codes[(size_t)j * BUCKET];
+    if (a == b) return 64 + __clz((unsigned)i ^ (unsigned)j);  // duplicates: fall back to the bucket number
     return __clzll((long long)(a ^ b));
 }
 
-__global__ void __launch_bounds__(256) lbvh_hierarchy_kernel(const unsigned long long* __restrict__ codes, uint32_t n,
-                                                             uint32_t* __restrict__ left, uint32_t* __restrict__ right,
-                                                             uint32_t* __restrict__ parent, uint32_t* __restrict__ leaf_parent) {
-    for (uint32_t t0 = blockIdx.x * blockDim.x + threadIdx.x; t0 + 1 < n; t0 += gridDim.x * blockDim.x) {
+__global__ void __launch_bounds__(256) lbvh_hierarchy_kernel(const unsigned long long* __restrict__ codes, uint32_t nb,
+                                                             Node* __restrict__ nodes, uint32_t* __restrict__ parent,
+                                                             uint32_t* __restrict__ leaf_parent) {
+    for (uint32_t t0 = blockIdx.x * blockDim.x + threadIdx.x; t0 + 1 < nb; t0 += gridDim.x * blockDim.x) {
         const long long i = t0;
-        const int d = (delta(codes, n, i, i + 1) - delta(codes, n, i, i - 1)) >= 0 ? 1 : -1;
-        const int dmin = delta(codes, n, i, i - d);
+        const int d = (delta(codes, nb, i, i + 1) - delta(codes, nb, i, i - 1)) >= 0 ? 1 : -1;
+        const int dmin = delta(codes, nb, i, i - d);
         long long lmax = 2;
-        while (delta(codes, n, i, i + lmax * d) > dmin) lmax *= 2;
+        while (delta(codes, nb, i, i + lmax * d) > dmin) lmax *= 2;
         long long l = 0;
         for (long long t = lmax / 2; t >= 1; t /= 2)
-            if (delta(codes, n, i, i + (l + t) * d) > dmin) l += t;
+            if (delta(codes, nb, i, i + (l + t) * d) > dmin) l += t;
         const long long j = i + l * d;
-        const int dnode = delta(codes, n, i, j);
+        const int dnode = delta(codes, nb, i, j);
         long long s = 0, t = l;
         do {
             t = (t + 1) >> 1;
-            if (delta(codes, n, i, i + (s + t) * d) > dnode) s += t;
+            if (delta(codes, nb, i, i + (s + t) * d) > dnode) s += t;
         } while (t > 1);
         const long long gamma = i + s * d + (d < 0 ? d : 0);
         const long long lo = i < j ? i : j, hi = i < j ? j : i;
-        const uint32_t lc = (lo == gamma) ? ((uint32_t)gamma | LEAF_FLAG) : (uint32_t)gamma;
-        const uint32_t rc = (hi == gamma + 1) ? ((uint32_t)(gamma + 1) | LEAF_FLAG) : (uint32_t)(gamma + 1);
-        left[i] = lc;
-        right[i] = rc;
-        if (lc & LEAF_FLAG) leaf_parent[lc & ~LEAF_FLAG] = (uint32_t)i; else parent[lc] = (uint32_t)i;
-        if (rc & LEAF_FLAG) leaf_parent[rc & ~LEAF_FLAG] = (uint32_t)i; else parent[rc] = (uint32_t)i;
-        if (i == 0) parent[0] = 0xFFFFFFFFu;
+        const bool ll = lo == gamma, rl = hi == gamma + 1;
+        nodes[i].split = (uint32_t)gamma | (ll ? LEFT_LEAF : 0u) | (rl ? RIGHT_LEAF : 0u);
+        nodes[i].first = (uint32_t)lo;
+        nodes[i].last = (uint32_t)hi;
+        if (ll) leaf_parent[gamma] = (uint32_t)i; else parent[gamma] = (uint32_t)i;
+        if (rl) leaf_parent[gamma + 1] = (uint32_t)i; else parent[gamma + 1] = (uint32_t)i;
+        if (i == 0) parent[0] = NONE;
     }
 }
 
-struct Box { float lo[3], hi[3]; };
-
-__device__ __forceinline__ Box child_box(uint32_t c, const double* __restrict__ spos, const Box* __restrict__ boxes) {
-    if (c & LEAF_FLAG) {
-        const double* p = spos + 3 * (size_t)(c & ~LEAF_FLAG);
-        Box b;
-        for (int a = 0; a < 3; ++a) { b.lo[a] = __double2float_rd(p[a]); b.hi[a] = __double2float_ru(p[a]); }
-        return b;
-    }
-    // written by another SM during this launch: read through L2 (a neighbouring box may sit in a stale L1 line)
-    const float* f = reinterpret_cast<const float*>(&boxes[c]);
-    Box b;
-    for (int a = 0; a < 3; ++a) { b.lo[a] = __ldcg(f + a); b.hi[a] = __ldcg(f + 3 + a); }
-    return b;
-}
-
-__global__ void __launch_bounds__(256) lbvh_refit_kernel(uint32_t n, const uint32_t* __restrict__ left, const uint32_t* __restrict__ right,
-                                                         const uint32_t* __restrict__ parent, const uint32_t* __restrict__ leaf_parent,
-                                                         const double* __restrict__ spos, Box* boxes, uint32_t* counters) {
-    for (uint32_t i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x) {
-        uint32_t node = leaf_parent[i];
-        while (node != 0xFFFFFFFFu) {
-            if (atomicAdd(&counters[node], 1u) == 0u) break;  // the second arrival owns the node
+// one thread per bucket: box of its points, then climb; the second arrival at a node owns it
+__global__ void __launch_bounds__(256) lbvh_refit_kernel(uint32_t n, uint32_t nb, Node* nodes, const uint32_t* __restrict__ parent,
+                                                         const uint32_t* __restrict__ leaf_parent,
+                                                         const double* __restrict__ spos, uint32_t* counters) {
+    for (uint32_t b = blockIdx.x * blockDim.x + threadIdx.x; b < nb; b += gridDim.x * blockDim.x) {
+        float lo[3] = {INFINITY, INFINITY, INFINITY}, hi[3] = {-INFINITY, -INFINITY, -INFINITY};
+        const uint32_t p0 = b * BUCKET, p1 = (p0 + BUCKET < n) ? p0 + BUCKET : n;
+        for (uint32_t p = p0; p < p1; ++p)
+            for (int a = 0; a < 3; ++a) {
+                const double v = spos[3 * (size_t)p + a];
+                lo[a] = fminf(lo[a], __double2float_rd(v));
+                hi[a] = fmaxf(hi[a], __double2float_ru(v));
+            }
+        uint32_t child = b, node = leaf_parent[b];
+        while (node != NONE) {
+            Node* nd = nodes + node;
+            const bool is_left = child == (nd->split & SPLIT_MASK);  // the left child (leaf or node) is number gamma
+            float* mine = is_left ? nd->l : nd->r;
+            for (int a = 0; a < 3; ++a) { __stcg(mine + a, lo[a]); __stcg(mine + 3 + a, hi[a]); }
+            __threadfence();  // publish the box before the arrival is counted
+            if (atomicAdd(&counters[node], 1u) == 0u) break;
             __threadfence();
-            const Box a = child_box(left[node], spos, boxes), b = child_box(right[node], spos, boxes);
-            Box u;
-            for (int c = 0; c < 3; ++c) { u.lo[c] = fminf(a.lo[c], b.lo[c]); u.hi[c] = fmaxf(a.hi[c], b.hi[c]); }
-            // volatile-style publication: write, then fence before the parent's counter is touched
-            boxes[node] = u;
-            __threadfence();
+            const float* other = is_left ? nd->r : nd->l;  // written by another SM during this launch: read through L2
+            for (int a = 0; a < 3; ++a) { lo[a] = fminf(lo[a], __ldcg(other + a)); hi[a] = fmaxf(hi[a], __ldcg(other + 3 + a)); }
+            child = node;
             node = parent[node];
         }
     }
 }
 
-__device__ __forceinline__ double box_dist2(const Box& b, double qx, double qy, double qz) {
-    const double dx = fmax(fmax((double)b.lo[0] - qx, 0.0), qx - (double)b.hi[0]);
-    const double dy = fmax(fmax((double)b.lo[1] - qy, 0.0), qy - (double)b.hi[1]);
-    const double dz = fmax(fmax((double)b.lo[2] - qz, 0.0), qz - (double)b.hi[2]);
+__device__ __forceinline__ double box_dist2(float lx, float ly, float lz, float hx, float hy, float hz, double qx, double qy, double qz) {
+    const double dx = fmax(fmax((double)lx - qx, 0.0), qx - (double)hx);
+    const double dy = fmax(fmax((double)ly - qy, 0.0), qy - (double)hy);
+    const double dz = fmax(fmax((double)lz - qz, 0.0), qz - (double)hz);
     return __dadd_rn(__dadd_rn(__dmul_rn(dx, dx), __dmul_rn(dy, dy)), __dmul_rn(dz, dz));
 }
 
@@ -250,96 +262,196 @@ __device__ void estimate_normal(const uint8_t* __restrict__ base, unsigned long 
 }
 
 struct QueryArgs {
-    uint32_t n, k;
-    const double* spos;        // positions in Morton order
+    uint32_t n, nb, k, init_radius;
+    const double* spos;        // positions in Morton order, padded to nb * BUCKET points
     const uint32_t* sidx;      // original index of sorted position i
-    const uint32_t *left, *right;
-    const Box* boxes;
+    const Node* nodes;
     double radius2;            // < 0: pure kNN
     uint32_t* idx_out;         // n*k (original order), nullable
     double* d2_out;            // n*k, nullable
     uint32_t* counts_out;      // n, nullable (radius search)
-    const uint8_t* pos_base;   // original-order positions (normals)
-    unsigned long long pos_stride;
     double* normals_out;       // n*3, nullable
     double* curvature_out;     // n, nullable
 };
 
-// MODE 0: kNN lists, 1: radius search, 2: normals
-template <int MODE>
+// The k best candidates, ordered by (d2, original index), worst first: slot 0 is the pruning bound, slots >= k are
+// unused.  Empty slots hold (+inf, NONE), which every real candidate beats.  All indices are compile-time constants
+// after unrolling, so the list stays in registers.
+template <int KMAX>
+struct KList {
+    double d[KMAX];
+    uint32_t j[KMAX];  // SORTED position of the neighbour (its original index is sidx[j], needed for ties only)
+    __device__ __forceinline__ void init() {
+#pragma unroll KMAX <= 32 ? KMAX : 1
+        for (int s = 0; s < KMAX; ++s) { d[s] = INFINITY; j[s] = NONE; }
+    }
+    __device__ __forceinline__ double worst() const { return d[0]; }
+    __device__ __forceinline__ void offer(double d2, uint32_t jj, uint32_t k, double limit, const uint32_t* __restrict__ sidx) {
+        if (!(d2 <= limit)) return;  // also rejects NaN and the +inf padding
+        if (d2 > d[0]) return;
+        if (d2 == d[0] && !(sidx[jj] < sidx[j[0]])) return;
+        if constexpr (KMAX > 32) {  // too long for registers: plain insertion in local memory
+            uint32_t s = 0;
+            while (s + 1 < k && (d[s + 1] > d2 || (d[s + 1] == d2 && sidx[j[s + 1]] > sidx[jj]))) {
+                d[s] = d[s + 1];
+                j[s] = j[s + 1];
+                ++s;
+            }
+            d[s] = d2;
+            j[s] = jj;
+            return;
+        }
+        // Branch-free insertion.  c[s] = "slot s is in use and worse than the candidate"; it holds for a prefix of the
+        // slots (the list is sorted, worst first; c[0] holds by the tests above).  The candidate lands in the last
+        // slot of that prefix, everything before it moves one slot towards 0, the old slot 0 drops out:
+        //     new[s] = c[s+1] ? old[s+1] : (c[s] ? candidate : old[s])
+        // Exact distance ties need the original indices (two loads each): handled by the same formula with a tie-aware
+        // predicate, on a path that is only taken when some slot really ties.
+        bool tie = false;
+#pragma unroll
+        for (int s = 1; s < KMAX; ++s) tie = tie || d[s] == d2;
+        if (!tie) {
+            bool cs = true;
+#pragma unroll
+            for (int s = 0; s < KMAX; ++s) {
+                const bool cn = (s + 1 < KMAX) && (uint32_t)(s + 1) < k && d[s + 1 < KMAX ? s + 1 : s] > d2;
+                const double nd = d[s + 1 < KMAX ? s + 1 : s];
+                const uint32_t nj = j[s + 1 < KMAX ? s + 1 : s];
+                d[s] = cn ? nd : (cs ? d2 : d[s]);
+                j[s] = cn ? nj : (cs ? jj : j[s]);
+                cs = cn;
+            }
+        } else {
+            const uint32_t my = sidx[jj];
+            bool cs = true;
+#pragma unroll
+            for (int s = 0; s < KMAX; ++s) {
+                const double nd = d[s + 1 < KMAX ? s + 1 : s];
+                const uint32_t nj = j[s + 1 < KMAX ? s + 1 : s];
+                bool cn = (s + 1 < KMAX) && (uint32_t)(s + 1) < k;
+                if (cn) cn = nd > d2 || (nd == d2 && sidx[nj] > my);
+                d[s] = cn ? nd : (cs ? d2 : d[s]);
+                j[s] = cn ? nj : (cs ? jj : j[s]);
+                cs = cn;
+            }
+        }
+    }
+};
+
+// MODE 0: kNN lists, 1: radius search, 2: normals, 3: kNN traversal statistics (diagnostics)
+// Control flow is arranged so that the (fully unrolled, KMAX-long) list insertion is instantiated exactly once:
+// buckets to scan are queued as a range [pend_lo, pend_hi) -- the priming range first, then the one or two leaf
+// children of the visited node, which are consecutive buckets by construction (gamma, gamma + 1).
+template <int KMAX, int MODE>
 __global__ void __launch_bounds__(128) lbvh_query_kernel(QueryArgs a) {
     const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
     if (i >= a.n) return;
     const double qx = a.spos[3 * (size_t)i], qy = a.spos[3 * (size_t)i + 1], qz = a.spos[3 * (size_t)i + 2];
-    const uint32_t self = a.sidx[i];
     const uint32_t k = a.k;
-    double bd[MAX_K];
-    uint32_t bi[MAX_K];
-    uint32_t cnt = 0;
     const double limit = MODE == 1 ? a.radius2 : DBL_MAX;
-    auto worst = [&]() { return cnt == k ? bd[k - 1] : limit; };
-    auto offer = [&](double d2, uint32_t id) {
-        if (!(d2 <= limit)) return;  // also rejects NaN distances
-        if (cnt == k && !(d2 < bd[k - 1] || (d2 == bd[k - 1] && id < bi[k - 1]))) return;
-        uint32_t pos = cnt < k ? cnt : k - 1;
-        while (pos > 0 && (d2 < bd[pos - 1] || (d2 == bd[pos - 1] && id < bi[pos - 1]))) { bd[pos] = bd[pos - 1]; bi[pos] = bi[pos - 1]; --pos; }
-        bd[pos] = d2;
-        bi[pos] = id;
-        if (cnt < k) ++cnt;
-    };
-    if (a.n == 1) {
-        offer(0.0, self);
-    } else {
-        uint32_t stack[STACK_DEPTH];
-        int sp = 0;
-        uint32_t node = 0;  // root
-        while (true) {
-            const uint32_t cl = a.left[node], cr = a.right[node];
-            double dl, dr;
-            if (cl & LEAF_FLAG) {
-                const double* p = a.spos + 3 * (size_t)(cl & ~LEAF_FLAG);
-                const double dx = p[0] - qx, dy = p[1] - qy, dz = p[2] - qz;
-                dl = __dadd_rn(__dadd_rn(__dmul_rn(dx, dx), __dmul_rn(dy, dy)), __dmul_rn(dz, dz));
-                offer(dl, a.sidx[cl & ~LEAF_FLAG]);
-                dl = DBL_MAX;  // consumed
-            } else dl = box_dist2(a.boxes[cl], qx, qy, qz);
-            if (cr & LEAF_FLAG) {
-                const double* p = a.spos + 3 * (size_t)(cr & ~LEAF_FLAG);
-                const double dx = p[0] - qx, dy = p[1] - qy, dz = p[2] - qz;
-                dr = __dadd_rn(__dadd_rn(__dmul_rn(dx, dx), __dmul_rn(dy, dy)), __dmul_rn(dz, dz));
-                offer(dr, a.sidx[cr & ~LEAF_FLAG]);
-                dr = DBL_MAX;
-            } else dr = box_dist2(a.boxes[cr], qx, qy, qz);
-            const bool vl = !(cl & LEAF_FLAG) && dl <= worst(), vr = !(cr & LEAF_FLAG) && dr <= worst();
-            if (vl && vr) {
-                const bool left_first = dl <= dr;
-                if (sp < STACK_DEPTH) stack[sp++] = left_first ? cr : cl;
-                node = left_first ? cl : cr;
-            } else if (vl) node = cl;
-            else if (vr) node = cr;
-            else {
-                // pop, re-checking the bound: the list may have tightened since the push
-                bool found = false;
-                while (sp > 0) {
-                    const uint32_t c = stack[--sp];
-                    if (box_dist2(a.boxes[c], qx, qy, qz) <= worst()) { node = c; found = true; break; }
-                }
-                if (!found) break;
+    const uint32_t* __restrict__ sidx = a.sidx;
+    KList<KMAX> list;
+    list.init();
+    // prime the list from the query's own bucket and its neighbours in Morton order
+    const uint32_t qb = i / BUCKET;
+    const uint32_t ib0 = qb > a.init_radius ? qb - a.init_radius : 0u;
+    const uint32_t ib1 = (qb + a.init_radius < a.nb - 1) ? qb + a.init_radius : a.nb - 1;
+    uint32_t pend_lo = ib0, pend_hi = ib1 + 1;
+    bool more = a.nb > 1 && !(ib0 == 0 && ib1 == a.nb - 1);
+    uint32_t stack[STACK_DEPTH];
+    float stack_d[STACK_DEPTH];  // lower bound of the box distance at push time (rounded down)
+    int sp = 0;
+    uint32_t node = 0;  // root
+    uint32_t st_nodes = 0, st_buckets = 0, st_offers = 0;
+    while (true) {
+        for (uint32_t b = pend_lo; b < pend_hi; ++b) {
+            if (MODE == 3) ++st_buckets;
+            const double2* p = reinterpret_cast<const double2*>(a.spos) + (size_t)b * (BUCKET * 3 / 2);
+            double c[BUCKET * 3], dd[BUCKET];
+#pragma unroll
+            for (int t = 0; t < BUCKET * 3 / 2; ++t) { const double2 v = __ldg(p + t); c[2 * t] = v.x; c[2 * t + 1] = v.y; }
+            uint32_t cand = 0;
+            const double bound = list.worst();
+#pragma unroll
+            for (int t = 0; t < BUCKET; ++t) {
+                const double dx = c[3 * t] - qx, dy = c[3 * t + 1] - qy, dz = c[3 * t + 2] - qz;
+                dd[t] = __dadd_rn(__dadd_rn(__dmul_rn(dx, dx), __dmul_rn(dy, dy)), __dmul_rn(dz, dz));
+                cand |= (dd[t] <= bound) ? (1u << t) : 0u;
+            }
+            while (cand) {
+                const int t = __ffs((int)cand) - 1;
+                cand &= cand - 1;
+                double d2 = dd[0];
+#pragma unroll
+                for (int u = 1; u < BUCKET; ++u) d2 = (t == u) ? dd[u] : d2;
+                if (MODE == 3) ++st_offers;
+                list.offer(d2, b * BUCKET + (uint32_t)t, k, limit, sidx);
+            }
+        }
+        pend_lo = pend_hi = 0;
+        if (!more) break;
+        if (MODE == 3) ++st_nodes;
+        const float4* rec = reinterpret_cast<const float4*>(a.nodes + node);
+        const float4 r0 = __ldg(rec), r1 = __ldg(rec + 1), r2 = __ldg(rec + 2);
+        const uint32_t split = __ldg(reinterpret_cast<const uint32_t*>(rec + 3));
+        const double dl = box_dist2(r0.x, r0.y, r0.z, r0.w, r1.x, r1.y, qx, qy, qz);
+        const double dr = box_dist2(r1.z, r1.w, r2.x, r2.y, r2.z, r2.w, qx, qy, qz);
+        const uint32_t cl = split & SPLIT_MASK, cr = cl + 1;
+        const bool ll = (split & LEFT_LEAF) != 0, rl = (split & RIGHT_LEAF) != 0;
+        const double bound = list.worst();
+        const bool sl = ll && dl <= bound && (cl < ib0 || cl > ib1), sr = rl && dr <= bound && (cr < ib0 || cr > ib1);
+        if (sl || sr) { pend_lo = sl ? cl : cr; pend_hi = sr ? cr + 1 : cl + 1; }
+        const bool vl = !ll && dl <= bound, vr = !rl && dr <= bound;
+        if (vl && vr) {
+            const bool left_first = dl <= dr;
+            if (sp < STACK_DEPTH) {
+                stack[sp] = left_first ? cr : cl;
+                stack_d[sp++] = __double2float_rd(left_first ? dr : dl);
+            }
+            node = left_first ? cl : cr;
+        } else if (vl) node = cl;
+        else if (vr) node = cr;
+        else {
+            // pop, re-checking the bound: the list may have tightened since the push (the pending leaf scan of this
+            // node is not yet reflected -- conservative)
+            more = false;
+            while (sp > 0) {
+                --sp;
+                if ((double)stack_d[sp] <= bound) { node = stack[sp]; more = true; break; }
             }
         }
     }
+    const uint32_t self = sidx[i];
     if (MODE == 2) {
+        uint32_t nb[KMAX];  // ascending (d2, index) order = the order kd-tree's nearests() returns
+        uint32_t cnt = 0;
+#pragma unroll KMAX <= 32 ? KMAX : 1
+        for (int s = KMAX - 1; s >= 0; --s)
+            if ((uint32_t)s < k && list.j[s] != NONE) nb[cnt++] = list.j[s];
         double nrm[3], curv;
-        estimate_normal(a.pos_base, a.pos_stride, bi, cnt, nrm, &curv);
+        estimate_normal(reinterpret_cast<const uint8_t*>(a.spos), 24ull, nb, cnt, nrm, &curv);
         a.normals_out[3 * (size_t)self] = nrm[0];
         a.normals_out[3 * (size_t)self + 1] = nrm[1];
         a.normals_out[3 * (size_t)self + 2] = nrm[2];
         a.curvature_out[self] = curv;
         return;
     }
-    for (uint32_t j = 0; j < k; ++j) {
-        if (a.idx_out) a.idx_out[(size_t)self * k + j] = j < cnt ? bi[j] : 0xFFFFFFFFu;
-        if (a.d2_out) a.d2_out[(size_t)self * k + j] = j < cnt ? bd[j] : INFINITY;
+    if (MODE == 3) {  // (nodes visited, buckets scanned, candidates offered) per query
+        a.idx_out[(size_t)self * 3] = st_nodes;
+        a.idx_out[(size_t)self * 3 + 1] = st_buckets;
+        a.idx_out[(size_t)self * 3 + 2] = st_offers;
+        return;
+    }
+    uint32_t cnt = 0;
+#pragma unroll KMAX <= 32 ? KMAX : 1
+    for (int s = 0; s < KMAX; ++s) {
+        if ((uint32_t)s < k) {
+            const uint32_t o = k - 1u - (uint32_t)s;
+            const bool valid = list.j[s] != NONE;
+            cnt += valid ? 1u : 0u;
+            if (a.idx_out) a.idx_out[(size_t)self * k + o] = valid ? sidx[list.j[s]] : NONE;
+            if (a.d2_out) a.d2_out[(size_t)self * k + o] = list.d[s];
+        }
     }
     if (a.counts_out) a.counts_out[self] = cnt;
 }
@@ -350,7 +462,7 @@ static unsigned grid_for(uint64_t n, int sm, unsigned block = 256) {
 }
 
 // positions of `buf` as a device (base, stride) view; host buffers are staged
-static int device_positions(pb200_ctx* ctx, const pb200_buffer_desc* buf, DBuf* staged, const uint8_t** base, uint64_t* stride) {
+static int device_positions(pb200_ctx* ctx, const pb200_buffer_desc* buf, DevTmp* staged, const uint8_t** base, uint64_t* stride) {
     const int pi = pb200_layout_index_of(buf->layout, "Position3D", PB200_VEC3F64);
     if (pi < 0) return set_error(PB200_ERR_ATTR_NOT_FOUND, "buffer has no Vec3f64 Position3D attribute (view_attribute::<Vector3<f64>> would panic)");
     const pb200_attr& at = buf->layout->attrs[(size_t)pi];
@@ -359,7 +471,7 @@ static int device_positions(pb200_ctx* ctx, const pb200_buffer_desc* buf, DBuf* 
     else { *stride = at.size; p = (const uint8_t*)buf->columns[pi]; }
     if (buf->memspace == PB200_HOST) {
         const size_t bytes = (size_t)(buf->len * (*stride));
-        PB_CUDA(staged->alloc(bytes));
+        PB_CUDA(staged->alloc(ctx->stream, bytes));
         PB_CUDA(cudaMemcpyAsync(staged->p, p, bytes, cudaMemcpyHostToDevice, ctx->stream));
         p = (const uint8_t*)staged->p;
     }
@@ -371,6 +483,8 @@ static int device_positions(pb200_ctx* ctx, const pb200_buffer_desc* buf, DBuf* 
 static int build_lbvh(pb200_ctx* ctx, const uint8_t* base, uint64_t stride, uint32_t n, Lbvh* t) {
     cudaStream_t st = ctx->stream;
     t->n = n;
+    t->nb = (n + BUCKET - 1) / BUCKET;
+    const uint32_t nb = t->nb, n_padded = nb * BUCKET;
     // global AABB on the device-resident view (an SoA-like descriptor over the strided positions)
     pb200_layout l;
     pb200_attr a{};
@@ -391,38 +505,56 @@ static int build_lbvh(pb200_ctx* ctx, const uint8_t* base, uint64_t stride, uint
     double bmin[3], bmax[3];
     int some = 0;
     PB_TRY(pb200_calculate_bounds(ctx, &d, bmin, bmax, &some));
+    // Quantisation for the tree's Morton order: ONE scale for all axes (cubic cells), so that neighbours on the curve
+    // are neighbours in space even for 2.5-D clouds whose z extent is a fraction of x/y.  (pb200_morton_codes, the
+    // public Z-row entry point, quantises per axis inside the AABB.)
     double s[3];
-    for (int c = 0; c < 3; ++c) { const double e = bmax[c] - bmin[c]; s[c] = e > 0.0 ? 2097152.0 / e : 0.0; }
-    PB_CUDA(t->codes.alloc((size_t)n * 8)); PB_CUDA(t->codes2.alloc((size_t)n * 8));
-    PB_CUDA(t->idx.alloc((size_t)n * 4)); PB_CUDA(t->idx2.alloc((size_t)n * 4));
-    PB_CUDA(t->spos.alloc((size_t)n * 24));
+    double emax = 0.0;
+    for (int c = 0; c < 3; ++c) { const double e = bmax[c] - bmin[c]; if (e > emax) emax = e; }
+    for (int c = 0; c < 3; ++c) {
+        const double e = ctx->knn_per_axis_codes ? bmax[c] - bmin[c] : emax;
+        s[c] = e > 0.0 ? 2097152.0 / e : 0.0;
+    }
+    PB_CUDA(t->codes.alloc(st, (size_t)n * 8)); PB_CUDA(t->codes2.alloc(st, (size_t)n * 8));
+    PB_CUDA(t->idx.alloc(st, (size_t)n * 4)); PB_CUDA(t->idx2.alloc(st, (size_t)n * 4));
+    PB_CUDA(t->spos.alloc(st, (size_t)n_padded * 24));
     lbvh_codes_kernel<<<grid_for(n, ctx->sm_count), 256, 0, st>>>(base, stride, n, bmin[0], bmin[1], bmin[2], s[0], s[1], s[2],
                                                                   (unsigned long long*)t->codes.p, (uint32_t*)t->idx.p);
     g_launches++;
     size_t tmp_bytes = 0;
     cub::DeviceRadixSort::SortPairs(nullptr, tmp_bytes, (const unsigned long long*)t->codes.p, (unsigned long long*)t->codes2.p,
                                     (const uint32_t*)t->idx.p, (uint32_t*)t->idx2.p, (int)n, 0, 63, st);
-    PB_CUDA(t->tmp.alloc(tmp_bytes));
+    PB_CUDA(t->tmp.alloc(st, tmp_bytes));
     PB_CUDA(cub::DeviceRadixSort::SortPairs(t->tmp.p, tmp_bytes, (const unsigned long long*)t->codes.p, (unsigned long long*)t->codes2.p,
                                             (const uint32_t*)t->idx.p, (uint32_t*)t->idx2.p, (int)n, 0, 63, st));
     g_launches += 9;
-    gather_positions_kernel<<<grid_for(n, ctx->sm_count), 256, 0, st>>>(base, stride, (const uint32_t*)t->idx2.p, n, (double*)t->spos.p);
+    gather_positions_kernel<<<grid_for(n_padded, ctx->sm_count), 256, 0, st>>>(base, stride, (const uint32_t*)t->idx2.p, n, n_padded,
+                                                                               (double*)t->spos.p);
     g_launches++;
-    if (n >= 2) {
-        PB_CUDA(t->left.alloc((size_t)(n - 1) * 4)); PB_CUDA(t->right.alloc((size_t)(n - 1) * 4));
-        PB_CUDA(t->parent.alloc((size_t)(n - 1) * 4)); PB_CUDA(t->leaf_parent.alloc((size_t)n * 4));
-        PB_CUDA(t->boxes.alloc((size_t)(n - 1) * sizeof(Box))); PB_CUDA(t->counters.alloc((size_t)(n - 1) * 4));
-        PB_CUDA(cudaMemsetAsync(t->counters.p, 0, (size_t)(n - 1) * 4, st));
-        lbvh_hierarchy_kernel<<<grid_for(n - 1, ctx->sm_count), 256, 0, st>>>((const unsigned long long*)t->codes2.p, n, (uint32_t*)t->left.p,
-                                                                              (uint32_t*)t->right.p, (uint32_t*)t->parent.p, (uint32_t*)t->leaf_parent.p);
+    if (nb >= 2) {
+        PB_CUDA(t->nodes.alloc(st, (size_t)(nb - 1) * sizeof(Node)));
+        PB_CUDA(t->parent.alloc(st, (size_t)(nb - 1) * 4)); PB_CUDA(t->leaf_parent.alloc(st, (size_t)nb * 4));
+        PB_CUDA(t->counters.alloc(st, (size_t)(nb - 1) * 4));
+        PB_CUDA(cudaMemsetAsync(t->counters.p, 0, (size_t)(nb - 1) * 4, st));
+        lbvh_hierarchy_kernel<<<grid_for(nb - 1, ctx->sm_count), 256, 0, st>>>((const unsigned long long*)t->codes2.p, nb, (Node*)t->nodes.p,
+                                                                               (uint32_t*)t->parent.p, (uint32_t*)t->leaf_parent.p);
         g_launches++;
-        lbvh_refit_kernel<<<grid_for(n, ctx->sm_count), 256, 0, st>>>(n, (const uint32_t*)t->left.p, (const uint32_t*)t->right.p,
-                                                                      (const uint32_t*)t->parent.p, (const uint32_t*)t->leaf_parent.p,
-                                                                      (const double*)t->spos.p, (Box*)t->boxes.p, (uint32_t*)t->counters.p);
+        lbvh_refit_kernel<<<grid_for(nb, ctx->sm_count), 256, 0, st>>>(n, nb, (Node*)t->nodes.p, (const uint32_t*)t->parent.p,
+                                                                       (const uint32_t*)t->leaf_parent.p, (const double*)t->spos.p,
+                                                                       (uint32_t*)t->counters.p);
         g_launches++;
     }
     PB_CUDA(cudaGetLastError());
     return PB200_OK;
+}
+
+template <int KMAX>
+static void launch_query(int mode, const QueryArgs& a, cudaStream_t st) {
+    const unsigned blocks = (a.n + 127) / 128;
+    if (mode == 3) { if constexpr (KMAX == 16) lbvh_query_kernel<16, 3><<<blocks, 128, 0, st>>>(a); }
+    else if (mode == 0) lbvh_query_kernel<KMAX, 0><<<blocks, 128, 0, st>>>(a);
+    else if (mode == 1) lbvh_query_kernel<KMAX, 1><<<blocks, 128, 0, st>>>(a);
+    else lbvh_query_kernel<KMAX, 2><<<blocks, 128, 0, st>>>(a);
 }
 
 // run a query kernel; outputs may live in host memory (staged through device temporaries)
@@ -430,31 +562,33 @@ static int run_query(pb200_ctx* ctx, const pb200_buffer_desc* buf, int mode, uin
                      double* d2_out, uint32_t* counts_out, double* normals_out, double* curvature_out) {
     PB_TRY(validate_desc(buf, "buffer"));
     PB_TRY(ensure_device(ctx));
-    if (buf->len > 0x7FFFFFFFull) return set_error(PB200_ERR_UNSUPPORTED, "more than 2^31-1 points per call");
+    if (buf->len > 0x7FFFFFF0ull) return set_error(PB200_ERR_UNSUPPORTED, "more than 2^31-16 points per call");
     if (k == 0 || k > MAX_K) return set_error(PB200_ERR_UNSUPPORTED, "k must be in 1..%d", MAX_K);
     const uint32_t n = (uint32_t)buf->len;
     if (n == 0) return PB200_OK;
-    DBuf staged;
+    DevTmp staged;
     const uint8_t* base = nullptr;
     uint64_t stride = 0;
     PB_TRY(device_positions(ctx, buf, &staged, &base, &stride));
     Lbvh tree;
     PB_TRY(build_lbvh(ctx, base, stride, n, &tree));
     const bool host = buf->memspace == PB200_HOST;
-    DBuf d_idx, d_d2, d_cnt, d_nrm, d_curv;
+    DevTmp d_idx, d_d2, d_cnt, d_nrm, d_curv;
     QueryArgs a{};
-    a.n = n; a.k = k;
+    a.n = n; a.nb = tree.nb; a.k = k;
+    // own bucket +- ceil(k/8) buckets (k = 16: 40 candidates).  Measured on the C4 stream (20 M points, k = 16): +-1 bucket
+    // 94 ms, +-2 42 ms, +-3..6 42-43 ms -- the mean work is the same, the slowest lane of a warp is not.
+    a.init_radius = (k + 7) / 8;
+    if (ctx->knn_init_radius >= 0) a.init_radius = (uint32_t)ctx->knn_init_radius;
     a.spos = tree.sorted_pos();
     a.sidx = (const uint32_t*)tree.idx2.p;
-    a.left = (const uint32_t*)tree.left.p; a.right = (const uint32_t*)tree.right.p;
-    a.boxes = (const Box*)tree.boxes.p;
+    a.nodes = (const Node*)tree.nodes.p;
     a.radius2 = mode == 1 ? radius * radius : -1.0;
-    a.pos_base = base; a.pos_stride = stride;
-    auto out_ptr = [&](void* user, DBuf& tmp, size_t bytes, void** dev) -> int {
+    auto out_ptr = [&](void* user, DevTmp& tmp, size_t bytes, void** dev) -> int {
         *dev = nullptr;
         if (!user) return PB200_OK;
         if (!host) { *dev = user; return PB200_OK; }
-        PB_CUDA(tmp.alloc(bytes));
+        PB_CUDA(tmp.alloc(ctx->stream, bytes));
         *dev = tmp.p;
         return PB200_OK;
     };
@@ -464,10 +598,10 @@ static int run_query(pb200_ctx* ctx, const pb200_buffer_desc* buf, int mode, uin
     PB_TRY(out_ptr(counts_out, d_cnt, (size_t)n * 4, &p)); a.counts_out = (uint32_t*)p;
     PB_TRY(out_ptr(normals_out, d_nrm, (size_t)n * 24, &p)); a.normals_out = (double*)p;
     PB_TRY(out_ptr(curvature_out, d_curv, (size_t)n * 8, &p)); a.curvature_out = (double*)p;
-    const unsigned blocks = (n + 127) / 128;
-    if (mode == 0) lbvh_query_kernel<0><<<blocks, 128, 0, ctx->stream>>>(a);
-    else if (mode == 1) lbvh_query_kernel<1><<<blocks, 128, 0, ctx->stream>>>(a);
-    else lbvh_query_kernel<2><<<blocks, 128, 0, ctx->stream>>>(a);
+    if (k <= 4) launch_query<4>(mode, a, ctx->stream);
+    else if (k <= 16) launch_query<16>(mode, a, ctx->stream);
+    else if (k <= 32) launch_query<32>(mode, a, ctx->stream);
+    else launch_query<64>(mode, a, ctx->stream);
     g_launches++;
     PB_CUDA(cudaGetLastError());
     if (host) {
@@ -476,9 +610,9 @@ static int run_query(pb200_ctx* ctx, const pb200_buffer_desc* buf, int mode, uin
         if (counts_out) PB_CUDA(cudaMemcpyAsync(counts_out, a.counts_out, (size_t)n * 4, cudaMemcpyDeviceToHost, ctx->stream));
         if (normals_out) PB_CUDA(cudaMemcpyAsync(normals_out, a.normals_out, (size_t)n * 24, cudaMemcpyDeviceToHost, ctx->stream));
         if (curvature_out) PB_CUDA(cudaMemcpyAsync(curvature_out, a.curvature_out, (size_t)n * 8, cudaMemcpyDeviceToHost, ctx->stream));
+        PB_CUDA(cudaStreamSynchronize(ctx->stream));  // host results must be complete on return
     }
-    // the tree and staging buffers die with this call: wait for the kernels that use them
-    PB_CUDA(cudaStreamSynchronize(ctx->stream));
+    // the tree and staging buffers are stream-ordered temporaries (DevTmp): released behind the kernels that use them
     return PB200_OK;
 }
 
@@ -490,7 +624,8 @@ extern "C" {
 
 int pb200_knn(pb200_ctx* ctx, const pb200_buffer_desc* buf, uint32_t k, uint32_t* idx_out, double* d2_out) {
     if (!ctx || !idx_out) return set_error(PB200_ERR_INVALID, "null argument");
-    return run_query(ctx, buf, 0, k, 0.0, idx_out, d2_out, nullptr, nullptr, nullptr);
+    const int mode = (ctx->knn_stats && k > 4 && k <= 16) ? 3 : 0;  // diagnostics: idx_out[3*i..] = traversal counters
+    return run_query(ctx, buf, mode, k, 0.0, idx_out, d2_out, nullptr, nullptr, nullptr);
 }
 
 int pb200_radius_search(pb200_ctx* ctx, const pb200_buffer_desc* buf, double radius, uint32_t max_neighbors,

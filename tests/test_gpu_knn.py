@@ -50,6 +50,36 @@ def test_knn_matches_bruteforce(name, pts, k):
     assert np.array_equal(idx, oidx), name
 
 
+@pytest.mark.parametrize("k", [5, 17, 32, 33, 64])
+def test_knn_every_list_width(k):
+    """k = 4/16/32 use register-resident lists of that width, k > 32 a local-memory list; bucket boundaries (8 points)
+    and partially filled last buckets are hit by the odd sizes"""
+    rng = np.random.default_rng(k)
+    for n in (k + 1, 8 * k + 3, 3001):
+        pts = rng.random((n, 3)) * [4, 4, 1]
+        oidx, od2 = O.knn_bruteforce(pts, pts, k)
+        idx, d2 = knn(cloud(pts), k)
+        assert np.array_equal(d2.cpu().numpy(), od2), (k, n)
+        assert np.array_equal(idx.cpu().numpy().view(np.uint32), oidx), (k, n)
+
+
+def test_knn_larger_cloud_deep_tree():
+    """30 k terrain points (3750 buckets): the traversal, not the priming range, finds most neighbours"""
+    pts = O.gen_terrain_positions(0, 30000)
+    oidx, od2 = O.knn_bruteforce(pts, pts, 16)
+    idx, d2 = knn(cloud(pts), 16)
+    assert np.array_equal(d2.cpu().numpy(), od2)
+    assert np.array_equal(idx.cpu().numpy().view(np.uint32), oidx)
+
+
+def test_knn_all_points_identical():
+    """every code and every distance ties: order must be by original index"""
+    pts = np.tile(np.array([[1.5, -2.0, 3.25]]), (100, 1))
+    idx, d2 = knn(cloud(pts), 16)
+    assert np.array_equal(idx.cpu().numpy().view(np.uint32), np.tile(np.arange(16, dtype=np.uint32), (100, 1)))
+    assert not d2.cpu().numpy().any()
+
+
 @pytest.mark.parametrize("columnar,device", [(True, "cuda"), (False, "cuda"), (True, "cpu"), (False, "cpu")])
 def test_knn_buffer_kinds_and_small_inputs(columnar, device):
     rng = np.random.default_rng(3)
