@@ -114,8 +114,8 @@ def _copy(ctx, dst, src, nbytes, memspace):
     if nbytes == 0:
         return
     if memspace == 1:
+        # the library-owned result buffer is released stream-ordered (behind this copy), so no synchronisation is needed
         check(lib().pb200_memcpy_d2d(ctx._h, C.c_void_p(dst), C.c_void_p(src), nbytes))
-        ctx.synchronize()  # the library-owned result buffer is freed right after the copy
     else:
         C.memmove(dst, src, nbytes)
 

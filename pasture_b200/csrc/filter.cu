@@ -132,11 +132,7 @@ __global__ void __launch_bounds__(FT_THREADS) filter_compact_kernel(const uint8_
     }
 }
 
-struct FBuf {
-    void* p = nullptr;
-    ~FBuf() { if (p) cudaFree(p); }
-    cudaError_t alloc(size_t b) { return cudaMalloc(&p, b ? b : 1); }
-};
+using FBuf = DevTmp;  // stream-ordered temporaries, recycled between calls
 
 static uint32_t word_bytes(uint64_t size, const void* sp, uint64_t ss, const void* dp, uint64_t ds) {
     uint32_t w = 16;
@@ -173,17 +169,17 @@ int pb200_filter_into(pb200_ctx* ctx, const pb200_buffer_desc* src, const uint8_
     if (src->kind == PB200_COLUMNAR)
         for (size_t a = 0; a < L.attrs.size(); ++a) s_cols[a] = (const uint8_t*)src->columns[a];
     if (src->memspace == PB200_HOST) {
-        PB_CUDA(d_mask_buf.alloc((size_t)n));
+        PB_CUDA(d_mask_buf.alloc(st, (size_t)n));
         PB_CUDA(cudaMemcpyAsync(d_mask_buf.p, mask, (size_t)n, cudaMemcpyHostToDevice, st));
         d_mask = (const uint8_t*)d_mask_buf.p;
         if (src->kind == PB200_INTERLEAVED) {
-            PB_CUDA(d_src_aos.alloc((size_t)(n * L.size)));
+            PB_CUDA(d_src_aos.alloc(st, (size_t)(n * L.size)));
             PB_CUDA(cudaMemcpyAsync(d_src_aos.p, src->aos, (size_t)(n * L.size), cudaMemcpyHostToDevice, st));
             s_aos = (const uint8_t*)d_src_aos.p;
         } else {
             for (size_t a = 0; a < L.attrs.size(); ++a) {
                 if (L.attrs[a].size == 0) continue;
-                PB_CUDA(d_src_cols[a].alloc((size_t)(n * L.attrs[a].size)));
+                PB_CUDA(d_src_cols[a].alloc(st, (size_t)(n * L.attrs[a].size)));
                 PB_CUDA(cudaMemcpyAsync(d_src_cols[a].p, src->columns[a], (size_t)(n * L.attrs[a].size), cudaMemcpyHostToDevice, st));
                 s_cols[a] = (const uint8_t*)d_src_cols[a].p;
             }
@@ -192,15 +188,15 @@ int pb200_filter_into(pb200_ctx* ctx, const pb200_buffer_desc* src, const uint8_
     // per-tile match counts -> exclusive scan -> total
     const uint32_t n_tiles = (uint32_t)((n + FT_TILE - 1) / FT_TILE);
     FBuf d_counts, d_offsets, d_tmp;
-    PB_CUDA(d_counts.alloc((size_t)n_tiles * 4));
-    PB_CUDA(d_offsets.alloc((size_t)n_tiles * 4));
+    PB_CUDA(d_counts.alloc(st, (size_t)n_tiles * 4));
+    PB_CUDA(d_offsets.alloc(st, (size_t)n_tiles * 4));
     const uint32_t cap = (uint32_t)ctx->sm_count * 8;
     const uint32_t blocks = n_tiles < cap ? n_tiles : cap;
     filter_count_kernel<<<blocks, FT_THREADS, 0, st>>>(d_mask, n, n_tiles, (uint32_t*)d_counts.p);
     g_launches++;
     size_t tmp_bytes = 0;
     cub::DeviceScan::ExclusiveSum(nullptr, tmp_bytes, (const uint32_t*)d_counts.p, (uint32_t*)d_offsets.p, (int)n_tiles, st);
-    PB_CUDA(d_tmp.alloc(tmp_bytes));
+    PB_CUDA(d_tmp.alloc(st, tmp_bytes));
     PB_CUDA(cub::DeviceScan::ExclusiveSum(d_tmp.p, tmp_bytes, (const uint32_t*)d_counts.p, (uint32_t*)d_offsets.p, (int)n_tiles, st));
     g_launches++;
     uint32_t last[2];
@@ -221,13 +217,13 @@ int pb200_filter_into(pb200_ctx* ctx, const pb200_buffer_desc* src, const uint8_
         for (size_t a = 0; a < L.attrs.size(); ++a) t_cols[a] = (uint8_t*)dst->columns[a];
     if (dst->memspace == PB200_HOST) {
         if (dst->kind == PB200_INTERLEAVED) {  // padding / bytes between attributes must survive: start from the target's bytes
-            PB_CUDA(d_dst_aos.alloc((size_t)(m * L.size)));
+            PB_CUDA(d_dst_aos.alloc(st, (size_t)(m * L.size)));
             PB_CUDA(cudaMemcpyAsync(d_dst_aos.p, dst->aos, (size_t)(m * L.size), cudaMemcpyHostToDevice, st));
             t_aos = (uint8_t*)d_dst_aos.p;
         } else {
             for (size_t a = 0; a < L.attrs.size(); ++a) {
                 if (L.attrs[a].size == 0) continue;
-                PB_CUDA(d_dst_cols[a].alloc((size_t)(m * L.attrs[a].size)));
+                PB_CUDA(d_dst_cols[a].alloc(st, (size_t)(m * L.attrs[a].size)));
                 t_cols[a] = (uint8_t*)d_dst_cols[a].p;
             }
         }

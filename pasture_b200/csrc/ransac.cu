@@ -24,11 +24,7 @@ constexpr int RS_WARPS = RS_THREADS / 32;
 constexpr int RS_PPT = 4;      // points per thread
 constexpr int RS_BATCH = 256;  // hypotheses per launch
 
-struct RBuf {
-    void* p = nullptr;
-    ~RBuf() { if (p) cudaFree(p); }
-    cudaError_t alloc(size_t b) { return cudaMalloc(&p, b ? b : 1); }
-};
+using RBuf = DevTmp;  // stream-ordered temporaries, recycled between calls
 
 // one hypothesis, pre-digested on the host. plane: m = a,b,c,d ; line: m = first xyz, v = second - first
 struct Hyp {
@@ -171,7 +167,7 @@ static int ransac_positions(pb200_ctx* ctx, const pb200_buffer_desc* buf, Positi
     else { P->stride = at.size; p = (const uint8_t*)buf->columns[pi]; }
     if (buf->memspace == PB200_HOST) {
         const size_t bytes = (size_t)(buf->len * P->stride);
-        PB_CUDA(P->staged.alloc(bytes));
+        PB_CUDA(P->staged.alloc(ctx->stream, bytes));
         PB_CUDA(cudaMemcpyAsync(P->staged.p, p, bytes, cudaMemcpyHostToDevice, ctx->stream));
         p = (const uint8_t*)P->staged.p;
     }
@@ -195,8 +191,8 @@ static int rank_models(pb200_ctx* ctx, const Positions& P, uint64_t n, int kind,
     std::vector<Hyp> hyps((size_t)n_models);
     for (uint64_t h = 0; h < n_models; ++h) hyps[(size_t)h] = make_hyp(kind, models + w * h, thr);
     RBuf d_h, d_r;
-    PB_CUDA(d_h.alloc(sizeof(Hyp) * (size_t)n_models));
-    PB_CUDA(d_r.alloc(8 * (size_t)n_models));
+    PB_CUDA(d_h.alloc(ctx->stream, sizeof(Hyp) * (size_t)n_models));
+    PB_CUDA(d_r.alloc(ctx->stream, 8 * (size_t)n_models));
     PB_CUDA(cudaMemcpyAsync(d_h.p, hyps.data(), sizeof(Hyp) * (size_t)n_models, cudaMemcpyHostToDevice, ctx->stream));
     PB_CUDA(cudaMemsetAsync(d_r.p, 0, 8 * (size_t)n_models, ctx->stream));
     const unsigned long long chunk = (unsigned long long)RS_THREADS * RS_PPT;
@@ -218,8 +214,8 @@ static int model_inliers(pb200_ctx* ctx, const Positions& P, uint64_t n, int kin
                          uint64_t* indices, uint64_t capacity, uint64_t* count) {
     const Hyp h = make_hyp(kind, model, thr);
     RBuf d_flags, d_idx, d_num, d_tmp;
-    PB_CUDA(d_flags.alloc((size_t)n));
-    PB_CUDA(d_num.alloc(8));
+    PB_CUDA(d_flags.alloc(ctx->stream, (size_t)n));
+    PB_CUDA(d_num.alloc(ctx->stream, 8));
     const unsigned long long cap = (unsigned long long)ctx->sm_count * 16;
     const unsigned blocks = (unsigned)(((n + 255) / 256) < cap ? ((n + 255) / 256) : cap);
     if (kind == 0) ransac_flags_kernel<0><<<blocks, 256, 0, ctx->stream>>>(P.base, P.stride, n, h, (uint8_t*)d_flags.p);
@@ -229,13 +225,13 @@ static int model_inliers(pb200_ctx* ctx, const Positions& P, uint64_t n, int kin
     // the select writes up to n indices: go through a device buffer of full size unless the caller's device buffer has room
     uint64_t* d_out = indices;
     if (host || capacity < n) {
-        PB_CUDA(d_idx.alloc(8 * (size_t)n));
+        PB_CUDA(d_idx.alloc(ctx->stream, 8 * (size_t)n));
         d_out = (uint64_t*)d_idx.p;
     }
     thrust::counting_iterator<unsigned long long> it(0);
     size_t tmp = 0;
     cub::DeviceSelect::Flagged(nullptr, tmp, it, (const uint8_t*)d_flags.p, (unsigned long long*)d_out, (unsigned long long*)d_num.p, (long long)n, ctx->stream);
-    PB_CUDA(d_tmp.alloc(tmp));
+    PB_CUDA(d_tmp.alloc(ctx->stream, tmp));
     PB_CUDA(cub::DeviceSelect::Flagged(d_tmp.p, tmp, it, (const uint8_t*)d_flags.p, (unsigned long long*)d_out, (unsigned long long*)d_num.p, (long long)n, ctx->stream));
     g_launches++;
     unsigned long long m = 0;
@@ -280,8 +276,8 @@ static int models_from_sample_indices(pb200_ctx* ctx, const Positions& P, int ki
     const int per = kind == 0 ? 3 : 2, w = kind == 0 ? 4 : 6;
     const size_t cnt = (size_t)n_models * per;
     RBuf d_s, d_p;
-    PB_CUDA(d_s.alloc(8 * cnt));
-    PB_CUDA(d_p.alloc(24 * cnt));
+    PB_CUDA(d_s.alloc(ctx->stream, 8 * cnt));
+    PB_CUDA(d_p.alloc(ctx->stream, 24 * cnt));
     PB_CUDA(cudaMemcpyAsync(d_s.p, samples, 8 * cnt, cudaMemcpyHostToDevice, ctx->stream));
     gather_samples_kernel<<<(unsigned)((cnt + 127) / 128), 128, 0, ctx->stream>>>(P.base, P.stride, (const unsigned long long*)d_s.p, (uint32_t)cnt, (double*)d_p.p);
     g_launches++;

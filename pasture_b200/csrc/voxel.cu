@@ -5,7 +5,12 @@
 //   create_markers_for_axis (:54-79)            host: the same running sum (sequential by definition), uploaded
 //   find_leaf per point (:22-51, linear scan)   K7 voxel_key_kernel: O(1) guess + local search on the exact markers,
 //                                               nearest-marker fix-up, packed key (ix,iy,iz)
-//   sorted Vec<Voxel> with insert (:141-152)    K8 stable LSD radix sort of (key, point index) over the significant bits
+//   sorted Vec<Voxel> with insert (:141-152)    K8 stable LSD radix sort over the significant key bits.  When key bits +
+//                                               index bits <= 64 (100 M points at 0.1 m: 34 + 27) the point index rides in
+//                                               the low bits of ONE u64 and the sort is keys-only: 16 B/point/pass
+//                                               instead of 24, and stability keeps input order inside a voxel for free
+//   voxel boundaries                            K8b head count per 2048-point tile -> scan of the tile counts -> emit
+//                                               (segment starts, voxel keys, unpacked point indices): 16 B/point read
 //   per-voxel attribute reduction (:168-689)    K9 one thread per voxel walks its points IN INPUT ORDER (stable sort),
 //                                               so f64 sums round exactly like the reference's sequential loops
 // Output order = lexicographic (ix,iy,iz) = ascending packed key.
@@ -52,8 +57,9 @@ __device__ __forceinline__ unsigned long long leaf_index(double p, const double*
     return i;
 }
 
+// idx_bits > 0: packed mode, keys[i] = voxel key << idx_bits | i (no index array)
 __global__ void __launch_bounds__(256) voxel_key_kernel(const uint8_t* __restrict__ pos_base, unsigned long long stride,
-                                                        unsigned long long n, AxisGrid g,
+                                                        unsigned long long n, AxisGrid g, unsigned idx_bits,
                                                         unsigned long long* __restrict__ keys, uint32_t* __restrict__ idx) {
     const unsigned long long step = (unsigned long long)gridDim.x * blockDim.x;
     for (unsigned long long i = (unsigned long long)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += step) {
@@ -61,30 +67,116 @@ __global__ void __launch_bounds__(256) voxel_key_kernel(const uint8_t* __restric
         const unsigned long long ix = leaf_index(p[0], g.markers[0], g.n[0], g.bmin[0], g.inv_leaf[0]);
         const unsigned long long iy = leaf_index(p[1], g.markers[1], g.n[1], g.bmin[1], g.inv_leaf[1]);
         const unsigned long long iz = leaf_index(p[2], g.markers[2], g.n[2], g.bmin[2], g.inv_leaf[2]);
-        keys[i] = (((ix << g.bits_y) | iy) << g.bits_z) | iz;
-        idx[i] = (uint32_t)i;
+        const unsigned long long key = (((ix << g.bits_y) | iy) << g.bits_z) | iz;
+        if (idx_bits) keys[i] = (key << idx_bits) | i;
+        else { keys[i] = key; idx[i] = (uint32_t)i; }
     }
 }
 
-__global__ void __launch_bounds__(256) head_flags_kernel(const unsigned long long* __restrict__ keys, unsigned long long n,
-                                                         uint32_t* __restrict__ flags) {
-    const unsigned long long step = (unsigned long long)gridDim.x * blockDim.x;
-    for (unsigned long long i = (unsigned long long)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += step)
-        flags[i] = (i == 0 || keys[i] != keys[i - 1]) ? 1u : 0u;
+// ---- voxel boundaries in the sorted key array ---------------------------------------------------------------------
+// A tile is HT_ROWS rows of HT_THREADS consecutive elements; thread t owns element r * HT_THREADS + t of every row, so
+// all loads are coalesced.  An element is a head if its voxel key differs from its predecessor's.
+constexpr int HT_THREADS = 256, HT_ROWS = 8, HT_TILE = HT_THREADS * HT_ROWS;
+
+__device__ __forceinline__ uint32_t tile_heads(const unsigned long long* __restrict__ keys, unsigned long long n, unsigned shift,
+                                               unsigned long long base, unsigned long long (&k)[HT_ROWS]) {
+    uint32_t flags = 0;
+#pragma unroll
+    for (int r = 0; r < HT_ROWS; ++r) {
+        const unsigned long long i = base + (unsigned long long)r * HT_THREADS + threadIdx.x;
+        k[r] = 0;
+        if (i < n) {
+            k[r] = keys[i];
+            const bool head = i == 0 || (keys[i - 1] >> shift) != (k[r] >> shift);
+            flags |= head ? (1u << r) : 0u;
+        }
+    }
+    return flags;
 }
 
-// seg[i] = exclusive scan of the head flags + own flag - 1 = voxel id of sorted position i
-__global__ void __launch_bounds__(256) segment_starts_kernel(const uint32_t* __restrict__ flags,
-                                                             const uint32_t* __restrict__ excl, unsigned long long n,
-                                                             uint32_t* __restrict__ starts,
-                                                             const unsigned long long* __restrict__ keys,
-                                                             unsigned long long* __restrict__ voxel_keys) {
-    const unsigned long long step = (unsigned long long)gridDim.x * blockDim.x;
-    for (unsigned long long i = (unsigned long long)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += step)
-        if (flags[i]) {
-            starts[excl[i]] = (uint32_t)i;
-            voxel_keys[excl[i]] = keys[i];
+__global__ void __launch_bounds__(HT_THREADS) heads_count_kernel(const unsigned long long* __restrict__ keys, unsigned long long n,
+                                                                 unsigned shift, uint32_t* __restrict__ tile_counts) {
+    __shared__ uint32_t warp_sum[HT_THREADS / 32];
+    unsigned long long k[HT_ROWS];
+    uint32_t c = __popc(tile_heads(keys, n, shift, (unsigned long long)blockIdx.x * HT_TILE, k));
+    for (int o = 16; o > 0; o >>= 1) c += __shfl_xor_sync(0xffffffffu, c, o);
+    if ((threadIdx.x & 31) == 0) warp_sum[threadIdx.x >> 5] = c;
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        uint32_t t = 0;
+        for (int w = 0; w < HT_THREADS / 32; ++w) t += warp_sum[w];
+        tile_counts[blockIdx.x] = t;
+    }
+}
+
+// exclusive scan of the tile counts in place (one CTA; a 100 M-point cloud has 48 829 tiles), total -> *total_out
+__global__ void __launch_bounds__(1024) tile_scan_kernel(uint32_t* __restrict__ counts, uint32_t n_tiles, uint32_t* __restrict__ total_out) {
+    __shared__ uint32_t warp_sum[32];
+    __shared__ uint32_t carry_s;
+    if (threadIdx.x == 0) carry_s = 0;
+    __syncthreads();
+    for (uint32_t base = 0; base < n_tiles; base += 1024) {
+        const uint32_t i = base + threadIdx.x;
+        const uint32_t v = i < n_tiles ? counts[i] : 0u;
+        uint32_t x = v;
+        for (int o = 1; o < 32; o <<= 1) { const uint32_t y = __shfl_up_sync(0xffffffffu, x, o); if ((int)(threadIdx.x & 31) >= o) x += y; }
+        if ((threadIdx.x & 31) == 31) warp_sum[threadIdx.x >> 5] = x;
+        __syncthreads();
+        if (threadIdx.x < 32) {
+            uint32_t w = warp_sum[threadIdx.x];
+            for (int o = 1; o < 32; o <<= 1) { const uint32_t y = __shfl_up_sync(0xffffffffu, w, o); if ((int)threadIdx.x >= o) w += y; }
+            warp_sum[threadIdx.x] = w;  // inclusive over warps
         }
+        __syncthreads();
+        const uint32_t carry = carry_s;
+        const uint32_t before = (threadIdx.x >> 5) ? warp_sum[(threadIdx.x >> 5) - 1] : 0u;
+        if (i < n_tiles) counts[i] = carry + before + x - v;
+        __syncthreads();
+        if (threadIdx.x == 1023) carry_s = carry + before + x;
+        __syncthreads();
+    }
+    if (threadIdx.x == 0) *total_out = carry_s;
+}
+
+// starts[rank] = sorted position of the rank-th voxel's first point, voxel_keys[rank] = its key; in packed mode the point
+// indices are unpacked into idx_out on the way (the keys are being read anyway)
+__global__ void __launch_bounds__(HT_THREADS) heads_emit_kernel(const unsigned long long* __restrict__ keys, unsigned long long n,
+                                                                unsigned shift, const uint32_t* __restrict__ tile_offsets,
+                                                                uint32_t n_voxels, uint32_t* __restrict__ starts,
+                                                                unsigned long long* __restrict__ voxel_keys,
+                                                                uint32_t* __restrict__ idx_out) {
+    __shared__ uint32_t part[HT_ROWS][HT_THREADS / 32];  // heads per (row, warp), then exclusive prefix in row-major order
+    unsigned long long k[HT_ROWS];
+    const unsigned long long base = (unsigned long long)blockIdx.x * HT_TILE;
+    const uint32_t flags = tile_heads(keys, n, shift, base, k);
+    const uint32_t lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    uint32_t lane_rank[HT_ROWS];
+#pragma unroll
+    for (int r = 0; r < HT_ROWS; ++r) {
+        const uint32_t b = __ballot_sync(0xffffffffu, (flags >> r) & 1u);
+        lane_rank[r] = __popc(b & ((1u << lane) - 1u));
+        if (lane == 0) part[r][warp] = __popc(b);
+    }
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        uint32_t run = tile_offsets[blockIdx.x];
+        for (int r = 0; r < HT_ROWS; ++r)
+            for (int w = 0; w < HT_THREADS / 32; ++w) { const uint32_t c = part[r][w]; part[r][w] = run; run += c; }
+    }
+    __syncthreads();
+    const unsigned long long idx_mask = shift ? ((1ull << shift) - 1ull) : 0ull;
+#pragma unroll
+    for (int r = 0; r < HT_ROWS; ++r) {
+        const unsigned long long i = base + (unsigned long long)r * HT_THREADS + threadIdx.x;
+        if (i >= n) continue;
+        if (idx_out) idx_out[i] = (uint32_t)(k[r] & idx_mask);
+        if ((flags >> r) & 1u) {
+            const uint32_t rank = part[r][warp] + lane_rank[r];
+            starts[rank] = (uint32_t)i;
+            voxel_keys[rank] = k[r] >> shift;
+        }
+    }
+    if (blockIdx.x == 0 && threadIdx.x == 0) starts[n_voxels] = (uint32_t)n;
 }
 
 template <class T>
@@ -203,13 +295,15 @@ __global__ void __launch_bounds__(256) max_occupancy_kernel(const uint32_t* __re
 }
 
 template <class S>
-__global__ void __launch_bounds__(256) mode_keys_kernel(const uint32_t* __restrict__ flags, const uint32_t* __restrict__ excl,
+__global__ void __launch_bounds__(256) mode_keys_kernel(const uint32_t* __restrict__ starts, uint32_t n_voxels,
                                                         const uint32_t* __restrict__ sorted_idx, unsigned long long n,
                                                         const uint8_t* __restrict__ src, unsigned long long stride, int aligned,
                                                         unsigned long long* __restrict__ keys) {
     const unsigned long long step = (unsigned long long)gridDim.x * blockDim.x;
     for (unsigned long long i = (unsigned long long)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += step) {
-        const unsigned long long voxel = (unsigned long long)excl[i] + flags[i] - 1ull;
+        uint32_t lo = 0, hi = n_voxels;  // voxel of sorted position i: last v with starts[v] <= i
+        while (hi - lo > 1) { const uint32_t mid = lo + (hi - lo) / 2; if (starts[mid] <= i) lo = mid; else hi = mid; }
+        const unsigned long long voxel = lo;
         const long long val = (long long)ld_attr<S>(src + (unsigned long long)sorted_idx[i] * stride, aligned != 0);
         constexpr long long bias = (S(-1) < S(0)) ? 32768 : 0;  // keeps signed values ordered as unsigned 16-bit fields
         keys[i] = (voxel << 16) | (unsigned long long)((val + bias) & 0xFFFF);
@@ -292,12 +386,6 @@ static unsigned bits_for(unsigned long long count) {  // bits needed for indices
     return b;
 }
 
-struct DeviceBuf {  // RAII for temporaries
-    void* p = nullptr;
-    ~DeviceBuf() { if (p) cudaFree(p); }
-    cudaError_t alloc(size_t bytes) { return cudaMalloc(&p, bytes ? bytes : 1); }
-};
-
 }  // namespace pb200
 
 using namespace pb200;
@@ -339,7 +427,7 @@ int pb200_voxelgrid_filter(pb200_ctx* ctx, const pb200_buffer_desc* src, double 
     cudaStream_t st = ctx->stream;
 
     // ---- source attribute streams on the device --------------------------------------------------------------
-    std::vector<DeviceBuf> staged(src->layout->attrs.size() + 1);
+    std::vector<DevTmp> staged(src->layout->attrs.size() + 1);
     const uint8_t* d_aos = nullptr;
     std::vector<const uint8_t*> d_cols(src->layout->attrs.size(), nullptr);
     auto need = [&](int idx) -> int {
@@ -350,13 +438,13 @@ int pb200_voxelgrid_filter(pb200_ctx* ctx, const pb200_buffer_desc* src, double 
         }
         if (src->kind == PB200_INTERLEAVED) {
             if (!d_aos) {
-                PB_CUDA(staged.back().alloc((size_t)(n * src->layout->size)));
+                PB_CUDA(staged.back().alloc(st, (size_t)(n * src->layout->size)));
                 PB_CUDA(cudaMemcpyAsync(staged.back().p, src->aos, (size_t)(n * src->layout->size), cudaMemcpyHostToDevice, st));
                 d_aos = (const uint8_t*)staged.back().p;
             }
         } else if (!d_cols[(size_t)idx]) {
             const size_t bytes = (size_t)(n * src->layout->attrs[(size_t)idx].size);
-            PB_CUDA(staged[(size_t)idx].alloc(bytes));
+            PB_CUDA(staged[(size_t)idx].alloc(st, bytes));
             PB_CUDA(cudaMemcpyAsync(staged[(size_t)idx].p, src->columns[idx], bytes, cudaMemcpyHostToDevice, st));
             d_cols[(size_t)idx] = (const uint8_t*)staged[(size_t)idx].p;
         }
@@ -392,9 +480,9 @@ int pb200_voxelgrid_filter(pb200_ctx* ctx, const pb200_buffer_desc* src, double 
         }
     }
     const unsigned bits_x = bits_for(markers[0].size()), bits_y = bits_for(markers[1].size()), bits_z = bits_for(markers[2].size());
-    DeviceBuf d_markers;
+    DevTmp d_markers;
     const size_t nm_total = markers[0].size() + markers[1].size() + markers[2].size();
-    PB_CUDA(d_markers.alloc(nm_total * sizeof(double) + 8));
+    PB_CUDA(d_markers.alloc(st, nm_total * sizeof(double) + 8));
     AxisGrid grid;
     {
         size_t off = 0;
@@ -412,65 +500,78 @@ int pb200_voxelgrid_filter(pb200_ctx* ctx, const pb200_buffer_desc* src, double 
     }
 
     // ---- keys, sort, segments ---------------------------------------------------------------------------------
-    DeviceBuf d_keys, d_keys2, d_idx, d_idx2, d_flags, d_excl, d_tmp;
-    PB_CUDA(d_keys.alloc(n * 8)); PB_CUDA(d_keys2.alloc(n * 8));
-    PB_CUDA(d_idx.alloc(n * 4)); PB_CUDA(d_idx2.alloc(n * 4));
-    PB_CUDA(d_flags.alloc(n * 4)); PB_CUDA(d_excl.alloc(n * 4));
+    // packed mode: the point index rides in the low bits of the key, the sort is keys-only
+    const unsigned key_bits = bits_x + bits_y + bits_z, idx_bits_needed = bits_for(n);
+    const bool packed = key_bits + idx_bits_needed <= 64;
+    const unsigned shift = packed ? idx_bits_needed : 0;
+    DevTmp d_keys, d_keys2, d_idx, d_idx2, d_tmp, d_tiles;
+    PB_CUDA(d_keys.alloc(st, n * 8)); PB_CUDA(d_keys2.alloc(st, n * 8));
+    PB_CUDA(d_idx2.alloc(st, n * 4));
+    if (!packed) PB_CUDA(d_idx.alloc(st, n * 4));
     uint64_t pstride = 0;
     const uint8_t* ppos = attr_ptr(pi, &pstride);
     if (((uintptr_t)ppos & 7) || (pstride & 7)) return set_error(PB200_ERR_UNSUPPORTED, "POSITION_3D must be 8-byte aligned in memory");
     const unsigned long long cap = (unsigned long long)ctx->sm_count * 16;
     const unsigned blocks = (unsigned)(((n + 255) / 256) < cap ? ((n + 255) / 256) : cap);
-    voxel_key_kernel<<<blocks, 256, 0, st>>>(ppos, pstride, n, grid, (unsigned long long*)d_keys.p, (uint32_t*)d_idx.p);
+    voxel_key_kernel<<<blocks, 256, 0, st>>>(ppos, pstride, n, grid, shift, (unsigned long long*)d_keys.p, (uint32_t*)d_idx.p);
     g_launches++;
-    size_t tmp_bytes = 0, tmp2 = 0;
-    const int end_bit = (int)(bits_x + bits_y + bits_z);
-    cub::DeviceRadixSort::SortPairs(nullptr, tmp_bytes, (const unsigned long long*)d_keys.p, (unsigned long long*)d_keys2.p,
-                                    (const uint32_t*)d_idx.p, (uint32_t*)d_idx2.p, (int)n, 0, end_bit, st);
-    cub::DeviceScan::ExclusiveSum(nullptr, tmp2, (const uint32_t*)d_flags.p, (uint32_t*)d_excl.p, (int)n, st);
-    PB_CUDA(d_tmp.alloc(tmp_bytes > tmp2 ? tmp_bytes : tmp2));
-    PB_CUDA(cub::DeviceRadixSort::SortPairs(d_tmp.p, tmp_bytes, (const unsigned long long*)d_keys.p, (unsigned long long*)d_keys2.p,
-                                            (const uint32_t*)d_idx.p, (uint32_t*)d_idx2.p, (int)n, 0, end_bit, st));
-    g_launches += (uint64_t)((end_bit + 7) / 8) + 1;
-    head_flags_kernel<<<blocks, 256, 0, st>>>((const unsigned long long*)d_keys2.p, n, (uint32_t*)d_flags.p);
-    g_launches++;
-    PB_CUDA(cub::DeviceScan::ExclusiveSum(d_tmp.p, tmp2, (const uint32_t*)d_flags.p, (uint32_t*)d_excl.p, (int)n, st));
-    g_launches++;
-    uint32_t last[2];
-    PB_CUDA(cudaMemcpyAsync(&last[0], (uint32_t*)d_excl.p + (n - 1), 4, cudaMemcpyDeviceToHost, st));
-    PB_CUDA(cudaMemcpyAsync(&last[1], (uint32_t*)d_flags.p + (n - 1), 4, cudaMemcpyDeviceToHost, st));
+    size_t tmp_bytes = 0;
+    if (packed) {
+        cub::DeviceRadixSort::SortKeys(nullptr, tmp_bytes, (const unsigned long long*)d_keys.p, (unsigned long long*)d_keys2.p, (int)n,
+                                       (int)shift, (int)(shift + key_bits), st);
+        PB_CUDA(d_tmp.alloc(st, tmp_bytes));
+        PB_CUDA(cub::DeviceRadixSort::SortKeys(d_tmp.p, tmp_bytes, (const unsigned long long*)d_keys.p, (unsigned long long*)d_keys2.p, (int)n,
+                                               (int)shift, (int)(shift + key_bits), st));
+    } else {
+        cub::DeviceRadixSort::SortPairs(nullptr, tmp_bytes, (const unsigned long long*)d_keys.p, (unsigned long long*)d_keys2.p,
+                                        (const uint32_t*)d_idx.p, (uint32_t*)d_idx2.p, (int)n, 0, (int)key_bits, st);
+        PB_CUDA(d_tmp.alloc(st, tmp_bytes));
+        PB_CUDA(cub::DeviceRadixSort::SortPairs(d_tmp.p, tmp_bytes, (const unsigned long long*)d_keys.p, (unsigned long long*)d_keys2.p,
+                                                (const uint32_t*)d_idx.p, (uint32_t*)d_idx2.p, (int)n, 0, (int)key_bits, st));
+    }
+    g_launches += (uint64_t)((key_bits + 7) / 8) + 1;
+    // voxel boundaries: heads per tile -> scan -> emit
+    const uint32_t n_tiles = (uint32_t)((n + HT_TILE - 1) / HT_TILE);
+    PB_CUDA(d_tiles.alloc(st, ((size_t)n_tiles + 1) * 4));
+    uint32_t* d_total = (uint32_t*)d_tiles.p + n_tiles;
+    heads_count_kernel<<<n_tiles, HT_THREADS, 0, st>>>((const unsigned long long*)d_keys2.p, n, shift, (uint32_t*)d_tiles.p);
+    tile_scan_kernel<<<1, 1024, 0, st>>>((uint32_t*)d_tiles.p, n_tiles, d_total);
+    g_launches += 2;
+    uint32_t* h_total = (uint32_t*)ctx->h_scratch;
+    PB_CUDA(cudaMemcpyAsync(h_total, d_total, 4, cudaMemcpyDeviceToHost, st));
     PB_CUDA(cudaStreamSynchronize(st));
-    const uint64_t V = (uint64_t)last[0] + last[1];
-    DeviceBuf d_starts, d_vkeys;
-    PB_CUDA(d_starts.alloc((V + 1) * 4));
-    PB_CUDA(d_vkeys.alloc(V * 8 + 8));
-    segment_starts_kernel<<<blocks, 256, 0, st>>>((const uint32_t*)d_flags.p, (const uint32_t*)d_excl.p, n, (uint32_t*)d_starts.p,
-                                                  (const unsigned long long*)d_keys2.p, (unsigned long long*)d_vkeys.p);
+    const uint64_t V = *h_total;
+    DevTmp d_starts;
+    DevTmp d_vkeys;  // handed over to the result buffer on success (result memory comes from the same stream-ordered pool)
+    PB_CUDA(d_starts.alloc(st, (V + 1) * 4));
+    PB_CUDA(d_vkeys.alloc(st, V * 8 + 8));
+    heads_emit_kernel<<<n_tiles, HT_THREADS, 0, st>>>((const unsigned long long*)d_keys2.p, n, shift, (const uint32_t*)d_tiles.p, (uint32_t)V,
+                                                      (uint32_t*)d_starts.p, (unsigned long long*)d_vkeys.p, packed ? (uint32_t*)d_idx2.p : nullptr);
     g_launches++;
-    const uint32_t n32 = (uint32_t)n;
-    PB_CUDA(cudaMemcpyAsync((uint32_t*)d_starts.p + V, &n32, 4, cudaMemcpyHostToDevice, st));
 
     // the most crowded voxel decides how the mode attributes are reduced
     bool any_mode = false;
     for (const Rule* r : rules) any_mode = any_mode || r->kind == R_MODE || r->kind == R_MODE_BOOL;
     uint32_t max_occ = 0;
-    DeviceBuf d_mode_keys, d_mode_keys2, d_head, d_head2, d_best, d_mode_tmp;
+    DevTmp d_mode_keys, d_mode_keys2, d_head, d_head2, d_best, d_mode_tmp, d_occ;
     size_t mode_tmp_bytes = 0;
     if (any_mode) {
-        PB_CUDA(cudaMemsetAsync(d_tmp.p, 0, 4, st));  // d_tmp[0..3] doubles as the max counter (the sort is done)
-        max_occupancy_kernel<<<blocks, 256, 0, st>>>((const uint32_t*)d_starts.p, V, (uint32_t*)d_tmp.p);
+        PB_CUDA(d_occ.alloc(st, 4));
+        PB_CUDA(cudaMemsetAsync(d_occ.p, 0, 4, st));
+        max_occupancy_kernel<<<blocks, 256, 0, st>>>((const uint32_t*)d_starts.p, V, (uint32_t*)d_occ.p);
         g_launches++;
-        PB_CUDA(cudaMemcpyAsync(&max_occ, d_tmp.p, 4, cudaMemcpyDeviceToHost, st));
+        PB_CUDA(cudaMemcpyAsync(h_total, d_occ.p, 4, cudaMemcpyDeviceToHost, st));
         PB_CUDA(cudaStreamSynchronize(st));
+        max_occ = *h_total;
         if (max_occ > MODE_THREAD_LIMIT) {
-            PB_CUDA(d_mode_keys.alloc(n * 8)); PB_CUDA(d_mode_keys2.alloc(n * 8));
-            PB_CUDA(d_head.alloc(n * 4)); PB_CUDA(d_head2.alloc(n * 4));
-            PB_CUDA(d_best.alloc((V + 1) * 8));
+            PB_CUDA(d_mode_keys.alloc(st, n * 8)); PB_CUDA(d_mode_keys2.alloc(st, n * 8));
+            PB_CUDA(d_head.alloc(st, n * 4)); PB_CUDA(d_head2.alloc(st, n * 4));
+            PB_CUDA(d_best.alloc(st, (V + 1) * 8));
             size_t t1 = 0, t2 = 0;
             cub::DeviceRadixSort::SortKeys(nullptr, t1, (const unsigned long long*)d_mode_keys.p, (unsigned long long*)d_mode_keys2.p, (int)n, 0, 64, st);
             cub::DeviceScan::InclusiveScan(nullptr, t2, (const uint32_t*)d_head.p, (uint32_t*)d_head2.p, MaxU32(), (int)n, st);
             mode_tmp_bytes = t1 > t2 ? t1 : t2;
-            PB_CUDA(d_mode_tmp.alloc(mode_tmp_bytes));
+            PB_CUDA(d_mode_tmp.alloc(st, mode_tmp_bytes));
         }
     }
 
@@ -483,14 +584,14 @@ int pb200_voxelgrid_filter(pb200_ctx* ctx, const pb200_buffer_desc* src, double 
     res->len = V;
     std::vector<void*> d_out(dst_layout->attrs.size(), nullptr);
     auto fail = [&](int rc) {
-        for (void* p : d_out) if (p) cudaFree(p);
-        if (res->d_packed_keys) cudaFree(res->d_packed_keys);
+        for (void* p : d_out) if (p) cudaFreeAsync(p, st);
+        if (res->d_packed_keys) cudaFreeAsync(res->d_packed_keys, st);
         delete res;
         return rc;
     };
     for (size_t a = 0; a < dst_layout->attrs.size(); ++a) {
-        cudaError_t e = cudaMalloc(&d_out[a], (size_t)(V * dst_layout->attrs[a].size) + 16);
-        if (e != cudaSuccess) return fail(cuda_error(e, "cudaMalloc(result column)"));
+        cudaError_t e = cudaMallocAsync(&d_out[a], (size_t)(V * dst_layout->attrs[a].size) + 16, st);
+        if (e != cudaSuccess) return fail(cuda_error(e, "cudaMallocAsync(result column)"));
         ReduceArgs ra;
         uint64_t sstride = 0;
         ra.src = attr_ptr(src_idx[a], &sstride);
@@ -506,11 +607,12 @@ int pb200_voxelgrid_filter(pb200_ctx* ctx, const pb200_buffer_desc* src, double 
         if (is_mode && max_occ > MODE_THREAD_LIMIT) {
             const uint32_t dt = rules[a]->dtype;
             unsigned long long* mk = (unsigned long long*)d_mode_keys.p;
-            const uint32_t *fl = (const uint32_t*)d_flags.p, *ex = (const uint32_t*)d_excl.p, *si2 = (const uint32_t*)d_idx2.p;
-            if (dt == PB200_U8) mode_keys_kernel<uint8_t><<<blocks, 256, 0, st>>>(fl, ex, si2, n, ra.src, sstride, ra.src_aligned, mk);
-            else if (dt == PB200_I8) mode_keys_kernel<int8_t><<<blocks, 256, 0, st>>>(fl, ex, si2, n, ra.src, sstride, ra.src_aligned, mk);
-            else if (dt == PB200_I16) mode_keys_kernel<int16_t><<<blocks, 256, 0, st>>>(fl, ex, si2, n, ra.src, sstride, ra.src_aligned, mk);
-            else mode_keys_kernel<uint16_t><<<blocks, 256, 0, st>>>(fl, ex, si2, n, ra.src, sstride, ra.src_aligned, mk);
+            const uint32_t *sts = (const uint32_t*)d_starts.p, *si2 = (const uint32_t*)d_idx2.p;
+            const uint32_t nv = (uint32_t)V;
+            if (dt == PB200_U8) mode_keys_kernel<uint8_t><<<blocks, 256, 0, st>>>(sts, nv, si2, n, ra.src, sstride, ra.src_aligned, mk);
+            else if (dt == PB200_I8) mode_keys_kernel<int8_t><<<blocks, 256, 0, st>>>(sts, nv, si2, n, ra.src, sstride, ra.src_aligned, mk);
+            else if (dt == PB200_I16) mode_keys_kernel<int16_t><<<blocks, 256, 0, st>>>(sts, nv, si2, n, ra.src, sstride, ra.src_aligned, mk);
+            else mode_keys_kernel<uint16_t><<<blocks, 256, 0, st>>>(sts, nv, si2, n, ra.src, sstride, ra.src_aligned, mk);
             size_t tb = mode_tmp_bytes;
             cudaError_t e2 = cub::DeviceRadixSort::SortKeys(d_mode_tmp.p, tb, (const unsigned long long*)mk, (unsigned long long*)d_mode_keys2.p,
                                                             (int)n, 0, 16 + (int)bits_for(V + 1), st);
@@ -534,10 +636,9 @@ int pb200_voxelgrid_filter(pb200_ctx* ctx, const pb200_buffer_desc* src, double 
     }
     // packed voxel keys stay on the device; pb200_result_buffer_voxel_keys unpacks them on demand
     res->d_packed_keys = d_vkeys.p;
-    d_vkeys.p = nullptr;
+    d_vkeys.p = nullptr;  // ownership moves to the result
     res->bits_y = bits_y;
     res->bits_z = bits_z;
-    cudaStreamSynchronize(st);  // temporaries (sorted keys, indices, staged inputs) are released on return
     // ---- hand the result over in the requested memory layout / space -------------------------------------------
     pb200_buffer_desc stage;
     stage.layout = dst_layout;
@@ -547,14 +648,17 @@ int pb200_voxelgrid_filter(pb200_ctx* ctx, const pb200_buffer_desc* src, double 
     stage.aos = nullptr;
     stage.columns = d_out.data();
     if (dst_kind == PB200_COLUMNAR && dst_memspace == PB200_DEVICE) {
+        // device-resident columnar result: nothing to wait for -- the temporaries are stream-ordered (DevTmp) and the
+        // result is valid for work queued on the context's stream
         res->columns = d_out;
         *out = res;
         return PB200_OK;
     }
+    cudaStreamSynchronize(st);
     // allocate the final storage
     if (dst_kind == PB200_INTERLEAVED) {
         const size_t bytes = (size_t)(V * dst_layout->size) + 16;
-        if (dst_memspace == PB200_DEVICE) { if (cudaMalloc(&res->aos, bytes) != cudaSuccess) return fail(set_error(PB200_ERR_OOM, "out of device memory")); cudaMemsetAsync(res->aos, 0, bytes, st); }
+        if (dst_memspace == PB200_DEVICE) { if (cudaMallocAsync(&res->aos, bytes, st) != cudaSuccess) return fail(set_error(PB200_ERR_OOM, "out of device memory")); cudaMemsetAsync(res->aos, 0, bytes, st); }
         else { res->aos = calloc(1, bytes); if (!res->aos) return fail(set_error(PB200_ERR_OOM, "out of host memory")); }
     } else {
         res->columns.assign(dst_layout->attrs.size(), nullptr);
@@ -578,7 +682,7 @@ int pb200_voxelgrid_filter(pb200_ctx* ctx, const pb200_buffer_desc* src, double 
         pb200_converter_destroy(cv);
         cudaStreamSynchronize(st);
     }
-    for (void* p : d_out) if (p) cudaFree(p);
+    for (void* p : d_out) if (p) cudaFreeAsync(p, st);
     if (rc < 0) {
         std::fill(d_out.begin(), d_out.end(), nullptr);
         pb200_result_buffer_destroy(res);
@@ -618,10 +722,11 @@ int pb200_result_buffer_voxel_keys(const pb200_result_buffer* r, uint64_t* keys_
 void pb200_result_buffer_destroy(pb200_result_buffer* r) {
     if (!r) return;
     if (r->ctx) cudaSetDevice(r->ctx->device);
-    if (r->d_packed_keys) cudaFree(r->d_packed_keys);
+    cudaStream_t st = r->ctx ? r->ctx->stream : nullptr;  // device memory goes back to the pool behind queued work
+    if (r->d_packed_keys) cudaFreeAsync(r->d_packed_keys, st);
     if (r->memspace == PB200_DEVICE) {
-        if (r->aos) cudaFree(r->aos);
-        for (void* p : r->columns) if (p) cudaFree(p);
+        if (r->aos) cudaFreeAsync(r->aos, st);
+        for (void* p : r->columns) if (p) cudaFreeAsync(p, st);
     } else {
         free(r->aos);
         for (void* p : r->columns) free(p);
