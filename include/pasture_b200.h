@@ -251,6 +251,33 @@ int pb200_result_buffer_desc(const pb200_result_buffer* r, pb200_buffer_desc* ou
 int pb200_result_buffer_voxel_keys(const pb200_result_buffer* r, uint64_t* keys_out);
 void pb200_result_buffer_destroy(pb200_result_buffer* r);
 
+/* ---- sharded voxel grid ------------------------------------------------------------------
+ * A cloud sharded by point range over several GPUs is filtered in three steps: (1) every shard reduces its points to
+ * PARTIALS on the grid of the GLOBAL bounding box (the all-reduced AABB: every shard derives the same markers,
+ * voxel_grid.rs:54-79, hence the same voxel keys); (2) partials are exchanged so that each rank holds all partials of a
+ * disjoint key range; (3) the rank merges them (sums added in source-rank order, counts added) and divides.  Voxel
+ * keys and counts equal the single-device filter exactly; centroids within 1e-9 relative (the f64 summation order
+ * differs between one in-order sum and a sum of per-shard sums).  POSITION_3D only. */
+typedef struct pb200_voxel_partials pb200_voxel_partials;
+typedef struct {
+  uint64_t len;           /* occupied voxels */
+  const uint64_t* keys;   /* device, ascending: (ix << (bits_y + bits_z)) | (iy << bits_z) | iz */
+  const uint32_t* counts; /* device: points per voxel */
+  const double* sums;     /* device: len * 3 position sums */
+  uint32_t bits_x, bits_y, bits_z;
+  uint64_t cells[3];      /* markers per axis of the global grid */
+} pb200_voxel_partials_desc;
+int pb200_voxelgrid_partials(pb200_ctx* ctx, const pb200_buffer_desc* src, double leaf_x, double leaf_y, double leaf_z,
+                             const double global_min[3], const double global_max[3], pb200_voxel_partials** out);
+/* keys / counts / sums: device arrays of m concatenated partials (source-rank order within equal keys is kept) */
+int pb200_voxelgrid_merge_partials(pb200_ctx* ctx, const uint64_t* keys, const uint32_t* counts, const double* sums,
+                                   uint64_t m, uint32_t bits_x, uint32_t bits_y, uint32_t bits_z,
+                                   pb200_voxel_partials** out);
+int pb200_voxel_partials_get(const pb200_voxel_partials* p, pb200_voxel_partials_desc* out);
+/* positions_out: device, len * 3 doubles: sums / count (voxel_grid.rs:382-386) */
+int pb200_voxel_partials_centroids(const pb200_voxel_partials* p, double* positions_out);
+void pb200_voxel_partials_destroy(pb200_voxel_partials* p);
+
 /* ---- kNN / radius / normals ------------------------------------------------------------------------ */
 /* KdTree::nearests(q, k) for every point of the buffer against the buffer itself
  * (normal_estimation.rs:103,108): k nearest by squared distance including the point itself, ascending.

@@ -485,6 +485,47 @@ def voxelgrid_filter(src, leaf, dst_layout, columnar=True, use_sort=False):
     return dst, keys[: dst.len].copy()
 
 
+def bits_for(count):
+    """bits needed for indices 0..count-1 (at least 1): the width of one axis in a packed voxel key"""
+    b = 1
+    while (1 << b) < count:
+        b += 1
+    return b
+
+
+def voxel_partials(pts, gmin, gmax, leaf):
+    """One shard's contribution to a sharded voxel grid, restated with the reference's own pieces: markers
+    of the GLOBAL box (voxel_grid.rs:54-79), find_leaf per point (:22-51), position sums in point order (:339-379
+    without the final division).  -> (packed keys int64 ascending, counts int32, sums [V,3], bits, cells)"""
+    pts = np.ascontiguousarray(pts, dtype=np.float64).reshape(-1, 3)
+    markers = [create_markers(gmin[c], gmax[c], leaf[c]) for c in range(3)]
+    bits = [bits_for(len(m)) for m in markers]
+    keys = np.zeros(len(pts), dtype=np.uint64)
+    for i, p in enumerate(pts):
+        ix, iy, iz = find_leaf(p, *markers)
+        keys[i] = (ix << (bits[1] + bits[2])) | (iy << bits[2]) | iz
+    k, c, s = merge_partials(keys.astype(np.int64), np.ones(len(pts), np.int32), pts)
+    return k, c, s, bits, [len(m) for m in markers]
+
+
+def merge_partials(keys, counts, sums):
+    """equal keys are added in the order given (stable), sequential f64 adds"""
+    keys = np.asarray(keys, dtype=np.int64)
+    order = np.argsort(keys, kind="stable")
+    uniq, starts, cnt = np.unique(keys[order], return_index=True, return_counts=True)
+    out_c = np.zeros(len(uniq), dtype=np.int32)
+    out_s = np.zeros((len(uniq), 3), dtype=np.float64)
+    for v, (s0, n) in enumerate(zip(starts, cnt)):
+        acc = np.zeros(3)
+        tot = 0
+        for j in order[s0:s0 + n]:
+            acc = acc + sums[j]
+            tot += int(counts[j])
+        out_s[v] = acc
+        out_c[v] = tot
+    return uniq, out_c, out_s
+
+
 def knn_bruteforce(pts, queries, k):
     pts = np.ascontiguousarray(pts, dtype=np.float64)
     queries = np.ascontiguousarray(queries, dtype=np.float64)

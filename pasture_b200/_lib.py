@@ -41,6 +41,12 @@ class LasWriteStats(C.Structure):
                 ("_pad", C.c_int32), ("bounds_min", C.c_double * 3), ("bounds_max", C.c_double * 3)]
 
 
+class VoxelPartialsDesc(C.Structure):
+    _fields_ = [("len", C.c_uint64), ("keys", C.c_void_p), ("counts", C.c_void_p), ("sums", C.c_void_p),
+                ("bits_x", C.c_uint32), ("bits_y", C.c_uint32), ("bits_z", C.c_uint32), ("_pad", C.c_uint32),
+                ("cells", C.c_uint64 * 3)]
+
+
 class ProjOp(C.Structure):
     _fields_ = [("kind", C.c_uint32), ("_pad", C.c_uint32), ("p", C.c_double * 12)]
 
@@ -120,6 +126,11 @@ SIGNATURES = {
     "pb200_result_buffer_desc": (i32, [vp, BD]),
     "pb200_result_buffer_voxel_keys": (i32, [vp, vp]),
     "pb200_result_buffer_destroy": (None, [vp]),
+    "pb200_voxelgrid_partials": (i32, [vp, BD, dbl, dbl, dbl, PD, PD, PVP]),
+    "pb200_voxelgrid_merge_partials": (i32, [vp, vp, vp, vp, u64, u32, u32, u32, PVP]),
+    "pb200_voxel_partials_get": (i32, [vp, C.POINTER(VoxelPartialsDesc)]),
+    "pb200_voxel_partials_centroids": (i32, [vp, vp]),
+    "pb200_voxel_partials_destroy": (None, [vp]),
     "pb200_knn": (i32, [vp, BD, u32, vp, vp]),
     "pb200_radius_search": (i32, [vp, BD, dbl, u32, vp, vp]),
     "pb200_compute_normals": (i32, [vp, BD, u32, vp, vp]),

@@ -5,7 +5,7 @@ import ctypes as C
 import numpy as np
 import torch
 
-from ._lib import BufferDesc, ProjOp, check, lib
+from ._lib import BufferDesc, ProjOp, VoxelPartialsDesc, check, lib
 from .containers import _NP, _VEC3, HashMapBuffer, VectorBuffer
 from .context import get_context
 from .layout import DT
@@ -108,6 +108,73 @@ def voxelgrid_filter(buffer, leafsize_x, leafsize_y, leafsize_z, filtered_layout
     finally:
         lib().pb200_result_buffer_destroy(h)
     return (out, keys) if return_keys else out
+
+
+class VoxelPartials:
+    """Per-voxel partial sums on a (global) voxel grid as device tensors: packed keys (int64 bit pattern of the u64 key
+    (ix << (bits_y + bits_z)) | (iy << bits_z) | iz, ascending), point counts (int32) and position sums [V, 3] f64.
+    `bits` = (bits_x, bits_y, bits_z), `cells` = markers per axis.  SURVEY 8e."""
+
+    def __init__(self, keys, counts, sums, bits, cells):
+        self.keys, self.counts, self.sums, self.bits, self.cells = keys, counts, sums, tuple(bits), tuple(cells)
+
+    def len(self):
+        return int(self.keys.numel())
+
+    def unpack_keys(self):
+        """-> [V, 3] int64 voxel indices (ix, iy, iz)"""
+        _, by, bz = self.bits
+        k = self.keys
+        return torch.stack([k >> (by + bz), (k >> bz) & ((1 << by) - 1), k & ((1 << bz) - 1)], 1)
+
+
+def _take_partials(ctx, h, want_centroids):
+    """copy a library-owned pb200_voxel_partials into torch tensors (stream-ordered) and release it"""
+    try:
+        d = VoxelPartialsDesc()
+        check(lib().pb200_voxel_partials_get(h, C.byref(d)))
+        v = int(d.len)
+        dev = torch.device("cuda", ctx.device)
+        keys = torch.empty(v, dtype=torch.int64, device=dev)
+        counts = torch.empty(v, dtype=torch.int32, device=dev)
+        sums = torch.empty((v, 3), dtype=torch.float64, device=dev)
+        cent = torch.empty((v, 3), dtype=torch.float64, device=dev) if want_centroids else None
+        if v:
+            check(lib().pb200_memcpy_d2d(ctx._h, C.c_void_p(keys.data_ptr()), C.c_void_p(d.keys), 8 * v))
+            check(lib().pb200_memcpy_d2d(ctx._h, C.c_void_p(counts.data_ptr()), C.c_void_p(d.counts), 4 * v))
+            check(lib().pb200_memcpy_d2d(ctx._h, C.c_void_p(sums.data_ptr()), C.c_void_p(d.sums), 24 * v))
+            if want_centroids:
+                check(lib().pb200_voxel_partials_centroids(h, C.c_void_p(cent.data_ptr())))
+        part = VoxelPartials(keys, counts, sums, (d.bits_x, d.bits_y, d.bits_z), tuple(d.cells))
+    finally:
+        lib().pb200_voxel_partials_destroy(h)
+    return (part, cent) if want_centroids else part
+
+
+def voxelgrid_partials(buffer, leafsize_x, leafsize_y, leafsize_z, global_bounds, ctx=None):
+    """one shard's contribution to a sharded voxel grid: partial sums on the grid of `global_bounds` (an AABB or a
+    (min, max) pair covering the WHOLE cloud, e.g. the all-reduced shard bounds)"""
+    ctx = ctx or get_context()
+    mn, mx = (global_bounds.min(), global_bounds.max()) if isinstance(global_bounds, AABB) else global_bounds
+    gmin, gmax = (C.c_double * 3)(*mn), (C.c_double * 3)(*mx)
+    d = buffer.desc()
+    h = C.c_void_p()
+    check(lib().pb200_voxelgrid_partials(ctx._h, C.byref(d), leafsize_x, leafsize_y, leafsize_z, gmin, gmax, C.byref(h)))
+    return _take_partials(ctx, h, False)
+
+
+def voxelgrid_merge_partials(keys, counts, sums, bits, cells=(0, 0, 0), ctx=None):
+    """merge concatenated partials (device tensors; equal keys are added in the order given = source-rank order)
+    -> (VoxelPartials with the totals, centroids [V, 3])"""
+    ctx = ctx or get_context()
+    keys, counts, sums = keys.contiguous(), counts.contiguous(), sums.contiguous()
+    assert keys.dtype == torch.int64 and counts.dtype == torch.int32 and sums.dtype == torch.float64
+    h = C.c_void_p()
+    check(lib().pb200_voxelgrid_merge_partials(ctx._h, C.c_void_p(keys.data_ptr()), C.c_void_p(counts.data_ptr()),
+                                               C.c_void_p(sums.data_ptr()), keys.numel(), bits[0], bits[1], bits[2], C.byref(h)))
+    part, cent = _take_partials(ctx, h, True)
+    part.cells = tuple(cells)
+    return part, cent
 
 
 def _copy(ctx, dst, src, nbytes, memspace):

@@ -33,6 +33,14 @@ struct pb200_result_buffer {
     unsigned bits_y = 0, bits_z = 0;
 };
 
+struct pb200_voxel_partials {
+    pb200_ctx* ctx = nullptr;
+    uint64_t len = 0;
+    void *keys = nullptr, *counts = nullptr, *sums = nullptr;  // device, from the stream-ordered pool
+    uint32_t bits_x = 0, bits_y = 0, bits_z = 0;
+    uint64_t cells[3] = {0, 0, 0};
+};
+
 namespace pb200 {
 
 struct AxisGrid {
@@ -386,6 +394,154 @@ static unsigned bits_for(unsigned long long count) {  // bits needed for indices
     return b;
 }
 
+// ---- sharded voxel grid: partial sums per shard, merge of exchanged partials ------------------------
+// per voxel of one shard: point count and position sums in point order (the division happens after the merge)
+__global__ void __launch_bounds__(128) voxel_partial_sums_kernel(const uint32_t* __restrict__ starts, const uint32_t* __restrict__ sorted_idx,
+                                                                 unsigned long long n_voxels, const uint8_t* __restrict__ pos,
+                                                                 unsigned long long stride, uint32_t* __restrict__ counts,
+                                                                 double* __restrict__ sums) {
+    const unsigned long long v = (unsigned long long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (v >= n_voxels) return;
+    const uint32_t b = starts[v], e = starts[v + 1];
+    double sx = 0.0, sy = 0.0, sz = 0.0;
+    for (uint32_t k = b; k < e; ++k) {
+        const double* p = reinterpret_cast<const double*>(pos + (unsigned long long)sorted_idx[k] * stride);
+        sx = __dadd_rn(sx, p[0]); sy = __dadd_rn(sy, p[1]); sz = __dadd_rn(sz, p[2]);
+    }
+    counts[v] = e - b;
+    sums[3 * v] = sx; sums[3 * v + 1] = sy; sums[3 * v + 2] = sz;
+}
+
+__global__ void __launch_bounds__(256) iota_kernel(uint32_t* __restrict__ out, unsigned long long n) {
+    const unsigned long long step = (unsigned long long)gridDim.x * blockDim.x;
+    for (unsigned long long i = (unsigned long long)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += step) out[i] = (uint32_t)i;
+}
+
+// per merged voxel: add up the partials in the order they were concatenated (= source rank order: the sort is stable)
+__global__ void __launch_bounds__(128) partials_merge_kernel(const uint32_t* __restrict__ starts, const uint32_t* __restrict__ sorted_idx,
+                                                             unsigned long long n_voxels, const uint32_t* __restrict__ in_counts,
+                                                             const double* __restrict__ in_sums, uint32_t* __restrict__ counts,
+                                                             double* __restrict__ sums) {
+    const unsigned long long v = (unsigned long long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (v >= n_voxels) return;
+    double sx = 0.0, sy = 0.0, sz = 0.0;
+    uint32_t c = 0;
+    for (uint32_t k = starts[v], e = starts[v + 1]; k < e; ++k) {
+        const uint32_t j = sorted_idx[k];
+        c += in_counts[j];
+        sx = __dadd_rn(sx, in_sums[3 * (size_t)j]); sy = __dadd_rn(sy, in_sums[3 * (size_t)j + 1]); sz = __dadd_rn(sz, in_sums[3 * (size_t)j + 2]);
+    }
+    counts[v] = c;
+    sums[3 * v] = sx; sums[3 * v + 1] = sy; sums[3 * v + 2] = sz;
+}
+
+// centroid = sum / count (voxel_grid.rs:382-386)
+__global__ void __launch_bounds__(256) partials_centroid_kernel(const uint32_t* __restrict__ counts, const double* __restrict__ sums,
+                                                                unsigned long long n_voxels, double* __restrict__ out) {
+    const unsigned long long step = (unsigned long long)gridDim.x * blockDim.x;
+    for (unsigned long long v = (unsigned long long)blockIdx.x * blockDim.x + threadIdx.x; v < n_voxels; v += step) {
+        const double c = (double)counts[v];
+        out[3 * v] = sums[3 * v] / c; out[3 * v + 1] = sums[3 * v + 1] / c; out[3 * v + 2] = sums[3 * v + 2] / c;
+    }
+}
+
+// Everything between the bounds and the per-voxel reductions: markers on the host (voxel_grid.rs:63-77), keys, sort,
+// voxel boundaries.  With the AABB of the WHOLE cloud every shard of a sharded cloud derives the same markers and
+// therefore the same global voxel keys.
+struct VoxelIndex {
+    DevTmp sorted_keys, sorted_idx, starts, voxel_keys;  // N, N, V+1, V
+    uint64_t V = 0;
+    unsigned bits_x = 0, bits_y = 0, bits_z = 0;
+    uint64_t cells[3] = {0, 0, 0};
+};
+
+static int build_voxel_index(pb200_ctx* ctx, const uint8_t* ppos, uint64_t pstride, uint64_t n, const double bmin[3],
+                             const double bmax[3], const double leaf[3], VoxelIndex* vi) {
+    cudaStream_t st = ctx->stream;
+    std::vector<double> markers[3];
+    for (int c = 0; c < 3; ++c) {  // voxel_grid.rs:63-77 running sum
+        double cur = bmin[c];
+        while (cur < bmax[c]) {
+            cur += leaf[c];
+            markers[c].push_back(cur);
+            if (markers[c].size() > (1u << 21)) return set_error(PB200_ERR_UNSUPPORTED, "more than 2^21 voxels along one axis");
+        }
+    }
+    const unsigned bits_x = bits_for(markers[0].size()), bits_y = bits_for(markers[1].size()), bits_z = bits_for(markers[2].size());
+    vi->bits_x = bits_x; vi->bits_y = bits_y; vi->bits_z = bits_z;
+    for (int c = 0; c < 3; ++c) vi->cells[c] = markers[c].size();
+    DevTmp d_markers;
+    const size_t nm_total = markers[0].size() + markers[1].size() + markers[2].size();
+    PB_CUDA(d_markers.alloc(st, nm_total * sizeof(double) + 8));
+    AxisGrid grid;
+    {
+        size_t off = 0;
+        for (int c = 0; c < 3; ++c) {
+            grid.markers[c] = (const double*)d_markers.p + off;
+            grid.n[c] = markers[c].size();
+            grid.bmin[c] = bmin[c];
+            grid.inv_leaf[c] = 1.0 / leaf[c];
+            if (!markers[c].empty())
+                PB_CUDA(cudaMemcpyAsync((double*)d_markers.p + off, markers[c].data(), markers[c].size() * sizeof(double), cudaMemcpyHostToDevice, st));
+            off += markers[c].size();
+        }
+        grid.bits_y = bits_y;
+        grid.bits_z = bits_z;
+    }
+
+    // ---- keys, sort, segments ---------------------------------------------------------------------------------
+    // packed mode: the point index rides in the low bits of the key, the sort is keys-only
+    const unsigned key_bits = bits_x + bits_y + bits_z, idx_bits_needed = bits_for(n);
+    const bool packed = key_bits + idx_bits_needed <= 64;
+    const unsigned shift = packed ? idx_bits_needed : 0;
+    DevTmp d_keys, d_idx, d_tmp, d_tiles;
+    DevTmp &d_keys2 = vi->sorted_keys, &d_idx2 = vi->sorted_idx;
+    PB_CUDA(d_keys.alloc(st, n * 8)); PB_CUDA(d_keys2.alloc(st, n * 8));
+    PB_CUDA(d_idx2.alloc(st, n * 4));
+    if (!packed) PB_CUDA(d_idx.alloc(st, n * 4));
+    if (((uintptr_t)ppos & 7) || (pstride & 7)) return set_error(PB200_ERR_UNSUPPORTED, "POSITION_3D must be 8-byte aligned in memory");
+    const unsigned long long cap = (unsigned long long)ctx->sm_count * 16;
+    const unsigned blocks = (unsigned)(((n + 255) / 256) < cap ? ((n + 255) / 256) : cap);
+    voxel_key_kernel<<<blocks, 256, 0, st>>>(ppos, pstride, n, grid, shift, (unsigned long long*)d_keys.p, (uint32_t*)d_idx.p);
+    g_launches++;
+    size_t tmp_bytes = 0;
+    if (packed) {
+        cub::DeviceRadixSort::SortKeys(nullptr, tmp_bytes, (const unsigned long long*)d_keys.p, (unsigned long long*)d_keys2.p, (int)n,
+                                       (int)shift, (int)(shift + key_bits), st);
+        PB_CUDA(d_tmp.alloc(st, tmp_bytes));
+        PB_CUDA(cub::DeviceRadixSort::SortKeys(d_tmp.p, tmp_bytes, (const unsigned long long*)d_keys.p, (unsigned long long*)d_keys2.p, (int)n,
+                                               (int)shift, (int)(shift + key_bits), st));
+    } else {
+        cub::DeviceRadixSort::SortPairs(nullptr, tmp_bytes, (const unsigned long long*)d_keys.p, (unsigned long long*)d_keys2.p,
+                                        (const uint32_t*)d_idx.p, (uint32_t*)d_idx2.p, (int)n, 0, (int)key_bits, st);
+        PB_CUDA(d_tmp.alloc(st, tmp_bytes));
+        PB_CUDA(cub::DeviceRadixSort::SortPairs(d_tmp.p, tmp_bytes, (const unsigned long long*)d_keys.p, (unsigned long long*)d_keys2.p,
+                                                (const uint32_t*)d_idx.p, (uint32_t*)d_idx2.p, (int)n, 0, (int)key_bits, st));
+    }
+    g_launches += (uint64_t)((key_bits + 7) / 8) + 1;
+    // voxel boundaries: heads per tile -> scan -> emit
+    const uint32_t n_tiles = (uint32_t)((n + HT_TILE - 1) / HT_TILE);
+    PB_CUDA(d_tiles.alloc(st, ((size_t)n_tiles + 1) * 4));
+    uint32_t* d_total = (uint32_t*)d_tiles.p + n_tiles;
+    heads_count_kernel<<<n_tiles, HT_THREADS, 0, st>>>((const unsigned long long*)d_keys2.p, n, shift, (uint32_t*)d_tiles.p);
+    tile_scan_kernel<<<1, 1024, 0, st>>>((uint32_t*)d_tiles.p, n_tiles, d_total);
+    g_launches += 2;
+    uint32_t* h_total = (uint32_t*)ctx->h_scratch;
+    PB_CUDA(cudaMemcpyAsync(h_total, d_total, 4, cudaMemcpyDeviceToHost, st));
+    PB_CUDA(cudaStreamSynchronize(st));
+    const uint64_t V = *h_total;
+    vi->V = V;
+    DevTmp &d_starts = vi->starts, &d_vkeys = vi->voxel_keys;
+    PB_CUDA(d_starts.alloc(st, (V + 1) * 4));
+    PB_CUDA(d_vkeys.alloc(st, V * 8 + 8));
+    heads_emit_kernel<<<n_tiles, HT_THREADS, 0, st>>>((const unsigned long long*)d_keys2.p, n, shift, (const uint32_t*)d_tiles.p, (uint32_t)V,
+                                                      (uint32_t*)d_starts.p, (unsigned long long*)d_vkeys.p, packed ? (uint32_t*)d_idx2.p : nullptr);
+    g_launches++;
+
+    PB_CUDA(cudaGetLastError());
+    return PB200_OK;
+}
+
 }  // namespace pb200
 
 using namespace pb200;
@@ -470,84 +626,16 @@ int pb200_voxelgrid_filter(pb200_ctx* ctx, const pb200_buffer_desc* src, double 
     int some = 0;
     PB_TRY(pb200_calculate_bounds(ctx, &dsrc, bmin, bmax, &some));
     if (!some) return set_error(PB200_ERR_INVALID, "calculate_bounds returned None");
-    std::vector<double> markers[3];
-    for (int c = 0; c < 3; ++c) {  // voxel_grid.rs:63-77 running sum
-        double cur = bmin[c];
-        while (cur < bmax[c]) {
-            cur += leaf[c];
-            markers[c].push_back(cur);
-            if (markers[c].size() > (1u << 21)) return set_error(PB200_ERR_UNSUPPORTED, "more than 2^21 voxels along one axis");
-        }
-    }
-    const unsigned bits_x = bits_for(markers[0].size()), bits_y = bits_for(markers[1].size()), bits_z = bits_for(markers[2].size());
-    DevTmp d_markers;
-    const size_t nm_total = markers[0].size() + markers[1].size() + markers[2].size();
-    PB_CUDA(d_markers.alloc(st, nm_total * sizeof(double) + 8));
-    AxisGrid grid;
-    {
-        size_t off = 0;
-        for (int c = 0; c < 3; ++c) {
-            grid.markers[c] = (const double*)d_markers.p + off;
-            grid.n[c] = markers[c].size();
-            grid.bmin[c] = bmin[c];
-            grid.inv_leaf[c] = 1.0 / leaf[c];
-            if (!markers[c].empty())
-                PB_CUDA(cudaMemcpyAsync((double*)d_markers.p + off, markers[c].data(), markers[c].size() * sizeof(double), cudaMemcpyHostToDevice, st));
-            off += markers[c].size();
-        }
-        grid.bits_y = bits_y;
-        grid.bits_z = bits_z;
-    }
-
-    // ---- keys, sort, segments ---------------------------------------------------------------------------------
-    // packed mode: the point index rides in the low bits of the key, the sort is keys-only
-    const unsigned key_bits = bits_x + bits_y + bits_z, idx_bits_needed = bits_for(n);
-    const bool packed = key_bits + idx_bits_needed <= 64;
-    const unsigned shift = packed ? idx_bits_needed : 0;
-    DevTmp d_keys, d_keys2, d_idx, d_idx2, d_tmp, d_tiles;
-    PB_CUDA(d_keys.alloc(st, n * 8)); PB_CUDA(d_keys2.alloc(st, n * 8));
-    PB_CUDA(d_idx2.alloc(st, n * 4));
-    if (!packed) PB_CUDA(d_idx.alloc(st, n * 4));
     uint64_t pstride = 0;
     const uint8_t* ppos = attr_ptr(pi, &pstride);
-    if (((uintptr_t)ppos & 7) || (pstride & 7)) return set_error(PB200_ERR_UNSUPPORTED, "POSITION_3D must be 8-byte aligned in memory");
+    VoxelIndex vi;
+    PB_TRY(build_voxel_index(ctx, ppos, pstride, n, bmin, bmax, leaf, &vi));
+    const uint64_t V = vi.V;
+    const unsigned bits_y = vi.bits_y, bits_z = vi.bits_z;
+    DevTmp &d_idx2 = vi.sorted_idx, &d_starts = vi.starts, &d_vkeys = vi.voxel_keys;
     const unsigned long long cap = (unsigned long long)ctx->sm_count * 16;
     const unsigned blocks = (unsigned)(((n + 255) / 256) < cap ? ((n + 255) / 256) : cap);
-    voxel_key_kernel<<<blocks, 256, 0, st>>>(ppos, pstride, n, grid, shift, (unsigned long long*)d_keys.p, (uint32_t*)d_idx.p);
-    g_launches++;
-    size_t tmp_bytes = 0;
-    if (packed) {
-        cub::DeviceRadixSort::SortKeys(nullptr, tmp_bytes, (const unsigned long long*)d_keys.p, (unsigned long long*)d_keys2.p, (int)n,
-                                       (int)shift, (int)(shift + key_bits), st);
-        PB_CUDA(d_tmp.alloc(st, tmp_bytes));
-        PB_CUDA(cub::DeviceRadixSort::SortKeys(d_tmp.p, tmp_bytes, (const unsigned long long*)d_keys.p, (unsigned long long*)d_keys2.p, (int)n,
-                                               (int)shift, (int)(shift + key_bits), st));
-    } else {
-        cub::DeviceRadixSort::SortPairs(nullptr, tmp_bytes, (const unsigned long long*)d_keys.p, (unsigned long long*)d_keys2.p,
-                                        (const uint32_t*)d_idx.p, (uint32_t*)d_idx2.p, (int)n, 0, (int)key_bits, st);
-        PB_CUDA(d_tmp.alloc(st, tmp_bytes));
-        PB_CUDA(cub::DeviceRadixSort::SortPairs(d_tmp.p, tmp_bytes, (const unsigned long long*)d_keys.p, (unsigned long long*)d_keys2.p,
-                                                (const uint32_t*)d_idx.p, (uint32_t*)d_idx2.p, (int)n, 0, (int)key_bits, st));
-    }
-    g_launches += (uint64_t)((key_bits + 7) / 8) + 1;
-    // voxel boundaries: heads per tile -> scan -> emit
-    const uint32_t n_tiles = (uint32_t)((n + HT_TILE - 1) / HT_TILE);
-    PB_CUDA(d_tiles.alloc(st, ((size_t)n_tiles + 1) * 4));
-    uint32_t* d_total = (uint32_t*)d_tiles.p + n_tiles;
-    heads_count_kernel<<<n_tiles, HT_THREADS, 0, st>>>((const unsigned long long*)d_keys2.p, n, shift, (uint32_t*)d_tiles.p);
-    tile_scan_kernel<<<1, 1024, 0, st>>>((uint32_t*)d_tiles.p, n_tiles, d_total);
-    g_launches += 2;
     uint32_t* h_total = (uint32_t*)ctx->h_scratch;
-    PB_CUDA(cudaMemcpyAsync(h_total, d_total, 4, cudaMemcpyDeviceToHost, st));
-    PB_CUDA(cudaStreamSynchronize(st));
-    const uint64_t V = *h_total;
-    DevTmp d_starts;
-    DevTmp d_vkeys;  // handed over to the result buffer on success (result memory comes from the same stream-ordered pool)
-    PB_CUDA(d_starts.alloc(st, (V + 1) * 4));
-    PB_CUDA(d_vkeys.alloc(st, V * 8 + 8));
-    heads_emit_kernel<<<n_tiles, HT_THREADS, 0, st>>>((const unsigned long long*)d_keys2.p, n, shift, (const uint32_t*)d_tiles.p, (uint32_t)V,
-                                                      (uint32_t*)d_starts.p, (unsigned long long*)d_vkeys.p, packed ? (uint32_t*)d_idx2.p : nullptr);
-    g_launches++;
 
     // the most crowded voxel decides how the mode attributes are reduced
     bool any_mode = false;
@@ -690,6 +778,166 @@ int pb200_voxelgrid_filter(pb200_ctx* ctx, const pb200_buffer_desc* src, double 
     }
     *out = res;
     return PB200_OK;
+}
+
+// positions of a buffer as a device (base, stride) view; host buffers are staged into `staged`
+static int voxel_positions(pb200_ctx* ctx, const pb200_buffer_desc* buf, DevTmp* staged, const uint8_t** base, uint64_t* stride) {
+    const int pi = pb200_layout_index_of(buf->layout, "Position3D", PB200_VEC3F64);
+    if (pi < 0)
+        return set_error(PB200_ERR_ATTR_NOT_FOUND, "The PointBuffer does not have the attribute attributes::POSITION_3D which is needed for the creation of the voxel grid.");
+    const pb200_attr& at = buf->layout->attrs[(size_t)pi];
+    const uint8_t* p;
+    if (buf->kind == PB200_INTERLEAVED) { *stride = buf->layout->size; p = (const uint8_t*)buf->aos; }
+    else { *stride = at.size; p = (const uint8_t*)buf->columns[pi]; }
+    if (buf->memspace == PB200_HOST) {
+        const size_t bytes = (size_t)(buf->len * (*stride));
+        PB_CUDA(staged->alloc(ctx->stream, bytes));
+        PB_CUDA(cudaMemcpyAsync(staged->p, p, bytes, cudaMemcpyHostToDevice, ctx->stream));
+        p = (const uint8_t*)staged->p;
+    }
+    *base = p + (buf->kind == PB200_INTERLEAVED ? at.offset : 0);
+    return PB200_OK;
+}
+
+int pb200_voxelgrid_partials(pb200_ctx* ctx, const pb200_buffer_desc* src, double lx, double ly, double lz,
+                             const double global_min[3], const double global_max[3], pb200_voxel_partials** out) {
+    if (!ctx || !out || !global_min || !global_max) return set_error(PB200_ERR_INVALID, "null argument");
+    *out = nullptr;
+    PB_TRY(validate_desc(src, "source buffer"));
+    PB_TRY(ensure_device(ctx));
+    const double leaf[3] = {lx, ly, lz};
+    for (int c = 0; c < 3; ++c) {
+        if (!(leaf[c] > 0.0)) return set_error(PB200_ERR_INVALID, "leaf sizes must be positive (the reference would not terminate)");
+        if (!(global_min[c] <= global_max[c])) return set_error(PB200_ERR_INVALID, "global bounds: min > max (AABB::from_min_max panics)");
+    }
+    if (src->len > 0xFFFFFFFFull) return set_error(PB200_ERR_UNSUPPORTED, "more than 2^32-1 points per call");
+    cudaStream_t st = ctx->stream;
+    pb200_voxel_partials* res = new pb200_voxel_partials();
+    res->ctx = ctx;
+    auto fail = [&](int rc) { pb200_voxel_partials_destroy(res); return rc; };
+    if (src->len == 0) {  // an empty shard contributes nothing; grid geometry is still reported
+        for (int c = 0; c < 3; ++c) {
+            uint64_t cnt = 0;
+            for (double cur = global_min[c]; cur < global_max[c]; cur += leaf[c])
+                if (++cnt > (1u << 21)) return fail(set_error(PB200_ERR_UNSUPPORTED, "more than 2^21 voxels along one axis"));
+            res->cells[c] = cnt;
+        }
+        res->bits_x = bits_for(res->cells[0]); res->bits_y = bits_for(res->cells[1]); res->bits_z = bits_for(res->cells[2]);
+        *out = res;
+        return PB200_OK;
+    }
+    DevTmp staged;
+    const uint8_t* ppos = nullptr;
+    uint64_t pstride = 0;
+    int rc = voxel_positions(ctx, src, &staged, &ppos, &pstride);
+    if (rc < 0) return fail(rc);
+    VoxelIndex vi;
+    rc = build_voxel_index(ctx, ppos, pstride, src->len, global_min, global_max, leaf, &vi);
+    if (rc < 0) return fail(rc);
+    res->len = vi.V;
+    res->bits_x = vi.bits_x; res->bits_y = vi.bits_y; res->bits_z = vi.bits_z;
+    for (int c = 0; c < 3; ++c) res->cells[c] = vi.cells[c];
+    res->keys = vi.voxel_keys.p;
+    vi.voxel_keys.p = nullptr;  // ownership moves to the result
+    if (cudaMallocAsync(&res->counts, vi.V * 4 + 4, st) != cudaSuccess || cudaMallocAsync(&res->sums, vi.V * 24 + 8, st) != cudaSuccess)
+        return fail(set_error(PB200_ERR_OOM, "out of device memory"));
+    voxel_partial_sums_kernel<<<(unsigned)((vi.V + 127) / 128), 128, 0, st>>>((const uint32_t*)vi.starts.p, (const uint32_t*)vi.sorted_idx.p, vi.V,
+                                                                           ppos, pstride, (uint32_t*)res->counts, (double*)res->sums);
+    g_launches++;
+    cudaError_t e = cudaGetLastError();
+    if (e != cudaSuccess) return fail(cuda_error(e, "voxel partial sums"));
+    if (src->memspace == PB200_HOST) cudaStreamSynchronize(st);
+    *out = res;
+    return PB200_OK;
+}
+
+int pb200_voxelgrid_merge_partials(pb200_ctx* ctx, const uint64_t* keys, const uint32_t* counts, const double* sums, uint64_t m,
+                                   uint32_t bits_x, uint32_t bits_y, uint32_t bits_z, pb200_voxel_partials** out) {
+    if (!ctx || !out) return set_error(PB200_ERR_INVALID, "null argument");
+    *out = nullptr;
+    if (m && (!keys || !counts || !sums)) return set_error(PB200_ERR_INVALID, "null partial arrays");
+    if (m > 0xFFFFFFFEull) return set_error(PB200_ERR_UNSUPPORTED, "more than 2^32-2 partial voxels per call");
+    if (bits_x + bits_y + bits_z > 64 || bits_x + bits_y + bits_z == 0) return set_error(PB200_ERR_INVALID, "bad key widths");
+    PB_TRY(ensure_device(ctx));
+    cudaStream_t st = ctx->stream;
+    pb200_voxel_partials* res = new pb200_voxel_partials();
+    res->ctx = ctx;
+    res->bits_x = bits_x; res->bits_y = bits_y; res->bits_z = bits_z;
+    if (m == 0) { *out = res; return PB200_OK; }
+    auto fail = [&](int rc) { pb200_voxel_partials_destroy(res); return rc; };
+    DevTmp d_keys2, d_idx, d_idx2, d_tmp, d_tiles, d_starts;
+    int rc = PB200_OK;
+    auto run = [&]() -> int {
+        PB_CUDA(d_keys2.alloc(st, m * 8)); PB_CUDA(d_idx.alloc(st, m * 4)); PB_CUDA(d_idx2.alloc(st, m * 4));
+        const unsigned long long cap = (unsigned long long)ctx->sm_count * 16;
+        const unsigned blocks = (unsigned)(((m + 255) / 256) < cap ? ((m + 255) / 256) : cap);
+        iota_kernel<<<blocks, 256, 0, st>>>((uint32_t*)d_idx.p, m);
+        size_t tmp_bytes = 0;
+        const int end_bit = (int)(bits_x + bits_y + bits_z);
+        cub::DeviceRadixSort::SortPairs(nullptr, tmp_bytes, (const unsigned long long*)keys, (unsigned long long*)d_keys2.p,
+                                        (const uint32_t*)d_idx.p, (uint32_t*)d_idx2.p, (int)m, 0, end_bit, st);
+        PB_CUDA(d_tmp.alloc(st, tmp_bytes));
+        PB_CUDA(cub::DeviceRadixSort::SortPairs(d_tmp.p, tmp_bytes, (const unsigned long long*)keys, (unsigned long long*)d_keys2.p,
+                                                (const uint32_t*)d_idx.p, (uint32_t*)d_idx2.p, (int)m, 0, end_bit, st));
+        const uint32_t n_tiles = (uint32_t)((m + HT_TILE - 1) / HT_TILE);
+        PB_CUDA(d_tiles.alloc(st, ((size_t)n_tiles + 1) * 4));
+        uint32_t* d_total = (uint32_t*)d_tiles.p + n_tiles;
+        heads_count_kernel<<<n_tiles, HT_THREADS, 0, st>>>((const unsigned long long*)d_keys2.p, m, 0u, (uint32_t*)d_tiles.p);
+        tile_scan_kernel<<<1, 1024, 0, st>>>((uint32_t*)d_tiles.p, n_tiles, d_total);
+        uint32_t* h_total = (uint32_t*)ctx->h_scratch;
+        PB_CUDA(cudaMemcpyAsync(h_total, d_total, 4, cudaMemcpyDeviceToHost, st));
+        PB_CUDA(cudaStreamSynchronize(st));
+        const uint64_t V = *h_total;
+        res->len = V;
+        PB_CUDA(d_starts.alloc(st, (V + 1) * 4));
+        PB_CUDA(cudaMallocAsync(&res->keys, V * 8 + 8, st));
+        PB_CUDA(cudaMallocAsync(&res->counts, V * 4 + 4, st));
+        PB_CUDA(cudaMallocAsync(&res->sums, V * 24 + 8, st));
+        heads_emit_kernel<<<n_tiles, HT_THREADS, 0, st>>>((const unsigned long long*)d_keys2.p, m, 0u, (const uint32_t*)d_tiles.p, (uint32_t)V,
+                                                          (uint32_t*)d_starts.p, (unsigned long long*)res->keys, nullptr);
+        partials_merge_kernel<<<(unsigned)((V + 127) / 128), 128, 0, st>>>((const uint32_t*)d_starts.p, (const uint32_t*)d_idx2.p, V, counts, sums,
+                                                                           (uint32_t*)res->counts, (double*)res->sums);
+        g_launches += 6 + (uint64_t)((end_bit + 7) / 8);
+        PB_CUDA(cudaGetLastError());
+        return PB200_OK;
+    };
+    rc = run();
+    if (rc < 0) return fail(rc);
+    *out = res;
+    return PB200_OK;
+}
+
+int pb200_voxel_partials_get(const pb200_voxel_partials* p, pb200_voxel_partials_desc* out) {
+    if (!p || !out) return set_error(PB200_ERR_INVALID, "null argument");
+    out->len = p->len;
+    out->keys = (const uint64_t*)p->keys;
+    out->counts = (const uint32_t*)p->counts;
+    out->sums = (const double*)p->sums;
+    out->bits_x = p->bits_x; out->bits_y = p->bits_y; out->bits_z = p->bits_z;
+    for (int c = 0; c < 3; ++c) out->cells[c] = p->cells[c];
+    return PB200_OK;
+}
+
+int pb200_voxel_partials_centroids(const pb200_voxel_partials* p, double* positions_out) {
+    if (!p || (!positions_out && p->len)) return set_error(PB200_ERR_INVALID, "null argument");
+    if (p->len == 0) return PB200_OK;
+    PB_TRY(ensure_device(p->ctx));
+    const unsigned long long cap = (unsigned long long)p->ctx->sm_count * 16;
+    const unsigned blocks = (unsigned)(((p->len + 255) / 256) < cap ? ((p->len + 255) / 256) : cap);
+    partials_centroid_kernel<<<blocks, 256, 0, p->ctx->stream>>>((const uint32_t*)p->counts, (const double*)p->sums, p->len, positions_out);
+    g_launches++;
+    PB_CUDA(cudaGetLastError());
+    return PB200_OK;
+}
+
+void pb200_voxel_partials_destroy(pb200_voxel_partials* p) {
+    if (!p) return;
+    if (p->ctx) cudaSetDevice(p->ctx->device);
+    cudaStream_t st = p->ctx ? p->ctx->stream : nullptr;
+    if (p->keys) cudaFreeAsync(p->keys, st);
+    if (p->counts) cudaFreeAsync(p->counts, st);
+    if (p->sums) cudaFreeAsync(p->sums, st);
+    delete p;
 }
 
 int pb200_result_buffer_desc(const pb200_result_buffer* r, pb200_buffer_desc* out) {

@@ -1,7 +1,8 @@
 """Point-range sharding across GPUs: one process per GPU, rank r owns the contiguous range
 [r*N/G, (r+1)*N/G) -- the `convert_into_range` / `slice(range)` contract of the reference
 (buffer_conversion.rs:292, containers/slice.rs:16-43).  The only exchange on the conversion path is the global
-AABB: one all-reduce(MIN) of [min xyz, -max xyz] (48 bytes)."""
+AABB: one all-reduce(MIN) of [min xyz, -max xyz] (48 bytes).  The voxel-grid filter adds one key-range all-to-all of
+per-shard partial sums (`voxelgrid_filter_sharded`)."""
 import torch
 import torch.distributed as dist
 
@@ -37,3 +38,62 @@ def allreduce_bounds(minmax6, group=None):
     if dist.is_available() and dist.is_initialized() and dist.get_world_size(group) > 1:
         dist.all_reduce(minmax6, op=dist.ReduceOp.MIN, group=group)
     return minmax6
+
+
+# ---- sharded voxel grid: partials -> key-range all-to-all -> merge --------------------------------------
+
+def key_range_boundaries(cells_x, bits_y, bits_z, world_size):
+    """Rank d finalises the voxels whose x index lies in [d*cells_x//W, (d+1)*cells_x//W): returns the W-1 packed keys at
+    which ownership changes (a key k belongs to rank = number of boundaries <= k)."""
+    cells_x = max(1, int(cells_x))
+    return [((d * cells_x) // world_size) << (bits_y + bits_z) for d in range(1, world_size)]
+
+
+def split_sizes(sorted_keys, boundaries):
+    """how many entries of an ascending key tensor go to each destination rank"""
+    if not boundaries:
+        return [int(sorted_keys.numel())]
+    b = torch.tensor(boundaries, dtype=sorted_keys.dtype, device=sorted_keys.device)
+    cut = torch.searchsorted(sorted_keys, b, right=False).tolist()
+    edges = [0] + cut + [int(sorted_keys.numel())]
+    return [edges[i + 1] - edges[i] for i in range(len(edges) - 1)]
+
+
+def exchange_partials(keys, counts, sums, send_sizes, group=None):
+    """all-to-all of the three partial arrays; what arrives is concatenated in source-rank order.  Works on CUDA tensors
+    (NCCL) and on CPU tensors (gloo); without a process group it is the identity."""
+    if not (dist.is_available() and dist.is_initialized()) or dist.get_world_size(group) == 1:
+        return keys, counts, sums
+    world = dist.get_world_size(group)
+    assert len(send_sizes) == world
+    dev = keys.device
+    sent = torch.tensor(send_sizes, dtype=torch.int64, device=dev)
+    recv = torch.empty(world, dtype=torch.int64, device=dev)
+    dist.all_to_all_single(recv, sent, group=group)
+    recv_sizes = recv.tolist()
+    m = sum(recv_sizes)
+    out_keys = torch.empty(m, dtype=keys.dtype, device=dev)
+    out_counts = torch.empty(m, dtype=counts.dtype, device=dev)
+    out_sums = torch.empty((m, 3), dtype=sums.dtype, device=dev)
+    dist.all_to_all_single(out_keys, keys.contiguous(), recv_sizes, list(send_sizes), group=group)
+    dist.all_to_all_single(out_counts, counts.contiguous(), recv_sizes, list(send_sizes), group=group)
+    dist.all_to_all_single(out_sums, sums.contiguous(), recv_sizes, list(send_sizes), group=group)
+    return out_keys, out_counts, out_sums
+
+
+def voxelgrid_filter_sharded(shard, leafsize_x, leafsize_y, leafsize_z, group=None, ctx=None):
+    """voxel_grid.rs:109-165 over a cloud sharded by point range, one shard per rank.  Returns (VoxelPartials, centroids)
+    for THIS rank's key range (ranks own ascending, disjoint x-index ranges, so concatenating the ranks' results in rank
+    order gives the reference's output order), or None if the whole cloud is empty.
+    Collectives: all-reduce(MIN) of the bounds (48 B), all-to-all of the send counts, 3 x all-to-all of the partials."""
+    from . import algorithms as alg
+    world = dist.get_world_size(group) if dist.is_available() and dist.is_initialized() else 1
+    b = alg.calculate_bounds(shard) if shard.len() else None
+    v = pack_bounds(None if b is None else (b.min(), b.max()), shard.device)
+    g = unpack_bounds(allreduce_bounds(v, group))
+    if g is None:
+        return None
+    part = alg.voxelgrid_partials(shard, leafsize_x, leafsize_y, leafsize_z, g, ctx)
+    bounds = key_range_boundaries(part.cells[0], part.bits[1], part.bits[2], world)
+    keys, counts, sums = exchange_partials(part.keys, part.counts, part.sums, split_sizes(part.keys, bounds), group)
+    return alg.voxelgrid_merge_partials(keys, counts, sums, part.bits, part.cells, ctx)

@@ -150,3 +150,71 @@ def test_crowded_voxels_use_the_sort_based_mode(leaf):
     out, keys = voxelgrid_filter(pbuf, *leaf, return_keys=True)
     assert np.array_equal(keys, okeys)
     util.assert_buffers_match(oout, out)
+
+
+# ---- sharded voxel grid: S logical shards on one GPU + the exchange emulated by slicing ------------------
+def _pos_cloud(pts, device="cuda"):
+    ol, pl = util.layouts([("Position3D", O.VEC3F64)])
+    ob = O.OBuffer(ol, len(pts), True)
+    if len(pts):
+        ob.set_attribute("Position3D", pts)
+    return ob, ol, util.to_pb(ob, pl, device)
+
+
+@pytest.mark.parametrize("shards,world", [(1, 1), (2, 2), (3, 2), (5, 4)])
+def test_sharded_partials_and_merge_equal_single_shot(shards, world):
+    from pasture_b200 import sharding
+    from pasture_b200.algorithms import calculate_bounds, voxelgrid_merge_partials, voxelgrid_partials
+    rng = np.random.default_rng(shards * 10 + world)
+    n, leaf = 4000, (0.8, 1.3, 0.6)
+    pts = rng.random((n, 3)) * [15.0, 8.0, 2.5] - [3.0, 1.0, 0.5]
+    ob, ol, whole = _pos_cloud(pts)
+    single, skeys = voxelgrid_filter(whole, *leaf, return_keys=True)
+    b = calculate_bounds(whole)
+    parts = []
+    for r in range(shards):
+        rr = sharding.shard_range(n, r, shards)
+        _, _, shard = _pos_cloud(pts[rr.start:rr.stop])
+        p = voxelgrid_partials(shard, *leaf, b)
+        ok, oc, osum, obits, ocells = O.voxel_partials(pts[rr.start:rr.stop], b.min(), b.max(), leaf)
+        assert list(p.bits) == list(obits) and list(p.cells) == list(ocells)
+        assert np.array_equal(p.keys.cpu().numpy(), ok) and np.array_equal(p.counts.cpu().numpy(), oc)
+        assert np.array_equal(p.sums.cpu().numpy(), osum)  # in-order sums: bit-exact
+        parts.append(p)
+    bounds = sharding.key_range_boundaries(parts[0].cells[0], parts[0].bits[1], parts[0].bits[2], world)
+    sizes = [sharding.split_sizes(p.keys, bounds) for p in parts]
+    out_keys, out_cent, out_counts = [], [], []
+    for d in range(world):  # what destination rank d receives: every source's slice, in source order
+        ks, cs, ss = [], [], []
+        for p, sz in zip(parts, sizes):
+            lo = sum(sz[:d])
+            ks.append(p.keys[lo:lo + sz[d]]); cs.append(p.counts[lo:lo + sz[d]]); ss.append(p.sums[lo:lo + sz[d]])
+        merged, cent = voxelgrid_merge_partials(torch.cat(ks), torch.cat(cs), torch.cat(ss), parts[0].bits, parts[0].cells)
+        mk, mc, ms = O.merge_partials(torch.cat(ks).cpu().numpy(), torch.cat(cs).cpu().numpy(), torch.cat(ss).cpu().numpy())
+        assert np.array_equal(merged.keys.cpu().numpy(), mk) and np.array_equal(merged.counts.cpu().numpy(), mc)
+        assert np.array_equal(merged.sums.cpu().numpy(), ms)
+        out_keys.append(merged.unpack_keys()); out_cent.append(cent); out_counts.append(merged.counts)
+    keys = torch.cat(out_keys).cpu().numpy().astype(np.uint64)
+    cent = torch.cat(out_cent).cpu().numpy()
+    assert np.array_equal(keys, skeys)                       # same voxels in the reference's output order
+    assert int(torch.cat(out_counts).sum()) == n
+    ref = single.view_attribute("Position3D")
+    if shards == 1:
+        assert np.array_equal(cent, ref)                     # one shard: the same in-order sums
+    else:
+        assert np.allclose(cent, ref, rtol=1e-9, atol=0)     # sum of per-shard sums: 1e-9 relative
+
+
+def test_sharded_voxelgrid_single_process_and_empty():
+    from pasture_b200 import sharding
+    pts = np.random.default_rng(9).random((2500, 3)) * 6.0
+    _, _, whole = _pos_cloud(pts)
+    single, skeys = voxelgrid_filter(whole, 0.5, 0.5, 0.5, return_keys=True)
+    part, cent = sharding.voxelgrid_filter_sharded(whole, 0.5, 0.5, 0.5)  # no process group: one rank owns everything
+    assert np.array_equal(part.unpack_keys().cpu().numpy().astype(np.uint64), skeys)
+    assert np.array_equal(cent.cpu().numpy(), single.view_attribute("Position3D"))
+    _, _, empty = _pos_cloud(np.zeros((0, 3)))
+    assert sharding.voxelgrid_filter_sharded(empty, 0.5, 0.5, 0.5) is None
+    b = pb.algorithms.calculate_bounds(whole)
+    p = pb.algorithms.voxelgrid_partials(empty, 0.5, 0.5, 0.5, b)  # an empty shard of a non-empty cloud
+    assert p.len() == 0 and p.cells[0] > 0

@@ -89,3 +89,68 @@ def test_shard_ranges_partition_the_cloud():
                 assert a.stop == b.start
             assert max(len(r) for r in rs) - min(len(r) for r in rs) <= 1
     assert sharding.unpack_bounds(sharding.pack_bounds(None)) is None
+
+
+# ---- sharded voxel grid: partials -> key-range all-to-all -> merge -------------------------------------------------
+VOX_N, VOX_LEAF = 1500, (0.9, 1.1, 0.7)
+
+
+def _vox_cloud():
+    rng = np.random.default_rng(5)
+    return rng.random((VOX_N, 3)) * [12.0, 9.0, 3.0] - [2.0, 4.0, 1.0]
+
+
+def _vox_worker(rank, world, port, empty_rank, out_q):
+    os.environ["MASTER_ADDR"] = "127.0.0.1"
+    os.environ["MASTER_PORT"] = str(port)
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    try:
+        pts = _vox_cloud()
+        r = sharding.shard_range(VOX_N, rank, world)
+        mine = pts[r.start:r.start] if rank == empty_rank else pts[r.start:r.stop]
+        v = sharding.pack_bounds(None if len(mine) == 0 else (mine.min(0).tolist(), mine.max(0).tolist()))
+        gmin, gmax = sharding.unpack_bounds(sharding.allreduce_bounds(v))
+        k, c, s, bits, cells = O.voxel_partials(mine, gmin, gmax, VOX_LEAF)
+        bounds = sharding.key_range_boundaries(cells[0], bits[1], bits[2], world)
+        tk = torch.from_numpy(k)
+        rk, rc, rs = sharding.exchange_partials(tk, torch.from_numpy(c), torch.from_numpy(s), sharding.split_sizes(tk, bounds))
+        mk, mc, ms = O.merge_partials(rk.numpy(), rc.numpy(), rs.numpy())
+        # every key this rank finalises lies in its own key range
+        lo = 0 if rank == 0 else bounds[rank - 1]
+        hi = bounds[rank] if rank < world - 1 else 1 << 62
+        assert all(lo <= int(x) < hi for x in mk)
+        out_q.put((rank, mk.tolist(), mc.tolist(), (ms / mc[:, None]).tolist(), bits))
+    finally:
+        dist.destroy_process_group()
+
+
+@pytest.mark.parametrize("world,empty_rank", [(2, -1), (3, 0)])
+def test_sharded_voxelgrid_equals_single_shot(world, empty_rank):
+    ctx = mp.get_context("spawn")
+    q = ctx.Queue()
+    port = _free_port()
+    procs = [ctx.Process(target=_vox_worker, args=(r, world, port, empty_rank, q)) for r in range(world)]
+    for p in procs:
+        p.start()
+    results = sorted(q.get(timeout=180) for _ in range(world))
+    for p in procs:
+        p.join(timeout=60)
+        assert p.exitcode == 0
+    # expected: the reference filter (oracle restatement) over the points that exist
+    pts = _vox_cloud()
+    if empty_rank >= 0:
+        r = sharding.shard_range(VOX_N, empty_rank, world)
+        pts = np.concatenate([pts[:r.start], pts[r.stop:]])
+    ol = O.OLayout.from_attributes([("Position3D", O.VEC3F64)])
+    ob = O.OBuffer(ol, len(pts), True)
+    ob.set_attribute("Position3D", pts)
+    oout, okeys = O.voxelgrid_filter(ob, VOX_LEAF, ol)
+    bits = results[0][4]
+    keys = np.array([k for _, ks, _, _, _ in results for k in ks], dtype=np.int64)  # rank order = key order
+    cent = np.array([c for _, _, _, cs, _ in results for c in cs]).reshape(-1, 3)
+    counts = np.array([c for _, _, cs, _, _ in results for c in cs])
+    packed = (okeys[:, 0].astype(np.int64) << (bits[1] + bits[2])) | (okeys[:, 1].astype(np.int64) << bits[2]) | okeys[:, 2].astype(np.int64)
+    assert np.array_equal(keys, packed)              # same voxels, same order
+    assert counts.sum() == len(pts)
+    expect = oout.attribute_bytes(0).view(np.float64).reshape(-1, 3)
+    assert np.allclose(cent, expect, rtol=1e-9, atol=0)  # sum of per-shard sums vs one in-order sum
