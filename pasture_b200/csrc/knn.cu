@@ -43,6 +43,7 @@ static_assert(sizeof(Node) == 64, "node record is one 64-byte line");
 
 struct Lbvh {
     uint32_t n = 0, nb = 0;
+    double origin[3] = {0.0, 0.0, 0.0};
     DevTmp codes, codes2, idx, idx2, tmp, spos, nodes, parent, leaf_parent, counters;
     const double* sorted_pos() const { return (const double*)spos.p; }
 };
@@ -128,17 +129,27 @@ __global__ void __launch_bounds__(256) lbvh_hierarchy_kernel(const unsigned long
 }
 
 // one thread per bucket: box of its points, then climb; the second arrival at a node owns it
+// f32 interval arithmetic for the box tests.  Boxes are stored RELATIVE to the AABB minimum (georeferenced clouds keep
+// sub-millimetre box resolution) and widened: round outwards, then one more f32 ulp, which swallows the f64 rounding of
+// the translation itself.  Together with round-down arithmetic and the safety factor in box_lower_bound this makes the
+// f32 value a strict lower bound of the f64 point distance the k-list compares against.
+__device__ __forceinline__ float f32_below(double v) { return nextafterf(__double2float_rd(v), -INFINITY); }
+__device__ __forceinline__ float f32_above(double v) { return nextafterf(__double2float_ru(v), INFINITY); }
+
 __global__ void __launch_bounds__(256) lbvh_refit_kernel(uint32_t n, uint32_t nb, Node* nodes, const uint32_t* __restrict__ parent,
                                                          const uint32_t* __restrict__ leaf_parent,
-                                                         const double* __restrict__ spos, uint32_t* counters) {
+                                                         const double* __restrict__ spos, double ox, double oy, double oz,
+                                                         uint32_t* counters) {
+    const double origin[3] = {ox, oy, oz};
     for (uint32_t b = blockIdx.x * blockDim.x + threadIdx.x; b < nb; b += gridDim.x * blockDim.x) {
         float lo[3] = {INFINITY, INFINITY, INFINITY}, hi[3] = {-INFINITY, -INFINITY, -INFINITY};
         const uint32_t p0 = b * BUCKET, p1 = (p0 + BUCKET < n) ? p0 + BUCKET : n;
         for (uint32_t p = p0; p < p1; ++p)
             for (int a = 0; a < 3; ++a) {
                 const double v = spos[3 * (size_t)p + a];
-                lo[a] = fminf(lo[a], __double2float_rd(v));
-                hi[a] = fmaxf(hi[a], __double2float_ru(v));
+                if (v != v) continue;  // NaN coordinates never become neighbours; keep them out of the boxes
+                lo[a] = fminf(lo[a], f32_below(v - origin[a]));
+                hi[a] = fmaxf(hi[a], f32_above(v - origin[a]));
             }
         uint32_t child = b, node = leaf_parent[b];
         while (node != NONE) {
@@ -157,11 +168,14 @@ __global__ void __launch_bounds__(256) lbvh_refit_kernel(uint32_t n, uint32_t nb
     }
 }
 
-__device__ __forceinline__ double box_dist2(float lx, float ly, float lz, float hx, float hy, float hz, double qx, double qy, double qz) {
-    const double dx = fmax(fmax((double)lx - qx, 0.0), qx - (double)hx);
-    const double dy = fmax(fmax((double)ly - qy, 0.0), qy - (double)hy);
-    const double dz = fmax(fmax((double)lz - qz, 0.0), qz - (double)hz);
-    return __dadd_rn(__dadd_rn(__dmul_rn(dx, dx), __dmul_rn(dy, dy)), __dmul_rn(dz, dz));
+// lower bound of the squared distance between the query interval [ql, qh] (per axis) and a box, all in round-down f32
+__device__ __forceinline__ float box_lower_bound(float lx, float ly, float lz, float hx, float hy, float hz, float qlx, float qly,
+                                                 float qlz, float qhx, float qhy, float qhz) {
+    const float dx = fmaxf(fmaxf(__fsub_rd(lx, qhx), __fsub_rd(qlx, hx)), 0.0f);
+    const float dy = fmaxf(fmaxf(__fsub_rd(ly, qhy), __fsub_rd(qly, hy)), 0.0f);
+    const float dz = fmaxf(fmaxf(__fsub_rd(lz, qhz), __fsub_rd(qlz, hz)), 0.0f);
+    const float d2 = __fadd_rd(__fadd_rd(__fmul_rd(dx, dx), __fmul_rd(dy, dy)), __fmul_rd(dz, dz));
+    return __fmul_rd(d2, 0.99999976f);  // 1 - 2^-22: strictly below the f64-rounded point distances
 }
 
 // ---- normal estimation on an explicit neighbourhood (normal_estimation.rs:198-476) ----------------------------
@@ -267,6 +281,7 @@ struct QueryArgs {
     const uint32_t* sidx;      // original index of sorted position i
     const Node* nodes;
     double radius2;            // < 0: pure kNN
+    double origin[3];          // boxes and query intervals are relative to this point (the AABB minimum)
     uint32_t* idx_out;         // n*k (original order), nullable
     double* d2_out;            // n*k, nullable
     uint32_t* counts_out;      // n, nullable (radius search)
@@ -339,27 +354,39 @@ struct KList {
 };
 
 // MODE 0: kNN lists, 1: radius search, 2: normals, 3: kNN traversal statistics (diagnostics)
-// Control flow is arranged so that the (fully unrolled, KMAX-long) list insertion is instantiated exactly once:
+//
+// PACKET traversal: the 32 queries of a warp are consecutive in Morton order (four buckets), so their search regions
+// overlap almost completely.  The warp walks the tree ONCE: node and bucket addresses are warp-uniform (every load is a
+// broadcast), each lane tests the two child boxes against its OWN query and bound, and a child is entered if ANY lane
+// needs it (ballot).  Control flow never diverges in the traversal; only the list insertions do.  The result per lane is
+// exactly what its private traversal would give: a lane ignores buckets whose box is beyond its own bound because no
+// point in them passes its candidate test.
+// Control flow is also arranged so that the (fully unrolled, KMAX-long) list insertion is instantiated exactly once:
 // buckets to scan are queued as a range [pend_lo, pend_hi) -- the priming range first, then the one or two leaf
 // children of the visited node, which are consecutive buckets by construction (gamma, gamma + 1).
 template <int KMAX, int MODE>
 __global__ void __launch_bounds__(128) lbvh_query_kernel(QueryArgs a) {
+    __shared__ uint32_t s_stack[4][STACK_DEPTH];  // one warp-uniform stack per warp
     const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
-    if (i >= a.n) return;
-    const double qx = a.spos[3 * (size_t)i], qy = a.spos[3 * (size_t)i + 1], qz = a.spos[3 * (size_t)i + 2];
+    const uint32_t warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const bool active = i < a.n;
+    // lanes beyond the cloud keep voting but never need anything: NaN fails every comparison
+    const double qnan = __longlong_as_double(0x7FF8000000000000ll);
+    const double qx = active ? a.spos[3 * (size_t)i] : qnan, qy = active ? a.spos[3 * (size_t)i + 1] : qnan,
+                 qz = active ? a.spos[3 * (size_t)i + 2] : qnan;
+    const float qlx = f32_below(qx - a.origin[0]), qly = f32_below(qy - a.origin[1]), qlz = f32_below(qz - a.origin[2]);
+    const float qhx = f32_above(qx - a.origin[0]), qhy = f32_above(qy - a.origin[1]), qhz = f32_above(qz - a.origin[2]);
     const uint32_t k = a.k;
     const double limit = MODE == 1 ? a.radius2 : DBL_MAX;
     const uint32_t* __restrict__ sidx = a.sidx;
     KList<KMAX> list;
     list.init();
-    // prime the list from the query's own bucket and its neighbours in Morton order
-    const uint32_t qb = i / BUCKET;
-    const uint32_t ib0 = qb > a.init_radius ? qb - a.init_radius : 0u;
-    const uint32_t ib1 = (qb + a.init_radius < a.nb - 1) ? qb + a.init_radius : a.nb - 1;
+    // prime the lists from the warp's own buckets and their neighbours in Morton order
+    const uint32_t qb0 = (i - lane) / BUCKET, qb1 = qb0 + 32 / BUCKET - 1;
+    const uint32_t ib0 = qb0 > a.init_radius ? qb0 - a.init_radius : 0u;
+    const uint32_t ib1 = (qb1 + a.init_radius < a.nb - 1) ? qb1 + a.init_radius : a.nb - 1;
     uint32_t pend_lo = ib0, pend_hi = ib1 + 1;
     bool more = a.nb > 1 && !(ib0 == 0 && ib1 == a.nb - 1);
-    uint32_t stack[STACK_DEPTH];
-    float stack_d[STACK_DEPTH];  // lower bound of the box distance at push time (rounded down)
     int sp = 0;
     uint32_t node = 0;  // root
     uint32_t st_nodes = 0, st_buckets = 0, st_offers = 0;
@@ -387,6 +414,7 @@ __global__ void __launch_bounds__(128) lbvh_query_kernel(QueryArgs a) {
                 if (MODE == 3) ++st_offers;
                 list.offer(d2, b * BUCKET + (uint32_t)t, k, limit, sidx);
             }
+            __syncwarp();
         }
         pend_lo = pend_hi = 0;
         if (!more) break;
@@ -394,33 +422,34 @@ __global__ void __launch_bounds__(128) lbvh_query_kernel(QueryArgs a) {
         const float4* rec = reinterpret_cast<const float4*>(a.nodes + node);
         const float4 r0 = __ldg(rec), r1 = __ldg(rec + 1), r2 = __ldg(rec + 2);
         const uint32_t split = __ldg(reinterpret_cast<const uint32_t*>(rec + 3));
-        const double dl = box_dist2(r0.x, r0.y, r0.z, r0.w, r1.x, r1.y, qx, qy, qz);
-        const double dr = box_dist2(r1.z, r1.w, r2.x, r2.y, r2.z, r2.w, qx, qy, qz);
+        const float dl = box_lower_bound(r0.x, r0.y, r0.z, r0.w, r1.x, r1.y, qlx, qly, qlz, qhx, qhy, qhz);
+        const float dr = box_lower_bound(r1.z, r1.w, r2.x, r2.y, r2.z, r2.w, qlx, qly, qlz, qhx, qhy, qhz);
         const uint32_t cl = split & SPLIT_MASK, cr = cl + 1;
         const bool ll = (split & LEFT_LEAF) != 0, rl = (split & RIGHT_LEAF) != 0;
         const double bound = list.worst();
-        const bool sl = ll && dl <= bound && (cl < ib0 || cl > ib1), sr = rl && dr <= bound && (cr < ib0 || cr > ib1);
+        const bool need_l = active && (double)dl <= bound, need_r = active && (double)dr <= bound;
+        const uint32_t bl = __ballot_sync(0xffffffffu, need_l), br = __ballot_sync(0xffffffffu, need_r);
+        const uint32_t left_votes = __popc(__ballot_sync(0xffffffffu, need_l && (!need_r || dl <= dr)));
+        const uint32_t right_votes = __popc(__ballot_sync(0xffffffffu, need_r && (!need_l || dr < dl)));
+        const bool sl = ll && bl != 0 && (cl < ib0 || cl > ib1), sr = rl && br != 0 && (cr < ib0 || cr > ib1);
         if (sl || sr) { pend_lo = sl ? cl : cr; pend_hi = sr ? cr + 1 : cl + 1; }
-        const bool vl = !ll && dl <= bound, vr = !rl && dr <= bound;
+        const bool vl = !ll && bl != 0, vr = !rl && br != 0;
         if (vl && vr) {
-            const bool left_first = dl <= dr;
+            const bool left_first = left_votes >= right_votes;
             if (sp < STACK_DEPTH) {
-                stack[sp] = left_first ? cr : cl;
-                stack_d[sp++] = __double2float_rd(left_first ? dr : dl);
+                if (lane == 0) s_stack[warp][sp] = left_first ? cr : cl;
+                ++sp;
             }
             node = left_first ? cl : cr;
         } else if (vl) node = cl;
         else if (vr) node = cr;
-        else {
-            // pop, re-checking the bound: the list may have tightened since the push (the pending leaf scan of this
-            // node is not yet reflected -- conservative)
-            more = false;
-            while (sp > 0) {
-                --sp;
-                if ((double)stack_d[sp] <= bound) { node = stack[sp]; more = true; break; }
-            }
-        }
+        else if (sp > 0) {
+            __syncwarp();  // lane 0's pushes are visible
+            node = s_stack[warp][--sp];
+            __syncwarp();  // everyone has read the entry before lane 0 may overwrite it
+        } else more = false;
     }
+    if (!active) return;
     const uint32_t self = sidx[i];
     if (MODE == 2) {
         uint32_t nb[KMAX];  // ascending (d2, index) order = the order kd-tree's nearests() returns
@@ -508,6 +537,7 @@ static int build_lbvh(pb200_ctx* ctx, const uint8_t* base, uint64_t stride, uint
     // Quantisation for the tree's Morton order: ONE scale for all axes (cubic cells), so that neighbours on the curve
     // are neighbours in space even for 2.5-D clouds whose z extent is a fraction of x/y.  (pb200_morton_codes, the
     // public Z-row entry point, quantises per axis inside the AABB.)
+    for (int c = 0; c < 3; ++c) t->origin[c] = (some && bmin[c] == bmin[c] && fabs(bmin[c]) <= DBL_MAX) ? bmin[c] : 0.0;
     double s[3];
     double emax = 0.0;
     for (int c = 0; c < 3; ++c) { const double e = bmax[c] - bmin[c]; if (e > emax) emax = e; }
@@ -541,7 +571,7 @@ static int build_lbvh(pb200_ctx* ctx, const uint8_t* base, uint64_t stride, uint
         g_launches++;
         lbvh_refit_kernel<<<grid_for(nb, ctx->sm_count), 256, 0, st>>>(n, nb, (Node*)t->nodes.p, (const uint32_t*)t->parent.p,
                                                                        (const uint32_t*)t->leaf_parent.p, (const double*)t->spos.p,
-                                                                       (uint32_t*)t->counters.p);
+                                                                       t->origin[0], t->origin[1], t->origin[2], (uint32_t*)t->counters.p);
         g_launches++;
     }
     PB_CUDA(cudaGetLastError());
@@ -576,14 +606,14 @@ static int run_query(pb200_ctx* ctx, const pb200_buffer_desc* buf, int mode, uin
     DevTmp d_idx, d_d2, d_cnt, d_nrm, d_curv;
     QueryArgs a{};
     a.n = n; a.nb = tree.nb; a.k = k;
-    // own bucket +- ceil(k/8) buckets (k = 16: 40 candidates).  Measured on the C4 stream (20 M points, k = 16): +-1 bucket
-    // 94 ms, +-2 42 ms, +-3..6 42-43 ms -- the mean work is the same, the slowest lane of a warp is not.
+    // the warp's own four buckets +- init_radius buckets prime every lane's list before the traversal
     a.init_radius = (k + 7) / 8;
     if (ctx->knn_init_radius >= 0) a.init_radius = (uint32_t)ctx->knn_init_radius;
     a.spos = tree.sorted_pos();
     a.sidx = (const uint32_t*)tree.idx2.p;
     a.nodes = (const Node*)tree.nodes.p;
     a.radius2 = mode == 1 ? radius * radius : -1.0;
+    for (int c = 0; c < 3; ++c) a.origin[c] = tree.origin[c];
     auto out_ptr = [&](void* user, DevTmp& tmp, size_t bytes, void** dev) -> int {
         *dev = nullptr;
         if (!user) return PB200_OK;

@@ -72,6 +72,20 @@ def test_knn_larger_cloud_deep_tree():
     assert np.array_equal(idx.cpu().numpy().view(np.uint32), oidx)
 
 
+def test_knn_georeferenced_coordinates():
+    """UTM-like magnitudes (5.4e6 m) with decimetre spacing: boxes are f32 intervals relative to the AABB minimum and
+    must stay conservative (result bit-exact) -- and a cloud whose points differ only in the last f64 bits"""
+    rng = np.random.default_rng(21)
+    pts = rng.random((5000, 3)) * [40.0, 40.0, 3.0] + [500000.0, 5400000.0, 100.0]
+    oidx, od2 = O.knn_bruteforce(pts, pts, 16)
+    idx, d2 = knn(cloud(pts), 16)
+    assert np.array_equal(d2.cpu().numpy(), od2) and np.array_equal(idx.cpu().numpy().view(np.uint32), oidx)
+    tiny = np.array([5400000.0, 5400000.0, 5400000.0]) + rng.integers(0, 64, (600, 3)) * 2.0 ** -30
+    oidx, od2 = O.knn_bruteforce(tiny, tiny, 16)
+    idx, d2 = knn(cloud(tiny), 16)
+    assert np.array_equal(d2.cpu().numpy(), od2) and np.array_equal(idx.cpu().numpy().view(np.uint32), oidx)
+
+
 def test_knn_all_points_identical():
     """every code and every distance ties: order must be by original index"""
     pts = np.tile(np.array([[1.5, -2.0, 3.25]]), (100, 1))
