@@ -199,8 +199,31 @@ def run_ours(args):
     minmax6 = torch.zeros(6, dtype=torch.float64, device=dev)
     rng_all = range(0, n)
 
+    # N > 1: the global AABB is exchanged over peer memory by the last CTA of the convert kernel itself (PeerComm: CUDA-IPC
+    # mapped exchange buffers, NVLink stores) -- no collective-library call inside a step.  --nccl-bounds (or a failed IPC
+    # set-up, agreed on by all ranks) falls back to the fused kernel + one 48-byte NCCL all-reduce(MIN).
+    comm, exchange = None, "none (single GPU)"
+    if world > 1:
+        exchange = "NCCL all-reduce(MIN), 48 B"
+        ok = torch.ones(1, dtype=torch.int32, device=dev)
+        if not args.nccl_bounds:
+            try:
+                from pasture_b200.sharding import PeerComm
+                comm = PeerComm(ctx)
+            except Exception as exc:  # noqa: BLE001
+                sys.stderr.write(f"[rank {rank}] peer-memory communicator unavailable ({exc}); using NCCL\n")
+                ok.zero_()
+                comm = None
+            dist.all_reduce(ok, op=dist.ReduceOp.MIN)
+            if int(ok.item()) == 1:
+                exchange = "peer memory: last CTA of the convert kernel stores its 6 keys into every peer's buffer over NVLink (no NCCL call per step)"
+            else:
+                comm = None
+
     def step():
-        if fused:
+        if comm is not None:
+            cv.convert_into_range_with_global_bounds(src, rng_all, dst, rng_all, comm, minmax6)
+        elif fused:
             cv.convert_into_range_with_bounds_device(src, rng_all, dst, rng_all, minmax6)
             if world > 1:
                 dist.all_reduce(minmax6, op=dist.ReduceOp.MIN)
@@ -236,9 +259,20 @@ def run_ours(args):
     value = world * n * args.steps / (total_ms * 1e-3)
 
     # ---- sanity: the produced bounds must be the bounds of the shard (cheap device-side check) ----------
+    if comm is not None:
+        comm.check()  # raises if a peer never arrived inside the kernel's timeout
     if fused:
         mm = minmax6.cpu().numpy()
         assert mm[0] <= -mm[3] and mm[1] <= -mm[4] and mm[2] <= -mm[5], mm
+        if world > 1:  # every rank must hold the same, global box; rank 0 also checks it against its own shard's box
+            allmm = [torch.zeros(6, dtype=torch.float64, device=dev) for _ in range(world)]
+            dist.all_gather(allmm, minmax6)
+            assert all(bool((a == allmm[0]).all()) for a in allmm), "ranks disagree on the global AABB"
+            local6 = torch.zeros(6, dtype=torch.float64, device=dev)
+            cv.convert_into_range_with_bounds_device(src, rng_all, dst, rng_all, local6)
+            ref6 = local6.clone()
+            dist.all_reduce(ref6, op=dist.ReduceOp.MIN)
+            assert bool((ref6 == minmax6).all()), (ref6, minmax6)
 
     # ---- roofline of the dominant kernel (the only kernel in a step at N = 1) -----------------------------
     peak, peak_src = measured_peak_gbs()
@@ -250,7 +284,7 @@ def run_ours(args):
                 "traffic": traffic, "peak_source": peak_src, "algorithmic_bytes_per_launch": (BYTES_IN + BYTES_OUT) * n,
                 "avg_launch_ms": avg_kernel_ms, "best_launch_ms": best_kernel_ms,
                 "frac_of_8TBps_nominal": achieved / 8000.0, "kernel": "convert_tiles_kernel",
-                "note": "rank 0; at N>1 the step also holds the 48 B all-reduce" if world > 1 else "rank 0"}
+                "note": "rank 0; at N>1 the launch also holds the fused AABB and its exchange" if world > 1 else "rank 0"}
 
     # ---- end to end through the C ABI with HOST buffers (pinned): H2D + kernel + D2H every step ------------
     # every rank runs it at the same time (each GPU has its own PCIe link), time = max over ranks
@@ -308,10 +342,10 @@ def run_ours(args):
         "metric": METRIC, "value": value, "unit": "points/s", "n_gpus": world, "steps": args.steps, "warmup": max(3, args.warmup),
         "ms_per_step": total_ms / args.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
         "dtype": "f64", "data": "synthetic",
-        "config": {"workload": ("C5: per-GPU 100M-point shard convert + fused AABB + 48 B NCCL all-reduce(min)" if world > 1 else
+        "config": {"workload": ("C5: per-GPU 100M-point shard convert + fused AABB + global AABB exchange" if world > 1 else
                                 "C2: 100M-point interleaved->columnar convert + scale/offset on 1xB200" +
                                 (" + fused AABB" if fused else "")),
-                   "points_per_gpu": n, "source": "VectorBuffer raw LAS fmt0 (20 B/pt)",
+                   "points_per_gpu": n, "bounds_exchange": exchange, "source": "VectorBuffer raw LAS fmt0 (20 B/pt)",
                    "target": "HashMapBuffer LasPointFormat0 (10 columns, 35 B/pt)", "parallelism": f"point-range shards x{world}",
                    "l2_policy": "inputs (2.0 GB) and outputs (3.5 GB) per step are far larger than the 126 MB L2"},
         "roofline": roofline, "cpu_baseline": cpu, "e2e": e2e, "gpu_launches": int(launches),
@@ -331,6 +365,7 @@ def main():
     ap.add_argument("--points", type=int, default=POINTS_PER_GPU, help="points per GPU (default: the 100 M of C2)")
     ap.add_argument("--e2e-points", type=int, default=POINTS_PER_GPU)
     ap.add_argument("--fused-bounds", action="store_true", help="N=1: also fuse the AABB (always on for N>1)")
+    ap.add_argument("--nccl-bounds", action="store_true", help="N>1: exchange the AABB with an NCCL all-reduce instead of peer memory")
     ap.add_argument("--no-e2e", action="store_true")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--param", action="append", default=[], help="tuning knob key=value (pb200_ctx_set_param), e.g. convert.threads=512")

@@ -251,6 +251,31 @@ int pb200_result_buffer_desc(const pb200_result_buffer* r, pb200_buffer_desc* ou
 int pb200_result_buffer_voxel_keys(const pb200_result_buffer* r, uint64_t* keys_out);
 void pb200_result_buffer_destroy(pb200_result_buffer* r);
 
+/* ---- peer-memory communicator --------------------------------------------------------
+ * The global AABB of a cloud sharded over the GPUs of one box WITHOUT a separate collective: the last CTA of the fused
+ * convert kernel stores its six min/max keys straight into every peer's exchange buffer over NVLink, signals, waits
+ * for the peers' stores and reduces.  Each rank creates a communicator, publishes its 64-byte CUDA-IPC handle
+ * (one process per GPU: exchange them with any host-side all-gather) or its raw device pointer (one process driving
+ * several GPUs), connects, and then calls the _with_global_bounds conversion in lockstep with its peers. */
+#define PB200_COMM_HANDLE_BYTES 64
+typedef struct pb200_comm pb200_comm;
+int pb200_comm_create(pb200_ctx* ctx, int rank, int world, pb200_comm** out);
+int pb200_comm_handle(pb200_comm* c, void* handle_out /* PB200_COMM_HANDLE_BYTES */);
+int pb200_comm_connect(pb200_comm* c, const void* handles /* world x PB200_COMM_HANDLE_BYTES, rank order */);
+int pb200_comm_exchange_ptr(pb200_comm* c, void** device_ptr_out);
+int pb200_comm_connect_ptrs(pb200_comm* c, void* const* peer_ptrs /* world device pointers, rank order */);
+/* synchronises the context's stream; PB200_ERR_CUDA if a peer failed to arrive within the kernel's 10 s timeout */
+int pb200_comm_check(pb200_comm* c);
+void pb200_comm_destroy(pb200_comm* c);
+/* convert_into_range + fused AABB of the produced POSITION_3D + all-reduce over peer memory, one kernel.
+ * device_minmax6 (device, 6 doubles) receives [min xyz, -max xyz] over ALL ranks (DBL_MAX where no rank has points).
+ * Collective: every rank of the communicator must call it the same number of times.  Returns 1 if this rank's
+ * conversion produces a Vec3f64 POSITION_3D (its shard contributes), 0 if not. */
+int pb200_converter_convert_into_range_with_global_bounds(pb200_converter* cv, const pb200_buffer_desc* src,
+                                                          uint64_t src_begin, uint64_t src_end,
+                                                          const pb200_buffer_desc* dst, uint64_t dst_begin,
+                                                          uint64_t dst_end, pb200_comm* comm, double* device_minmax6);
+
 /* ---- sharded voxel grid ------------------------------------------------------------------
  * A cloud sharded by point range over several GPUs is filtered in three steps: (1) every shard reduces its points to
  * PARTIALS on the grid of the GLOBAL bounding box (the all-reduced AABB: every shard derives the same markers,

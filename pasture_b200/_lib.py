@@ -126,6 +126,14 @@ SIGNATURES = {
     "pb200_result_buffer_desc": (i32, [vp, BD]),
     "pb200_result_buffer_voxel_keys": (i32, [vp, vp]),
     "pb200_result_buffer_destroy": (None, [vp]),
+    "pb200_comm_create": (i32, [vp, i32, i32, PVP]),
+    "pb200_comm_handle": (i32, [vp, vp]),
+    "pb200_comm_connect": (i32, [vp, vp]),
+    "pb200_comm_exchange_ptr": (i32, [vp, PVP]),
+    "pb200_comm_connect_ptrs": (i32, [vp, PVP]),
+    "pb200_comm_check": (i32, [vp]),
+    "pb200_comm_destroy": (None, [vp]),
+    "pb200_converter_convert_into_range_with_global_bounds": (i32, [vp, BD, u64, u64, BD, u64, u64, vp, vp]),
     "pb200_voxelgrid_partials": (i32, [vp, BD, dbl, dbl, dbl, PD, PD, PVP]),
     "pb200_voxelgrid_merge_partials": (i32, [vp, vp, vp, vp, u64, u32, u32, u32, PVP]),
     "pb200_voxel_partials_get": (i32, [vp, C.POINTER(VoxelPartialsDesc)]),

@@ -128,6 +128,15 @@ class BufferLayoutConverter:
             self._h, C.byref(sd), source_range.start, source_range.stop, C.byref(dd), target_range.start,
             target_range.stop, C.c_void_p(minmax6.data_ptr())))
 
+    def convert_into_range_with_global_bounds(self, source_buffer, source_range, target_buffer, target_range, comm, minmax6):
+        """collective over `comm` (sharding.PeerComm): converts this rank's range and leaves the bounds of ALL ranks'
+        produced POSITION_3D as [min xyz, -max xyz] in the CUDA tensor `minmax6` -- one kernel, no NCCL call: the
+        exchange happens over peer memory in the kernel's last CTA"""
+        sd, dd = source_buffer.desc(), target_buffer.desc()
+        return check(lib().pb200_converter_convert_into_range_with_global_bounds(
+            self._h, C.byref(sd), source_range.start, source_range.stop, C.byref(dd), target_range.start,
+            target_range.stop, comm._h, C.c_void_p(minmax6.data_ptr())))
+
 
 def get_default_las_converter(raw_las_layout, target_layout, scale, offset, ctx=None):
     """raw_readers.rs:31-167 (las_header.transforms() -> scale/offset per axis)"""

@@ -3,6 +3,8 @@
 (buffer_conversion.rs:292, containers/slice.rs:16-43).  The only exchange on the conversion path is the global
 AABB: one all-reduce(MIN) of [min xyz, -max xyz] (48 bytes).  The voxel-grid filter adds one key-range all-to-all of
 per-shard partial sums (`voxelgrid_filter_sharded`)."""
+import ctypes as C
+
 import torch
 import torch.distributed as dist
 
@@ -97,3 +99,63 @@ def voxelgrid_filter_sharded(shard, leafsize_x, leafsize_y, leafsize_z, group=No
     bounds = key_range_boundaries(part.cells[0], part.bits[1], part.bits[2], world)
     keys, counts, sums = exchange_partials(part.keys, part.counts, part.sums, split_sizes(part.keys, bounds), group)
     return alg.voxelgrid_merge_partials(keys, counts, sums, part.bits, part.cells, ctx)
+
+
+# ---- peer-memory communicator: the global AABB inside the convert kernel (no NCCL on the data path) ----------------
+
+class PeerComm:
+    """pb200_comm: every rank owns a small exchange buffer that its peers map over NVLink.
+    `PeerComm(ctx, group=None)` -- one process per GPU: the CUDA-IPC handles travel through ONE host-side all-gather at
+    set-up time (torch.distributed, any backend); after that `convert_into_range_with_global_bounds` needs no
+    collective library call.  `PeerComm.local_group(contexts)` wires several contexts of one process by raw pointers."""
+
+    HANDLE_BYTES = 64
+
+    def __init__(self, ctx, group=None, _rank=None, _world=None, _connect=True):
+        from ._lib import check, lib
+        self.ctx = ctx
+        have = dist.is_available() and dist.is_initialized()
+        self.rank = _rank if _rank is not None else (dist.get_rank(group) if have else 0)
+        self.world = _world if _world is not None else (dist.get_world_size(group) if have else 1)
+        h = C.c_void_p()
+        check(lib().pb200_comm_create(ctx._h, self.rank, self.world, C.byref(h)))
+        self._h = h
+        if _connect and self.world > 1:
+            mine = (C.c_uint8 * self.HANDLE_BYTES)()
+            check(lib().pb200_comm_handle(self._h, mine))
+            gathered = [None] * self.world
+            dist.all_gather_object(gathered, bytes(mine), group=group)
+            blob = (C.c_uint8 * (self.HANDLE_BYTES * self.world)).from_buffer_copy(b"".join(gathered))
+            check(lib().pb200_comm_connect(self._h, blob))
+            dist.barrier(group)  # nobody starts publishing before every mapping exists
+
+    @classmethod
+    def local_group(cls, contexts):
+        """one process, several contexts (streams / devices): ranks are the list positions"""
+        from ._lib import check, lib
+        comms = [cls(c, _rank=r, _world=len(contexts), _connect=False) for r, c in enumerate(contexts)]
+        ptrs = (C.c_void_p * len(comms))()
+        for r, cm in enumerate(comms):
+            p = C.c_void_p()
+            check(lib().pb200_comm_exchange_ptr(cm._h, C.byref(p)))
+            ptrs[r] = p.value
+        for cm in comms:
+            check(lib().pb200_comm_connect_ptrs(cm._h, ptrs))
+        return comms
+
+    def check(self):
+        """synchronise and raise if a peer never arrived (the kernel gives up after 10 s)"""
+        from ._lib import check, lib
+        check(lib().pb200_comm_check(self._h))
+
+    def close(self):
+        from ._lib import lib
+        if self._h:
+            lib().pb200_comm_destroy(self._h)
+            self._h = None
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass

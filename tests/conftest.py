@@ -1,6 +1,12 @@
 import os
 import sys
 
+import os
+
+# several spin-waiting kernels of ONE process on ONE device (logical ranks in test_gpu_multigpu.py) must not share a
+# hardware work queue: with the default 8 connections, streams alias and a waiting kernel can block the kernel it waits for
+os.environ.setdefault("CUDA_DEVICE_MAX_CONNECTIONS", "32")
+
 import pytest
 
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
