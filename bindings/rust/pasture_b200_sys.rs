@@ -192,4 +192,30 @@ extern "C" {
                            ops: *const pb200_proj_op, n_ops: u32) -> c_int;
     pub fn pb200_synth_las_fmt0_records(ctx: *mut pb200_ctx, device_out: *mut c_void, first_index: u64, n: u64, seed: u64) -> c_int;
     pub fn pb200_synth_terrain_positions(ctx: *mut pb200_ctx, device_out: *mut c_void, first_index: u64, n: u64, seed: u64) -> c_int;
+    // ---- peer-memory communicator + sharded voxel grid ----
+    pub fn pb200_comm_create(ctx: *mut pb200_ctx, rank: c_int, world: c_int, out: *mut *mut pb200_comm) -> c_int;
+    pub fn pb200_comm_handle(c: *mut pb200_comm, handle_out: *mut c_void) -> c_int;
+    pub fn pb200_comm_connect(c: *mut pb200_comm, handles: *const c_void) -> c_int;
+    pub fn pb200_comm_exchange_ptr(c: *mut pb200_comm, device_ptr_out: *mut *mut c_void) -> c_int;
+    pub fn pb200_comm_connect_ptrs(c: *mut pb200_comm, peer_ptrs: *const *mut c_void) -> c_int;
+    pub fn pb200_comm_check(c: *mut pb200_comm) -> c_int;
+    pub fn pb200_comm_destroy(c: *mut pb200_comm);
+    pub fn pb200_converter_convert_into_range_with_global_bounds(cv: *mut pb200_converter, src: *const pb200_buffer_desc,
+        src_begin: u64, src_end: u64, dst: *const pb200_buffer_desc, dst_begin: u64, dst_end: u64, comm: *mut pb200_comm,
+        device_minmax6: *mut f64) -> c_int;
+    pub fn pb200_voxelgrid_partials(ctx: *mut pb200_ctx, src: *const pb200_buffer_desc, leaf_x: f64, leaf_y: f64, leaf_z: f64,
+        global_min: *const f64, global_max: *const f64, out: *mut *mut pb200_voxel_partials) -> c_int;
+    pub fn pb200_voxelgrid_merge_partials(ctx: *mut pb200_ctx, keys: *const u64, counts: *const u32, sums: *const f64, m: u64,
+        bits_x: u32, bits_y: u32, bits_z: u32, out: *mut *mut pb200_voxel_partials) -> c_int;
+    pub fn pb200_voxel_partials_get(p: *const pb200_voxel_partials, out: *mut pb200_voxel_partials_desc) -> c_int;
+    pub fn pb200_voxel_partials_centroids(p: *const pb200_voxel_partials, positions_out: *mut f64) -> c_int;
+    pub fn pb200_voxel_partials_destroy(p: *mut pb200_voxel_partials);
+}
+
+#[repr(C)] pub struct pb200_comm { _private: [u8; 0] }
+#[repr(C)] pub struct pb200_voxel_partials { _private: [u8; 0] }
+#[repr(C)]
+pub struct pb200_voxel_partials_desc {
+    pub len: u64, pub keys: *const u64, pub counts: *const u32, pub sums: *const f64,
+    pub bits_x: u32, pub bits_y: u32, pub bits_z: u32, pub _pad: u32, pub cells: [u64; 3],
 }
