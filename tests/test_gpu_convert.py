@@ -466,3 +466,52 @@ def test_large_range_matches_direct_kernel_and_torch(ctx):
     got = a.columns[0][: 24 * n].view(torch.float64).view(n, 3)
     assert torch.equal(got, pos)
     assert list(bounds[0]) == pos.min(0).values.tolist() and list(bounds[1]) == pos.max(0).values.tolist()
+
+
+def test_c2_full_size_bit_exact_against_torch_and_direct_kernel(ctx):
+    """BASELINE config C2 at its full 100 M points: every output column of the tile pipeline equals (a) the direct
+    kernel (second implementation) and (b) an independent torch recomputation from the raw record bytes -- positions
+    cast i32 -> f64, * scale, + offset as two roundings (raw_readers.rs:42-48), bit fields (:61-103), plain copies --
+    and the write direction brings every coordinate back to within one LAS unit (truncation, write_helpers.rs:15-17)."""
+    n = 100_000_000 if torch.cuda.get_device_properties(0).total_memory > 100e9 else 4_000_000
+    pl, plt = pb.PointLayout.las_raw(0), pb.PointLayout.las_default(0)
+    src = pb.algorithms.synth_las_fmt0_records(n)
+    scale, offset = (0.001, 0.001, 0.001), (500000.0, 5400000.0, 100.0)
+    cv = pb.get_default_las_converter(pl, plt, scale, offset)
+    a = HashMapBuffer(plt, n, "cuda")
+    bounds = cv.convert_into_range_with_bounds(src, range(0, n), a, range(0, n))
+    ctx.set_param("convert.force_direct", 1)
+    try:
+        b = cv.convert(src, HashMapBuffer)
+    finally:
+        ctx.set_param("convert.force_direct", 0)
+    for i in range(len(plt)):
+        assert torch.equal(a.columns[i], b.columns[i]), plt.at(i)
+    del b
+    rec = src.data[: 20 * n].view(n, 20)
+    xyz = rec[:, :12].contiguous().view(torch.int32).view(n, 3)
+    pos = xyz.double() * 0.001 + torch.tensor(offset, dtype=torch.float64, device="cuda")
+    assert torch.equal(a.columns[0][: 24 * n].view(torch.float64).view(n, 3), pos)
+    assert list(bounds[0]) == pos.min(0).values.tolist() and list(bounds[1]) == pos.max(0).values.tolist()
+    del pos
+    names = [m.name() for m in plt.attributes()]
+    col = lambda name: a.columns[names.index(name)]
+    flags = rec[:, 14]
+    assert torch.equal(col("Intensity")[: 2 * n].view(n, 2), rec[:, 12:14])
+    assert torch.equal(col("ReturnNumber")[:n], flags & 7)
+    assert torch.equal(col("NumberOfReturns")[:n], (flags >> 3) & 7)
+    assert torch.equal(col("ScanDirectionFlag")[:n], (flags >> 6) & 1)
+    assert torch.equal(col("EdgeOfFlightLine")[:n], (flags >> 7) & 1)
+    assert torch.equal(col("Classification")[:n], rec[:, 15])
+    assert torch.equal(col("ScanAngleRank")[:n], rec[:, 16])
+    assert torch.equal(col("UserData")[:n], rec[:, 17])
+    assert torch.equal(col("PointSourceID")[: 2 * n].view(n, 2), rec[:, 18:20])
+    # write direction: (p - offset) / scale truncated back to i32
+    back = pb.VectorBuffer(pl, n, "cuda")
+    wr = pb.BufferLayoutConverter.for_layouts_with_default(plt, pl)
+    wr.set_custom_mapping_with_transformation(A.POSITION_3D, pb.ATTRIBUTE_LOCAL_LAS_POSITION, pb.InvScaleOffset(0.001, offset), True)
+    oor = wr.convert_into(a, back, count_out_of_range=True)
+    xyz2 = back.data[: 20 * n].view(n, 20)[:, :12].contiguous().view(torch.int32).view(n, 3)
+    assert int((xyz2 - xyz).abs().max()) <= 1
+    assert oor == 0
+    assert torch.equal(back.data[: 20 * n].view(n, 20)[:, 12:14], rec[:, 12:14])  # intensity survives the round trip
