@@ -192,6 +192,7 @@ extern "C" {
                            ops: *const pb200_proj_op, n_ops: u32) -> c_int;
     pub fn pb200_synth_las_fmt0_records(ctx: *mut pb200_ctx, device_out: *mut c_void, first_index: u64, n: u64, seed: u64) -> c_int;
     pub fn pb200_synth_terrain_positions(ctx: *mut pb200_ctx, device_out: *mut c_void, first_index: u64, n: u64, seed: u64) -> c_int;
+    pub fn pb200_radix_sort_u64(ctx: *mut pb200_ctx, keys: *mut u64, vals: *mut u32, n: u64, begin_bit: c_int, end_bit: c_int) -> c_int;
     // ---- peer-memory communicator + sharded voxel grid ----
     pub fn pb200_comm_create(ctx: *mut pb200_ctx, rank: c_int, world: c_int, out: *mut *mut pb200_comm) -> c_int;
     pub fn pb200_comm_handle(c: *mut pb200_comm, handle_out: *mut c_void) -> c_int;

@@ -251,6 +251,11 @@ int pb200_result_buffer_desc(const pb200_result_buffer* r, pb200_buffer_desc* ou
 int pb200_result_buffer_voxel_keys(const pb200_result_buffer* r, uint64_t* keys_out);
 void pb200_result_buffer_destroy(pb200_result_buffer* r);
 
+/* ---- radix sort (K8) -----------------------------------------------------------------------------------
+ * Stable LSD radix sort of n device-resident u64 keys by their bits [begin_bit, end_bit), optionally carrying a u32
+ * payload (vals may be NULL); in place from the caller's point of view.  The sort behind the voxel grid and the LBVH. */
+int pb200_radix_sort_u64(pb200_ctx* ctx, uint64_t* keys, uint32_t* vals, uint64_t n, int begin_bit, int end_bit);
+
 /* ---- peer-memory communicator --------------------------------------------------------
  * The global AABB of a cloud sharded over the GPUs of one box WITHOUT a separate collective: the last CTA of the fused
  * convert kernel stores its six min/max keys straight into every peer's exchange buffer over NVLink, signals, waits

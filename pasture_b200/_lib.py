@@ -126,6 +126,7 @@ SIGNATURES = {
     "pb200_result_buffer_desc": (i32, [vp, BD]),
     "pb200_result_buffer_voxel_keys": (i32, [vp, vp]),
     "pb200_result_buffer_destroy": (None, [vp]),
+    "pb200_radix_sort_u64": (i32, [vp, vp, vp, u64, i32, i32]),
     "pb200_comm_create": (i32, [vp, i32, i32, PVP]),
     "pb200_comm_handle": (i32, [vp, vp]),
     "pb200_comm_connect": (i32, [vp, vp]),

@@ -110,6 +110,17 @@ def voxelgrid_filter(buffer, leafsize_x, leafsize_y, leafsize_z, filtered_layout
     return (out, keys) if return_keys else out
 
 
+def radix_sort(keys, vals=None, begin_bit=0, end_bit=64, ctx=None):
+    """K8: stable LSD radix sort of a CUDA int64 tensor (u64 bit patterns) by the bits [begin_bit, end_bit), in place,
+    optionally carrying an int32 payload (stability: equal keys keep their input order)"""
+    ctx = ctx or get_context()
+    assert keys.dtype == torch.int64 and keys.is_contiguous() and keys.is_cuda
+    assert vals is None or (vals.dtype == torch.int32 and vals.is_contiguous() and vals.numel() == keys.numel())
+    check(lib().pb200_radix_sort_u64(ctx._h, C.c_void_p(keys.data_ptr()), C.c_void_p(vals.data_ptr()) if vals is not None else None,
+                                     keys.numel(), begin_bit, end_bit))
+    return keys if vals is None else (keys, vals)
+
+
 class VoxelPartials:
     """Per-voxel partial sums on a (global) voxel grid as device tensors: packed keys (int64 bit pattern of the u64 key
     (ix << (bits_y + bits_z)) | (iy << bits_z) | iz, ascending), point counts (int32) and position sums [V, 3] f64.

@@ -8,6 +8,7 @@
 #include <cstdio>
 #include <cstring>
 #include <string>
+#include <utility>
 #include <vector>
 
 #include "../../include/pasture_b200.h"
@@ -95,5 +96,10 @@ struct DevTmp {
         return cudaMallocAsync(&p, bytes ? bytes : 1, s);
     }
 };
+
+// radix_sort.cu: stable LSD radix sort by the key bits [begin_bit, end_bit); keys/vals are clobbered, the result is in
+// (keys, vals) or (keys_alt, vals_alt) as *in_alt says; vals may be null (keys only); n < 2^30
+int radix_sort_u64(pb200_ctx* ctx, unsigned long long* keys, unsigned long long* keys_alt, uint32_t* vals, uint32_t* vals_alt,
+                   uint64_t n, int begin_bit, int end_bit, bool* in_alt);
 
 }  // namespace pb200

@@ -5,7 +5,7 @@
 // `nearests(point, k)` per point (:108).  Tree shape is not part of the contract; the RESULT is: the k points with the
 // smallest squared distance ((dx*dx + dy*dy) + dz*dz in f64), the query itself included, ascending.  Here:
 //   K10  63-bit Morton codes inside the global AABB (expand_bits_by_3, math/bitmanip.rs:2-10)
-//   K8   radix sort of (code, index); positions gathered into Morton order (padded with +inf to whole buckets)
+//   K8   radix sort of (code, index) (radix_sort.cu); positions gathered into Morton order (padded with +inf to whole buckets)
 //   K11  BUCKETS of 8 consecutive sorted points are the leaves; a Karras-style radix hierarchy is built over the first
 //        code of every bucket (ties broken by bucket number).  One 64-byte record per internal node holds BOTH child
 //        boxes (conservative f32, rounded outwards) and the split, so a visit is four 16-byte loads and decides on both
@@ -17,8 +17,6 @@
 //        only if its box distance (same f64 association as the point distance, hence monotone) is > the current worst.
 //   K13  centroid -> covariance (neighbour order) -> closed-form cubic -> cross products, as written in the reference
 //        (the eigenvalue shift at :446-449 is a no-op there); fused into the query kernel.
-#include <cub/device/device_radix_sort.cuh>
-
 #include <cfloat>
 #include <cmath>
 
@@ -551,13 +549,12 @@ static int build_lbvh(pb200_ctx* ctx, const uint8_t* base, uint64_t stride, uint
     lbvh_codes_kernel<<<grid_for(n, ctx->sm_count), 256, 0, st>>>(base, stride, n, bmin[0], bmin[1], bmin[2], s[0], s[1], s[2],
                                                                   (unsigned long long*)t->codes.p, (uint32_t*)t->idx.p);
     g_launches++;
-    size_t tmp_bytes = 0;
-    cub::DeviceRadixSort::SortPairs(nullptr, tmp_bytes, (const unsigned long long*)t->codes.p, (unsigned long long*)t->codes2.p,
-                                    (const uint32_t*)t->idx.p, (uint32_t*)t->idx2.p, (int)n, 0, 63, st);
-    PB_CUDA(t->tmp.alloc(st, tmp_bytes));
-    PB_CUDA(cub::DeviceRadixSort::SortPairs(t->tmp.p, tmp_bytes, (const unsigned long long*)t->codes.p, (unsigned long long*)t->codes2.p,
-                                            (const uint32_t*)t->idx.p, (uint32_t*)t->idx2.p, (int)n, 0, 63, st));
-    g_launches += 9;
+    {   // K8: own one-sweep radix sort over the 63 code bits; the sorted codes / indices must end up in codes2 / idx2
+        bool in_alt = false;
+        PB_TRY(radix_sort_u64(ctx, (unsigned long long*)t->codes.p, (unsigned long long*)t->codes2.p, (uint32_t*)t->idx.p,
+                              (uint32_t*)t->idx2.p, n, 0, 63, &in_alt));
+        if (!in_alt) { std::swap(t->codes.p, t->codes2.p); std::swap(t->idx.p, t->idx2.p); }
+    }
     gather_positions_kernel<<<grid_for(n_padded, ctx->sm_count), 256, 0, st>>>(base, stride, (const uint32_t*)t->idx2.p, n, n_padded,
                                                                                (double*)t->spos.p);
     g_launches++;

@@ -1,0 +1,269 @@
+// radix_sort.cu -- stable LSD radix sort of 64-bit keys (optionally with a 32-bit payload), 8-bit digits, ONE sweep
+// over the data per digit: the sort behind the voxel grid (K8: packed voxel key | point index, voxel_grid.rs:141-152
+// keeps its voxels sorted) and the LBVH (K8: Morton code, point index).
+//
+//   1. radix_histogram_kernel   one read of the keys -> digit histograms of ALL passes (shared-memory atomics, then
+//                               one global atomic per bin and CTA); a tiny kernel turns them into bin bases
+//   2. radix_onesweep_kernel    per pass.  A CTA takes the next tile (ticket counter: tiles are claimed in order, so a
+//                               CTA only ever waits for tiles that are already running), ranks its 8192 keys by digit
+//                               (warp match-any + warp-private digit counters, stable), publishes the tile's digit
+//                               counts, resolves its global offsets by DECOUPLED LOOK-BACK over the preceding tiles
+//                               (one thread per digit; flag and value share one 32-bit word, so a single relaxed load
+//                               is a consistent snapshot), reorders the tile in shared memory and writes each digit's
+//                               run to its final place: every digit run is a contiguous burst.
+// Algorithmic bytes per key and pass: 8 read + 8 written (+ 4 + 4 with a payload); the histogram adds one 8-byte read.
+#include "internal.h"
+
+namespace pb200 {
+
+namespace rs {
+
+constexpr int RADIX_BITS = 8, RADIX = 1 << RADIX_BITS;
+constexpr int THREADS = 512, WARPS = THREADS / 32, IPT = 16, TILE = THREADS * IPT;  // 8192 keys per tile
+constexpr int MAX_PASSES = 8;
+constexpr uint32_t FLAG_LOCAL = 1u << 30, FLAG_INCLUSIVE = 2u << 30, VALUE_MASK = (1u << 30) - 1u;
+
+struct Passes {
+    int n_passes;
+    int shift[MAX_PASSES];
+    uint32_t mask[MAX_PASSES];
+};
+
+__global__ void __launch_bounds__(512) radix_histogram_kernel(const unsigned long long* __restrict__ keys, unsigned long long n,
+                                                              Passes ps, uint32_t* __restrict__ hist /* [passes][256] */) {
+    __shared__ uint32_t s_hist[MAX_PASSES * RADIX];
+    for (int i = threadIdx.x; i < ps.n_passes * RADIX; i += blockDim.x) s_hist[i] = 0;
+    __syncthreads();
+    // per-thread run cache: consecutive keys of a thread that share a digit (the high digits of Morton codes and of
+    // packed voxel keys are nearly constant) cost one shared atomic per run instead of one per key
+    uint32_t last[MAX_PASSES], run[MAX_PASSES];
+#pragma unroll
+    for (int p = 0; p < MAX_PASSES; ++p) { last[p] = 0; run[p] = 0; }
+    const unsigned long long step = (unsigned long long)gridDim.x * blockDim.x;
+    for (unsigned long long i = (unsigned long long)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += step) {
+        const unsigned long long k = keys[i];
+#pragma unroll
+        for (int p = 0; p < MAX_PASSES; ++p) {
+            if (p < ps.n_passes) {
+                const uint32_t d = (uint32_t)((k >> ps.shift[p]) & ps.mask[p]);
+                if (d != last[p]) {
+                    if (run[p]) atomicAdd(&s_hist[p * RADIX + last[p]], run[p]);
+                    last[p] = d;
+                    run[p] = 0;
+                }
+                ++run[p];
+            }
+        }
+    }
+#pragma unroll
+    for (int p = 0; p < MAX_PASSES; ++p)
+        if (p < ps.n_passes && run[p]) atomicAdd(&s_hist[p * RADIX + last[p]], run[p]);
+    __syncthreads();
+    for (int i = threadIdx.x; i < ps.n_passes * RADIX; i += blockDim.x)
+        if (s_hist[i]) atomicAdd(&hist[i], s_hist[i]);
+}
+
+// exclusive scan of every pass's histogram in place: hist[p][d] -> first output position of digit d in pass p
+__global__ void __launch_bounds__(RADIX) radix_bases_kernel(uint32_t* __restrict__ hist) {
+    __shared__ uint32_t s[RADIX];
+    uint32_t* h = hist + blockIdx.x * RADIX;
+    const uint32_t v = h[threadIdx.x];
+    s[threadIdx.x] = v;
+    __syncthreads();
+    for (int o = 1; o < RADIX; o <<= 1) {
+        const uint32_t t = threadIdx.x >= (unsigned)o ? s[threadIdx.x - o] : 0u;
+        __syncthreads();
+        s[threadIdx.x] += t;
+        __syncthreads();
+    }
+    h[threadIdx.x] = s[threadIdx.x] - v;
+}
+
+template <bool PAIRS>
+__global__ void __launch_bounds__(THREADS, 2)
+radix_onesweep_kernel(const unsigned long long* __restrict__ keys_in, unsigned long long* __restrict__ keys_out,
+                      const uint32_t* __restrict__ vals_in, uint32_t* __restrict__ vals_out, uint32_t n, int shift, uint32_t mask,
+                      const uint32_t* __restrict__ bin_base /* [256] of this pass */, uint32_t* __restrict__ status /* [tiles][256] */,
+                      uint32_t* __restrict__ ticket) {
+    extern __shared__ __align__(16) uint8_t rs_smem[];
+    unsigned long long* s_keys = reinterpret_cast<unsigned long long*>(rs_smem);                  // [TILE]
+    uint32_t* s_vals = reinterpret_cast<uint32_t*>(rs_smem + (size_t)TILE * 8);                    // [TILE] (pairs only)
+    uint16_t* s_cnt = reinterpret_cast<uint16_t*>(rs_smem + (size_t)TILE * (PAIRS ? 12 : 8));      // [WARPS][RADIX], <= 8192
+    uint32_t* s_base = reinterpret_cast<uint32_t*>(s_cnt + WARPS * RADIX);  // [RADIX] first slot of digit d in the sorted tile
+    uint32_t* s_goff = s_base + RADIX;          // [RADIX] global position of sorted-tile slot 0 of digit d, minus s_base[d]
+    uint32_t* s_scan = s_goff + RADIX;          // [WARPS] + tile id
+    const uint32_t tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+
+    if (tid == 0) s_scan[WARPS] = atomicAdd(ticket, 1u);
+    for (uint32_t i = tid; i < WARPS * RADIX / 2; i += THREADS) reinterpret_cast<uint32_t*>(s_cnt)[i] = 0;
+    __syncthreads();
+    const uint32_t tile = s_scan[WARPS];
+    const uint32_t base = tile * (uint32_t)TILE;
+    const uint32_t n_tile = n - base < (uint32_t)TILE ? n - base : (uint32_t)TILE;
+
+    // warp-striped load: warp w owns tile slots [w * 32 * IPT, (w + 1) * 32 * IPT), lane l its slots i * 32 + l
+    unsigned long long key[IPT];
+    uint16_t rank[IPT];
+    const uint32_t wbase = warp * 32u * IPT;
+#pragma unroll
+    for (int i = 0; i < IPT; ++i) {
+        const uint32_t slot = wbase + (uint32_t)i * 32u + lane;
+        key[i] = slot < n_tile ? keys_in[base + slot] : ~0ull;  // padding: highest digit, behind every real key of the tile
+    }
+    // stable ranking inside the warp's chunk: peers of the same digit in this row, plus what earlier rows counted
+    uint16_t* my_cnt = s_cnt + warp * RADIX;
+    const uint32_t lt_mask = (1u << lane) - 1u;
+#pragma unroll
+    for (int i = 0; i < IPT; ++i) {
+        const uint32_t d = (uint32_t)((key[i] >> shift) & mask);
+        const uint32_t peers = __match_any_sync(0xffffffffu, d);
+        const uint32_t before = my_cnt[d];
+        rank[i] = (uint16_t)(before + __popc(peers & lt_mask));
+        __syncwarp();
+        if ((peers & lt_mask) == 0) my_cnt[d] = (uint16_t)(before + __popc(peers));
+        __syncwarp();
+    }
+    __syncthreads();
+    // per digit: exclusive scan over the warps (in place), tile total
+    uint32_t total = 0;
+    if (tid < RADIX) {
+#pragma unroll
+        for (int w = 0; w < WARPS; ++w) { const uint32_t c = s_cnt[w * RADIX + tid]; s_cnt[w * RADIX + tid] = (uint16_t)total; total += c; }
+    }
+    // padding keys all carry digit `mask` (all ones): they are not part of the tile's real counts
+    const uint32_t n_pad = (uint32_t)TILE - n_tile;
+    uint32_t real_total = total;
+    if (tid == mask) real_total -= n_pad;
+    // exclusive scan of the (padded) totals over the 256 digits -> position of each digit inside the sorted tile
+    uint32_t incl = total;
+    if (tid < RADIX) {
+#pragma unroll
+        for (int o = 1; o < 32; o <<= 1) { const uint32_t t = __shfl_up_sync(0xffffffffu, incl, o); if ((int)lane >= o) incl += t; }
+        if (lane == 31) s_scan[warp] = incl;
+    }
+    __syncthreads();
+    if (tid < RADIX) {
+        uint32_t before = 0;
+        for (uint32_t w = 0; w < warp; ++w) before += s_scan[w];
+        const uint32_t tile_base = before + incl - total;
+        s_base[tid] = tile_base;
+        // decoupled look-back: publish the local count, walk back until an inclusive prefix is found
+        uint32_t* my_status = status + (size_t)tile * RADIX + tid;
+        uint32_t excl = 0;
+        if (tile == 0) {
+            *reinterpret_cast<volatile uint32_t*>(my_status) = FLAG_INCLUSIVE | real_total;
+        } else {
+            *reinterpret_cast<volatile uint32_t*>(my_status) = FLAG_LOCAL | real_total;
+            const uint32_t* look = my_status - RADIX;
+            while (true) {
+                const uint32_t s = *reinterpret_cast<const volatile uint32_t*>(look);
+                if (s & FLAG_INCLUSIVE) { excl += s & VALUE_MASK; break; }
+                if (s & FLAG_LOCAL) { excl += s & VALUE_MASK; look -= RADIX; }
+            }
+            *reinterpret_cast<volatile uint32_t*>(my_status) = FLAG_INCLUSIVE | (excl + real_total);
+        }
+        s_goff[tid] = bin_base[tid] + excl - tile_base;
+    }
+    __syncthreads();
+    // reorder the tile in shared memory
+#pragma unroll
+    for (int i = 0; i < IPT; ++i) {
+        const uint32_t d = (uint32_t)((key[i] >> shift) & mask);
+        const uint32_t pos = s_base[d] + my_cnt[d] + rank[i];
+        s_keys[pos] = key[i];
+        if (PAIRS) {  // the payload goes straight from global to its sorted slot (it never occupies registers)
+            const uint32_t slot = wbase + (uint32_t)i * 32u + lane;
+            s_vals[pos] = slot < n_tile ? vals_in[base + slot] : 0u;
+        }
+    }
+    __syncthreads();
+    // every digit's run leaves as one contiguous burst (padding occupies the last slots of the sorted tile)
+    for (uint32_t j = tid; j < n_tile; j += THREADS) {
+        const unsigned long long k = s_keys[j];
+        const uint32_t d = (uint32_t)((k >> shift) & mask);
+        const uint32_t dst = s_goff[d] + j;
+        keys_out[dst] = k;
+        if (PAIRS) vals_out[dst] = s_vals[j];
+    }
+}
+
+}  // namespace rs
+
+// Sorts n keys by the bits [begin_bit, end_bit).  `keys` / `vals` are clobbered; the result ends up in (keys, vals) or in
+// (keys_alt, vals_alt): *in_alt tells which.  vals / vals_alt may be null (keys only).
+int radix_sort_u64(pb200_ctx* ctx, unsigned long long* keys, unsigned long long* keys_alt, uint32_t* vals, uint32_t* vals_alt,
+                   uint64_t n, int begin_bit, int end_bit, bool* in_alt) {
+    using namespace rs;
+    *in_alt = false;
+    if (n <= 1 || end_bit <= begin_bit) return PB200_OK;
+    if (n >= (1ull << 30)) return set_error(PB200_ERR_UNSUPPORTED, "radix sort: more than 2^30 - 1 keys per call");
+    if (end_bit - begin_bit > 64 || begin_bit < 0 || end_bit > 64) return set_error(PB200_ERR_INVALID, "radix sort: bad bit range");
+    cudaStream_t st = ctx->stream;
+    Passes ps;
+    ps.n_passes = (end_bit - begin_bit + RADIX_BITS - 1) / RADIX_BITS;
+    for (int p = 0; p < MAX_PASSES; ++p) { ps.shift[p] = 0; ps.mask[p] = 0; }
+    for (int p = 0; p < ps.n_passes; ++p) {
+        ps.shift[p] = begin_bit + p * RADIX_BITS;
+        const int bits = end_bit - ps.shift[p] < RADIX_BITS ? end_bit - ps.shift[p] : RADIX_BITS;
+        ps.mask[p] = (1u << bits) - 1u;
+    }
+    const uint32_t n_tiles = (uint32_t)((n + TILE - 1) / TILE);
+    DevTmp d_hist, d_status;
+    const size_t hist_bytes = (size_t)MAX_PASSES * RADIX * 4 + MAX_PASSES * 4;  // histograms + one ticket per pass
+    const size_t status_bytes = (size_t)ps.n_passes * n_tiles * RADIX * 4;
+    PB_CUDA(d_hist.alloc(st, hist_bytes));
+    PB_CUDA(d_status.alloc(st, status_bytes));
+    PB_CUDA(cudaMemsetAsync(d_hist.p, 0, hist_bytes, st));
+    PB_CUDA(cudaMemsetAsync(d_status.p, 0, status_bytes, st));
+    uint32_t* hist = (uint32_t*)d_hist.p;
+    uint32_t* tickets = hist + MAX_PASSES * RADIX;
+    const bool pairs = vals != nullptr;
+    const size_t smem = (size_t)TILE * (pairs ? 12 : 8) + (size_t)WARPS * RADIX * 2 + (size_t)(2 * RADIX + WARPS + 4) * 4;
+    static bool attr_set[2] = {false, false};
+    if (!attr_set[pairs ? 1 : 0]) {
+        if (pairs) PB_CUDA(cudaFuncSetAttribute(radix_onesweep_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        else PB_CUDA(cudaFuncSetAttribute(radix_onesweep_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        attr_set[pairs ? 1 : 0] = true;
+    }
+    unsigned long long hb = (n + 511) / 512, cap = (unsigned long long)ctx->sm_count * 4;
+    radix_histogram_kernel<<<(unsigned)(hb < cap ? hb : cap), 512, 0, st>>>(keys, n, ps, hist);
+    radix_bases_kernel<<<ps.n_passes, RADIX, 0, st>>>(hist);
+    g_launches += 2;
+    unsigned long long *src = keys, *dst = keys_alt;
+    uint32_t *vsrc = vals, *vdst = vals_alt;
+    for (int p = 0; p < ps.n_passes; ++p) {
+        uint32_t* status = (uint32_t*)d_status.p + (size_t)p * n_tiles * RADIX;
+        if (pairs)
+            radix_onesweep_kernel<true><<<n_tiles, THREADS, smem, st>>>(src, dst, vsrc, vdst, (uint32_t)n, ps.shift[p], ps.mask[p],
+                                                                        hist + p * RADIX, status, tickets + p);
+        else
+            radix_onesweep_kernel<false><<<n_tiles, THREADS, smem, st>>>(src, dst, nullptr, nullptr, (uint32_t)n, ps.shift[p], ps.mask[p],
+                                                                         hist + p * RADIX, status, tickets + p);
+        g_launches++;
+        unsigned long long* t = src; src = dst; dst = t;
+        uint32_t* tv = vsrc; vsrc = vdst; vdst = tv;
+    }
+    PB_CUDA(cudaGetLastError());
+    *in_alt = (ps.n_passes & 1) != 0;
+    return PB200_OK;
+}
+
+}  // namespace pb200
+
+using namespace pb200;
+
+extern "C" int pb200_radix_sort_u64(pb200_ctx* ctx, uint64_t* keys, uint32_t* vals, uint64_t n, int begin_bit, int end_bit) {
+    if (!ctx || (!keys && n)) return set_error(PB200_ERR_INVALID, "null argument");
+    PB_TRY(ensure_device(ctx));
+    if (n <= 1) return PB200_OK;
+    DevTmp k2, v2;
+    PB_CUDA(k2.alloc(ctx->stream, n * 8));
+    if (vals) PB_CUDA(v2.alloc(ctx->stream, n * 4));
+    bool in_alt = false;
+    PB_TRY(radix_sort_u64(ctx, (unsigned long long*)keys, (unsigned long long*)k2.p, vals, (uint32_t*)v2.p, n, begin_bit, end_bit, &in_alt));
+    if (in_alt) {
+        PB_CUDA(cudaMemcpyAsync(keys, k2.p, n * 8, cudaMemcpyDeviceToDevice, ctx->stream));
+        if (vals) PB_CUDA(cudaMemcpyAsync(vals, v2.p, n * 4, cudaMemcpyDeviceToDevice, ctx->stream));
+    }
+    return PB200_OK;
+}

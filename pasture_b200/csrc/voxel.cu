@@ -504,21 +504,32 @@ static int build_voxel_index(pb200_ctx* ctx, const uint8_t* ppos, uint64_t pstri
     const unsigned blocks = (unsigned)(((n + 255) / 256) < cap ? ((n + 255) / 256) : cap);
     voxel_key_kernel<<<blocks, 256, 0, st>>>(ppos, pstride, n, grid, shift, (unsigned long long*)d_keys.p, (uint32_t*)d_idx.p);
     g_launches++;
-    size_t tmp_bytes = 0;
-    if (packed) {
-        cub::DeviceRadixSort::SortKeys(nullptr, tmp_bytes, (const unsigned long long*)d_keys.p, (unsigned long long*)d_keys2.p, (int)n,
-                                       (int)shift, (int)(shift + key_bits), st);
-        PB_CUDA(d_tmp.alloc(st, tmp_bytes));
-        PB_CUDA(cub::DeviceRadixSort::SortKeys(d_tmp.p, tmp_bytes, (const unsigned long long*)d_keys.p, (unsigned long long*)d_keys2.p, (int)n,
-                                               (int)shift, (int)(shift + key_bits), st));
+    // K8: own one-sweep radix sort (radix_sort.cu); cub only for clouds beyond its 2^30-key limit
+    if (n < (1ull << 30)) {
+        bool in_alt = false;
+        PB_TRY(radix_sort_u64(ctx, (unsigned long long*)d_keys.p, (unsigned long long*)d_keys2.p, packed ? nullptr : (uint32_t*)d_idx.p,
+                              packed ? nullptr : (uint32_t*)d_idx2.p, n, (int)shift, (int)(shift + key_bits), &in_alt));
+        if (!in_alt) {  // the result must end up in d_keys2 / d_idx2 (= vi->sorted_keys / sorted_idx)
+            std::swap(d_keys.p, d_keys2.p);
+            if (!packed) std::swap(d_idx.p, d_idx2.p);
+        }
     } else {
-        cub::DeviceRadixSort::SortPairs(nullptr, tmp_bytes, (const unsigned long long*)d_keys.p, (unsigned long long*)d_keys2.p,
-                                        (const uint32_t*)d_idx.p, (uint32_t*)d_idx2.p, (int)n, 0, (int)key_bits, st);
-        PB_CUDA(d_tmp.alloc(st, tmp_bytes));
-        PB_CUDA(cub::DeviceRadixSort::SortPairs(d_tmp.p, tmp_bytes, (const unsigned long long*)d_keys.p, (unsigned long long*)d_keys2.p,
-                                                (const uint32_t*)d_idx.p, (uint32_t*)d_idx2.p, (int)n, 0, (int)key_bits, st));
+        size_t tmp_bytes = 0;
+        if (packed) {
+            cub::DeviceRadixSort::SortKeys(nullptr, tmp_bytes, (const unsigned long long*)d_keys.p, (unsigned long long*)d_keys2.p, (int)n,
+                                           (int)shift, (int)(shift + key_bits), st);
+            PB_CUDA(d_tmp.alloc(st, tmp_bytes));
+            PB_CUDA(cub::DeviceRadixSort::SortKeys(d_tmp.p, tmp_bytes, (const unsigned long long*)d_keys.p, (unsigned long long*)d_keys2.p, (int)n,
+                                                   (int)shift, (int)(shift + key_bits), st));
+        } else {
+            cub::DeviceRadixSort::SortPairs(nullptr, tmp_bytes, (const unsigned long long*)d_keys.p, (unsigned long long*)d_keys2.p,
+                                            (const uint32_t*)d_idx.p, (uint32_t*)d_idx2.p, (int)n, 0, (int)key_bits, st);
+            PB_CUDA(d_tmp.alloc(st, tmp_bytes));
+            PB_CUDA(cub::DeviceRadixSort::SortPairs(d_tmp.p, tmp_bytes, (const unsigned long long*)d_keys.p, (unsigned long long*)d_keys2.p,
+                                                    (const uint32_t*)d_idx.p, (uint32_t*)d_idx2.p, (int)n, 0, (int)key_bits, st));
+        }
+        g_launches += (uint64_t)((key_bits + 7) / 8) + 1;
     }
-    g_launches += (uint64_t)((key_bits + 7) / 8) + 1;
     // voxel boundaries: heads per tile -> scan -> emit
     const uint32_t n_tiles = (uint32_t)((n + HT_TILE - 1) / HT_TILE);
     PB_CUDA(d_tiles.alloc(st, ((size_t)n_tiles + 1) * 4));
@@ -865,20 +876,19 @@ int pb200_voxelgrid_merge_partials(pb200_ctx* ctx, const uint64_t* keys, const u
     res->bits_x = bits_x; res->bits_y = bits_y; res->bits_z = bits_z;
     if (m == 0) { *out = res; return PB200_OK; }
     auto fail = [&](int rc) { pb200_voxel_partials_destroy(res); return rc; };
-    DevTmp d_keys2, d_idx, d_idx2, d_tmp, d_tiles, d_starts;
+    DevTmp d_keys1, d_keys2, d_idx, d_idx2, d_tiles, d_starts;
     int rc = PB200_OK;
     auto run = [&]() -> int {
-        PB_CUDA(d_keys2.alloc(st, m * 8)); PB_CUDA(d_idx.alloc(st, m * 4)); PB_CUDA(d_idx2.alloc(st, m * 4));
+        PB_CUDA(d_keys1.alloc(st, m * 8)); PB_CUDA(d_keys2.alloc(st, m * 8)); PB_CUDA(d_idx.alloc(st, m * 4)); PB_CUDA(d_idx2.alloc(st, m * 4));
         const unsigned long long cap = (unsigned long long)ctx->sm_count * 16;
         const unsigned blocks = (unsigned)(((m + 255) / 256) < cap ? ((m + 255) / 256) : cap);
         iota_kernel<<<blocks, 256, 0, st>>>((uint32_t*)d_idx.p, m);
-        size_t tmp_bytes = 0;
+        PB_CUDA(cudaMemcpyAsync(d_keys1.p, keys, m * 8, cudaMemcpyDeviceToDevice, st));  // the caller's keys stay intact
         const int end_bit = (int)(bits_x + bits_y + bits_z);
-        cub::DeviceRadixSort::SortPairs(nullptr, tmp_bytes, (const unsigned long long*)keys, (unsigned long long*)d_keys2.p,
-                                        (const uint32_t*)d_idx.p, (uint32_t*)d_idx2.p, (int)m, 0, end_bit, st);
-        PB_CUDA(d_tmp.alloc(st, tmp_bytes));
-        PB_CUDA(cub::DeviceRadixSort::SortPairs(d_tmp.p, tmp_bytes, (const unsigned long long*)keys, (unsigned long long*)d_keys2.p,
-                                                (const uint32_t*)d_idx.p, (uint32_t*)d_idx2.p, (int)m, 0, end_bit, st));
+        bool in_alt = false;
+        PB_TRY(radix_sort_u64(ctx, (unsigned long long*)d_keys1.p, (unsigned long long*)d_keys2.p, (uint32_t*)d_idx.p, (uint32_t*)d_idx2.p,
+                              m, 0, end_bit, &in_alt));
+        if (!in_alt) { std::swap(d_keys1.p, d_keys2.p); std::swap(d_idx.p, d_idx2.p); }  // sorted data in d_keys2 / d_idx2
         const uint32_t n_tiles = (uint32_t)((m + HT_TILE - 1) / HT_TILE);
         PB_CUDA(d_tiles.alloc(st, ((size_t)n_tiles + 1) * 4));
         uint32_t* d_total = (uint32_t*)d_tiles.p + n_tiles;
@@ -897,7 +907,7 @@ int pb200_voxelgrid_merge_partials(pb200_ctx* ctx, const uint64_t* keys, const u
                                                           (uint32_t*)d_starts.p, (unsigned long long*)res->keys, nullptr);
         partials_merge_kernel<<<(unsigned)((V + 127) / 128), 128, 0, st>>>((const uint32_t*)d_starts.p, (const uint32_t*)d_idx2.p, V, counts, sums,
                                                                            (uint32_t*)res->counts, (double*)res->sums);
-        g_launches += 6 + (uint64_t)((end_bit + 7) / 8);
+        g_launches += 5;
         PB_CUDA(cudaGetLastError());
         return PB200_OK;
     };
