@@ -21,6 +21,7 @@ namespace rs {
 constexpr int RADIX_BITS = 8, RADIX = 1 << RADIX_BITS;
 constexpr int THREADS = 512, WARPS = THREADS / 32, IPT = 16, TILE = THREADS * IPT;  // 8192 keys per tile
 constexpr int MAX_PASSES = 8;
+constexpr int LOOK = 8;  // predecessors fetched per look-back batch
 constexpr uint32_t FLAG_LOCAL = 1u << 30, FLAG_INCLUSIVE = 2u << 30, VALUE_MASK = (1u << 30) - 1u;
 
 struct Passes {
@@ -34,30 +35,21 @@ __global__ void __launch_bounds__(512) radix_histogram_kernel(const unsigned lon
     __shared__ uint32_t s_hist[MAX_PASSES * RADIX];
     for (int i = threadIdx.x; i < ps.n_passes * RADIX; i += blockDim.x) s_hist[i] = 0;
     __syncthreads();
-    // per-thread run cache: consecutive keys of a thread that share a digit (the high digits of Morton codes and of
-    // packed voxel keys are nearly constant) cost one shared atomic per run instead of one per key
-    uint32_t last[MAX_PASSES], run[MAX_PASSES];
+    auto count = [&](unsigned long long k) {
 #pragma unroll
-    for (int p = 0; p < MAX_PASSES; ++p) { last[p] = 0; run[p] = 0; }
+        for (int p = 0; p < MAX_PASSES; ++p)
+            if (p < ps.n_passes) atomicAdd(&s_hist[p * RADIX + (uint32_t)((k >> ps.shift[p]) & ps.mask[p])], 1u);
+    };
+    // two keys per 16-byte load (cudaMalloc'd key arrays are 16-byte aligned; an odd tail key is counted separately)
+    const unsigned long long pairs = ((reinterpret_cast<uintptr_t>(keys) & 15) == 0) ? n / 2 : 0;
+    const ulonglong2* k2 = reinterpret_cast<const ulonglong2*>(keys);
     const unsigned long long step = (unsigned long long)gridDim.x * blockDim.x;
-    for (unsigned long long i = (unsigned long long)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += step) {
-        const unsigned long long k = keys[i];
-#pragma unroll
-        for (int p = 0; p < MAX_PASSES; ++p) {
-            if (p < ps.n_passes) {
-                const uint32_t d = (uint32_t)((k >> ps.shift[p]) & ps.mask[p]);
-                if (d != last[p]) {
-                    if (run[p]) atomicAdd(&s_hist[p * RADIX + last[p]], run[p]);
-                    last[p] = d;
-                    run[p] = 0;
-                }
-                ++run[p];
-            }
-        }
+    for (unsigned long long i = (unsigned long long)blockIdx.x * blockDim.x + threadIdx.x; i < pairs; i += step) {
+        const ulonglong2 v = k2[i];
+        count(v.x);
+        count(v.y);
     }
-#pragma unroll
-    for (int p = 0; p < MAX_PASSES; ++p)
-        if (p < ps.n_passes && run[p]) atomicAdd(&s_hist[p * RADIX + last[p]], run[p]);
+    for (unsigned long long i = 2 * pairs + (unsigned long long)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += step) count(keys[i]);
     __syncthreads();
     for (int i = threadIdx.x; i < ps.n_passes * RADIX; i += blockDim.x)
         if (s_hist[i]) atomicAdd(&hist[i], s_hist[i]);
@@ -110,18 +102,34 @@ radix_onesweep_kernel(const unsigned long long* __restrict__ keys_in, unsigned l
         const uint32_t slot = wbase + (uint32_t)i * 32u + lane;
         key[i] = slot < n_tile ? keys_in[base + slot] : ~0ull;  // padding: highest digit, behind every real key of the tile
     }
-    // stable ranking inside the warp's chunk: peers of the same digit in this row, plus what earlier rows counted
+    // stable ranking inside the warp's chunk: rank = (same-digit keys of earlier rows of this warp) + (same-digit lanes
+    // below me in this row).  The row's leader (lowest peer lane) bumps the warp-private counter -- two 16-bit counters
+    // share a 32-bit word so that a plain 32-bit shared atomic serves both -- and broadcasts the old value.
     uint16_t* my_cnt = s_cnt + warp * RADIX;
+    uint32_t* my_cnt32 = reinterpret_cast<uint32_t*>(my_cnt);
     const uint32_t lt_mask = (1u << lane) - 1u;
+    // MATCH.ANY has a long latency: GROUP rows are matched back to back (independent), then their counters are bumped in
+    // row order (shared atomics of one warp on one address execute in program order, which keeps the ranking stable)
+    constexpr int GROUP = 4;
 #pragma unroll
-    for (int i = 0; i < IPT; ++i) {
-        const uint32_t d = (uint32_t)((key[i] >> shift) & mask);
-        const uint32_t peers = __match_any_sync(0xffffffffu, d);
-        const uint32_t before = my_cnt[d];
-        rank[i] = (uint16_t)(before + __popc(peers & lt_mask));
-        __syncwarp();
-        if ((peers & lt_mask) == 0) my_cnt[d] = (uint16_t)(before + __popc(peers));
-        __syncwarp();
+    for (int i0 = 0; i0 < IPT; i0 += GROUP) {
+        uint32_t d[GROUP], peers[GROUP];
+#pragma unroll
+        for (int g = 0; g < GROUP; ++g) {
+            d[g] = (uint32_t)((key[i0 + g] >> shift) & mask);
+            peers[g] = __match_any_sync(0xffffffffu, d[g]);
+        }
+        uint32_t old[GROUP];
+#pragma unroll
+        for (int g = 0; g < GROUP; ++g) {
+            old[g] = 0;
+            if ((peers[g] & lt_mask) == 0) old[g] = atomicAdd(&my_cnt32[d[g] >> 1], (uint32_t)__popc(peers[g]) << ((d[g] & 1u) * 16u));
+        }
+#pragma unroll
+        for (int g = 0; g < GROUP; ++g) {
+            const uint32_t o = __shfl_sync(0xffffffffu, old[g], __ffs((int)peers[g]) - 1);
+            rank[i0 + g] = (uint16_t)(((o >> ((d[g] & 1u) * 16u)) & 0xFFFFu) + __popc(peers[g] & lt_mask));
+        }
     }
     __syncthreads();
     // per digit: exclusive scan over the warps (in place), tile total
@@ -142,30 +150,18 @@ radix_onesweep_kernel(const unsigned long long* __restrict__ keys_in, unsigned l
         if (lane == 31) s_scan[warp] = incl;
     }
     __syncthreads();
+    uint32_t tile_base = 0;
+    uint32_t* my_status = status + (size_t)tile * RADIX + tid;
     if (tid < RADIX) {
         uint32_t before = 0;
         for (uint32_t w = 0; w < warp; ++w) before += s_scan[w];
-        const uint32_t tile_base = before + incl - total;
+        tile_base = before + incl - total;
         s_base[tid] = tile_base;
-        // decoupled look-back: publish the local count, walk back until an inclusive prefix is found
-        uint32_t* my_status = status + (size_t)tile * RADIX + tid;
-        uint32_t excl = 0;
-        if (tile == 0) {
-            *reinterpret_cast<volatile uint32_t*>(my_status) = FLAG_INCLUSIVE | real_total;
-        } else {
-            *reinterpret_cast<volatile uint32_t*>(my_status) = FLAG_LOCAL | real_total;
-            const uint32_t* look = my_status - RADIX;
-            while (true) {
-                const uint32_t s = *reinterpret_cast<const volatile uint32_t*>(look);
-                if (s & FLAG_INCLUSIVE) { excl += s & VALUE_MASK; break; }
-                if (s & FLAG_LOCAL) { excl += s & VALUE_MASK; look -= RADIX; }
-            }
-            *reinterpret_cast<volatile uint32_t*>(my_status) = FLAG_INCLUSIVE | (excl + real_total);
-        }
-        s_goff[tid] = bin_base[tid] + excl - tile_base;
+        // publish the tile's own count at once: successors can already add it while this tile is still looking back
+        *reinterpret_cast<volatile uint32_t*>(my_status) = (tile == 0 ? FLAG_INCLUSIVE : FLAG_LOCAL) | real_total;
     }
     __syncthreads();
-    // reorder the tile in shared memory
+    // reorder the tile in shared memory (needs only tile-local information) ...
 #pragma unroll
     for (int i = 0; i < IPT; ++i) {
         const uint32_t d = (uint32_t)((key[i] >> shift) & mask);
@@ -175,6 +171,32 @@ radix_onesweep_kernel(const unsigned long long* __restrict__ keys_in, unsigned l
             const uint32_t slot = wbase + (uint32_t)i * 32u + lane;
             s_vals[pos] = slot < n_tile ? vals_in[base + slot] : 0u;
         }
+    }
+    // ... then resolve the global offsets by decoupled look-back (one thread per digit)
+    if (tid < RADIX) {
+        uint32_t excl = 0;
+        if (tile != 0) {
+            // Speculative batches: the LOOK predecessors' words are loaded at once (independent L2 round trips instead of
+            // a chain of them), then consumed in order; an unpublished word ends the batch and is polled again.
+            int look = (int)tile - 1;
+            bool done = false;
+            while (!done) {
+                uint32_t s[LOOK];
+#pragma unroll
+                for (int b = 0; b < LOOK; ++b)
+                    s[b] = look - b >= 0 ? *reinterpret_cast<const volatile uint32_t*>(status + (size_t)(look - b) * RADIX + tid) : FLAG_INCLUSIVE;
+                int consumed = 0;
+#pragma unroll
+                for (int b = 0; b < LOOK; ++b) {
+                    if (done || consumed != b) continue;
+                    if (s[b] & FLAG_INCLUSIVE) { excl += s[b] & VALUE_MASK; done = true; }
+                    else if (s[b] & FLAG_LOCAL) { excl += s[b] & VALUE_MASK; ++consumed; }
+                }
+                look -= consumed;
+            }
+            *reinterpret_cast<volatile uint32_t*>(my_status) = FLAG_INCLUSIVE | (excl + real_total);
+        }
+        s_goff[tid] = bin_base[tid] + excl - tile_base;
     }
     __syncthreads();
     // every digit's run leaves as one contiguous burst (padding occupies the last slots of the sorted tile)
