@@ -6,8 +6,6 @@
 // coalesced for any record stride and the gathered reads stay inside the tile.
 // Algorithmic bytes per point: 2 (mask, read twice) + stride (source) + kept fraction x stride (target).  The reference takes a closure `Fn(usize) -> bool` over the point index; the
 // FFI-crossable form of that is a byte mask with one entry per point (non-zero = keep).
-#include <cub/device/device_scan.cuh>
-
 #include "internal.h"
 
 namespace pb200 {
@@ -187,21 +185,15 @@ int pb200_filter_into(pb200_ctx* ctx, const pb200_buffer_desc* src, const uint8_
     }
     // per-tile match counts -> exclusive scan -> total
     const uint32_t n_tiles = (uint32_t)((n + FT_TILE - 1) / FT_TILE);
-    FBuf d_counts, d_offsets, d_tmp;
-    PB_CUDA(d_counts.alloc(st, (size_t)n_tiles * 4));
-    PB_CUDA(d_offsets.alloc(st, (size_t)n_tiles * 4));
+    FBuf d_offsets;  // per-tile counts, scanned in place into the tiles' output offsets; one extra word for the total
+    PB_CUDA(d_offsets.alloc(st, ((size_t)n_tiles + 1) * 4));
     const uint32_t cap = (uint32_t)ctx->sm_count * 8;
     const uint32_t blocks = n_tiles < cap ? n_tiles : cap;
-    filter_count_kernel<<<blocks, FT_THREADS, 0, st>>>(d_mask, n, n_tiles, (uint32_t*)d_counts.p);
+    filter_count_kernel<<<blocks, FT_THREADS, 0, st>>>(d_mask, n, n_tiles, (uint32_t*)d_offsets.p);
     g_launches++;
-    size_t tmp_bytes = 0;
-    cub::DeviceScan::ExclusiveSum(nullptr, tmp_bytes, (const uint32_t*)d_counts.p, (uint32_t*)d_offsets.p, (int)n_tiles, st);
-    PB_CUDA(d_tmp.alloc(st, tmp_bytes));
-    PB_CUDA(cub::DeviceScan::ExclusiveSum(d_tmp.p, tmp_bytes, (const uint32_t*)d_counts.p, (uint32_t*)d_offsets.p, (int)n_tiles, st));
-    g_launches++;
-    uint32_t last[2];
-    PB_CUDA(cudaMemcpyAsync(&last[0], (uint32_t*)d_offsets.p + (n_tiles - 1), 4, cudaMemcpyDeviceToHost, st));
-    PB_CUDA(cudaMemcpyAsync(&last[1], (uint32_t*)d_counts.p + (n_tiles - 1), 4, cudaMemcpyDeviceToHost, st));
+    PB_TRY(exclusive_scan_u32(ctx, (uint32_t*)d_offsets.p, n_tiles, (uint32_t*)d_offsets.p + n_tiles));
+    uint32_t last[2] = {0, 0};
+    PB_CUDA(cudaMemcpyAsync(&last[0], (uint32_t*)d_offsets.p + n_tiles, 4, cudaMemcpyDeviceToHost, st));
     PB_CUDA(cudaStreamSynchronize(st));
     const uint64_t m = (uint64_t)last[0] + last[1];
     *num_matches = m;

@@ -102,4 +102,7 @@ struct DevTmp {
 int radix_sort_u64(pb200_ctx* ctx, unsigned long long* keys, unsigned long long* keys_alt, uint32_t* vals, uint32_t* vals_alt,
                    uint64_t n, int begin_bit, int end_bit, bool* in_alt);
 
+// exclusive prefix sum of n device counters in place (one CTA; meant for per-tile counts), total -> *total_out (device)
+int exclusive_scan_u32(pb200_ctx* ctx, uint32_t* counts, uint32_t n, uint32_t* total_out);
+
 }  // namespace pb200

@@ -14,8 +14,7 @@
 //   per-voxel attribute reduction (:168-689)    K9 one thread per voxel walks its points IN INPUT ORDER (stable sort),
 //                                               so f64 sums round exactly like the reference's sequential loops
 // Output order = lexicographic (ix,iy,iz) = ascending packed key.
-#include <cub/device/device_radix_sort.cuh>
-#include <cub/device/device_scan.cuh>
+#include <cub/device/device_radix_sort.cuh>  // fallback for clouds beyond the own sort's 2^30-key limit only
 
 #include <cfloat>
 #include <climits>
@@ -115,35 +114,6 @@ __global__ void __launch_bounds__(HT_THREADS) heads_count_kernel(const unsigned 
         for (int w = 0; w < HT_THREADS / 32; ++w) t += warp_sum[w];
         tile_counts[blockIdx.x] = t;
     }
-}
-
-// exclusive scan of the tile counts in place (one CTA; a 100 M-point cloud has 48 829 tiles), total -> *total_out
-__global__ void __launch_bounds__(1024) tile_scan_kernel(uint32_t* __restrict__ counts, uint32_t n_tiles, uint32_t* __restrict__ total_out) {
-    __shared__ uint32_t warp_sum[32];
-    __shared__ uint32_t carry_s;
-    if (threadIdx.x == 0) carry_s = 0;
-    __syncthreads();
-    for (uint32_t base = 0; base < n_tiles; base += 1024) {
-        const uint32_t i = base + threadIdx.x;
-        const uint32_t v = i < n_tiles ? counts[i] : 0u;
-        uint32_t x = v;
-        for (int o = 1; o < 32; o <<= 1) { const uint32_t y = __shfl_up_sync(0xffffffffu, x, o); if ((int)(threadIdx.x & 31) >= o) x += y; }
-        if ((threadIdx.x & 31) == 31) warp_sum[threadIdx.x >> 5] = x;
-        __syncthreads();
-        if (threadIdx.x < 32) {
-            uint32_t w = warp_sum[threadIdx.x];
-            for (int o = 1; o < 32; o <<= 1) { const uint32_t y = __shfl_up_sync(0xffffffffu, w, o); if ((int)threadIdx.x >= o) w += y; }
-            warp_sum[threadIdx.x] = w;  // inclusive over warps
-        }
-        __syncthreads();
-        const uint32_t carry = carry_s;
-        const uint32_t before = (threadIdx.x >> 5) ? warp_sum[(threadIdx.x >> 5) - 1] : 0u;
-        if (i < n_tiles) counts[i] = carry + before + x - v;
-        __syncthreads();
-        if (threadIdx.x == 1023) carry_s = carry + before + x;
-        __syncthreads();
-    }
-    if (threadIdx.x == 0) *total_out = carry_s;
 }
 
 // starts[rank] = sorted position of the rank-th voxel's first point, voxel_keys[rank] = its key; in packed mode the point
@@ -318,21 +288,18 @@ __global__ void __launch_bounds__(256) mode_keys_kernel(const uint32_t* __restri
     }
 }
 
-__global__ void __launch_bounds__(256) run_heads_kernel(const unsigned long long* __restrict__ keys, unsigned long long n,
-                                                        uint32_t* __restrict__ head_idx) {
-    const unsigned long long step = (unsigned long long)gridDim.x * blockDim.x;
-    for (unsigned long long i = (unsigned long long)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += step)
-        head_idx[i] = (i == 0 || keys[i] != keys[i - 1]) ? (uint32_t)i : 0u;
-}
-
-__global__ void __launch_bounds__(256) run_vote_kernel(const unsigned long long* __restrict__ keys, const uint32_t* __restrict__ head_of,
-                                                       unsigned long long n, unsigned long long* __restrict__ best) {
+// one vote per run of equal (voxel, value) keys: the thread at a run's head finds its end by binary search in the sorted
+// keys (runs are long in the crowded case this path exists for), then length << 16 | 65535 - value competes per voxel
+__global__ void __launch_bounds__(256) run_vote_kernel(const unsigned long long* __restrict__ keys, unsigned long long n,
+                                                       unsigned long long* __restrict__ best) {
     const unsigned long long step = (unsigned long long)gridDim.x * blockDim.x;
     for (unsigned long long i = (unsigned long long)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += step) {
-        if (i + 1 < n && keys[i + 1] == keys[i]) continue;  // only the last element of a run votes
-        const unsigned long long len = i - head_of[i] + 1ull;
-        const unsigned long long voxel = keys[i] >> 16, biased = keys[i] & 0xFFFFull;
-        atomicMax(&best[voxel], (len << 16) | (65535ull - biased));
+        const unsigned long long k = keys[i];
+        if (i > 0 && keys[i - 1] == k) continue;  // not a head
+        unsigned long long lo = i, hi = n;        // last index with keys[idx] == k lies in [lo, hi)
+        while (hi - lo > 1) { const unsigned long long mid = lo + (hi - lo) / 2; if (keys[mid] == k) lo = mid; else hi = mid; }
+        const unsigned long long len = lo - i + 1ull;
+        atomicMax(&best[k >> 16], (len << 16) | (65535ull - (k & 0xFFFFull)));
     }
 }
 
@@ -345,10 +312,6 @@ __global__ void __launch_bounds__(256) mode_decode_kernel(const unsigned long lo
         else memcpy(dst + v * dst_size, &val, dst_size);
     }
 }
-
-struct MaxU32 {
-    __device__ __forceinline__ uint32_t operator()(uint32_t a, uint32_t b) const { return a > b ? a : b; }
-};
 
 struct Rule { const char* name; uint32_t dtype; ReduceKind kind; };
 static const Rule RULES[] = {  // voxel_grid.rs:461-679, source order
@@ -535,7 +498,7 @@ static int build_voxel_index(pb200_ctx* ctx, const uint8_t* ppos, uint64_t pstri
     PB_CUDA(d_tiles.alloc(st, ((size_t)n_tiles + 1) * 4));
     uint32_t* d_total = (uint32_t*)d_tiles.p + n_tiles;
     heads_count_kernel<<<n_tiles, HT_THREADS, 0, st>>>((const unsigned long long*)d_keys2.p, n, shift, (uint32_t*)d_tiles.p);
-    tile_scan_kernel<<<1, 1024, 0, st>>>((uint32_t*)d_tiles.p, n_tiles, d_total);
+    PB_TRY(exclusive_scan_u32(ctx, (uint32_t*)d_tiles.p, n_tiles, d_total));
     g_launches += 2;
     uint32_t* h_total = (uint32_t*)ctx->h_scratch;
     PB_CUDA(cudaMemcpyAsync(h_total, d_total, 4, cudaMemcpyDeviceToHost, st));
@@ -652,8 +615,7 @@ int pb200_voxelgrid_filter(pb200_ctx* ctx, const pb200_buffer_desc* src, double 
     bool any_mode = false;
     for (const Rule* r : rules) any_mode = any_mode || r->kind == R_MODE || r->kind == R_MODE_BOOL;
     uint32_t max_occ = 0;
-    DevTmp d_mode_keys, d_mode_keys2, d_head, d_head2, d_best, d_mode_tmp, d_occ;
-    size_t mode_tmp_bytes = 0;
+    DevTmp d_mode_keys, d_mode_keys2, d_best, d_occ;
     if (any_mode) {
         PB_CUDA(d_occ.alloc(st, 4));
         PB_CUDA(cudaMemsetAsync(d_occ.p, 0, 4, st));
@@ -664,13 +626,7 @@ int pb200_voxelgrid_filter(pb200_ctx* ctx, const pb200_buffer_desc* src, double 
         max_occ = *h_total;
         if (max_occ > MODE_THREAD_LIMIT) {
             PB_CUDA(d_mode_keys.alloc(st, n * 8)); PB_CUDA(d_mode_keys2.alloc(st, n * 8));
-            PB_CUDA(d_head.alloc(st, n * 4)); PB_CUDA(d_head2.alloc(st, n * 4));
             PB_CUDA(d_best.alloc(st, (V + 1) * 8));
-            size_t t1 = 0, t2 = 0;
-            cub::DeviceRadixSort::SortKeys(nullptr, t1, (const unsigned long long*)d_mode_keys.p, (unsigned long long*)d_mode_keys2.p, (int)n, 0, 64, st);
-            cub::DeviceScan::InclusiveScan(nullptr, t2, (const uint32_t*)d_head.p, (uint32_t*)d_head2.p, MaxU32(), (int)n, st);
-            mode_tmp_bytes = t1 > t2 ? t1 : t2;
-            PB_CUDA(d_mode_tmp.alloc(st, mode_tmp_bytes));
         }
     }
 
@@ -712,19 +668,15 @@ int pb200_voxelgrid_filter(pb200_ctx* ctx, const pb200_buffer_desc* src, double 
             else if (dt == PB200_I8) mode_keys_kernel<int8_t><<<blocks, 256, 0, st>>>(sts, nv, si2, n, ra.src, sstride, ra.src_aligned, mk);
             else if (dt == PB200_I16) mode_keys_kernel<int16_t><<<blocks, 256, 0, st>>>(sts, nv, si2, n, ra.src, sstride, ra.src_aligned, mk);
             else mode_keys_kernel<uint16_t><<<blocks, 256, 0, st>>>(sts, nv, si2, n, ra.src, sstride, ra.src_aligned, mk);
-            size_t tb = mode_tmp_bytes;
-            cudaError_t e2 = cub::DeviceRadixSort::SortKeys(d_mode_tmp.p, tb, (const unsigned long long*)mk, (unsigned long long*)d_mode_keys2.p,
-                                                            (int)n, 0, 16 + (int)bits_for(V + 1), st);
-            if (e2 != cudaSuccess) return fail(cuda_error(e2, "mode sort"));
-            run_heads_kernel<<<blocks, 256, 0, st>>>((const unsigned long long*)d_mode_keys2.p, n, (uint32_t*)d_head.p);
-            tb = mode_tmp_bytes;
-            e2 = cub::DeviceScan::InclusiveScan(d_mode_tmp.p, tb, (const uint32_t*)d_head.p, (uint32_t*)d_head2.p, MaxU32(), (int)n, st);
-            if (e2 != cudaSuccess) return fail(cuda_error(e2, "mode scan"));
+            bool in_alt = false;
+            int src_rc = radix_sort_u64(ctx, mk, (unsigned long long*)d_mode_keys2.p, nullptr, nullptr, n, 0, 16 + (int)bits_for(V + 1), &in_alt);
+            if (src_rc < 0) return fail(src_rc);
+            const unsigned long long* sorted_mk = in_alt ? (const unsigned long long*)d_mode_keys2.p : mk;
             cudaMemsetAsync(d_best.p, 0, (V + 1) * 8, st);
-            run_vote_kernel<<<blocks, 256, 0, st>>>((const unsigned long long*)d_mode_keys2.p, (const uint32_t*)d_head2.p, n, (unsigned long long*)d_best.p);
+            run_vote_kernel<<<blocks, 256, 0, st>>>(sorted_mk, n, (unsigned long long*)d_best.p);
             mode_decode_kernel<<<blocks, 256, 0, st>>>((const unsigned long long*)d_best.p, V, ra.dst, ra.dst_size, rules[a]->kind == R_MODE_BOOL ? 1 : 0,
                                                            (dt == PB200_I8 || dt == PB200_I16) ? 32768ll : 0ll);
-            g_launches += 8;
+            g_launches += 3;
         } else {
             launch_reduce(*rules[a], ra, st);
         }
@@ -893,7 +845,7 @@ int pb200_voxelgrid_merge_partials(pb200_ctx* ctx, const uint64_t* keys, const u
         PB_CUDA(d_tiles.alloc(st, ((size_t)n_tiles + 1) * 4));
         uint32_t* d_total = (uint32_t*)d_tiles.p + n_tiles;
         heads_count_kernel<<<n_tiles, HT_THREADS, 0, st>>>((const unsigned long long*)d_keys2.p, m, 0u, (uint32_t*)d_tiles.p);
-        tile_scan_kernel<<<1, 1024, 0, st>>>((uint32_t*)d_tiles.p, n_tiles, d_total);
+        PB_TRY(exclusive_scan_u32(ctx, (uint32_t*)d_tiles.p, n_tiles, d_total));
         uint32_t* h_total = (uint32_t*)ctx->h_scratch;
         PB_CUDA(cudaMemcpyAsync(h_total, d_total, 4, cudaMemcpyDeviceToHost, st));
         PB_CUDA(cudaStreamSynchronize(st));
