@@ -152,6 +152,7 @@ int pb200_ctx_set_param(pb200_ctx* ctx, const char* key, int64_t v) {
     else if (k == "convert.stages") ctx->stages = v;
     else if (k == "convert.ctas_per_sm") ctx->ctas_per_sm = v;
     else if (k == "convert.force_direct") ctx->force_direct = v;
+    else if (k == "convert.stage_chunk_mb") ctx->stage_chunk_mb = v;
     else if (k == "knn.init_radius") ctx->knn_init_radius = v;
     else if (k == "knn.stats") ctx->knn_stats = v;
     else if (k == "knn.per_axis_codes") ctx->knn_per_axis_codes = v;
