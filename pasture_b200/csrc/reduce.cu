@@ -65,37 +65,66 @@ __global__ void init_keys_kernel(unsigned long long* keys, int nc) {
     else if ((int)threadIdx.x < 2 * nc) keys[threadIdx.x] = KEY_MIN;
 }
 
-// K5 fast path: packed Vec3f64 column (HashMapBuffer POSITION_3D), 16 B aligned. One 16 B load per lane and
-// step; the pair of doubles in chunk c holds components (2c mod 3, 2c+1 mod 3).
+// K5 fast path: packed Vec3f64 column (HashMapBuffer POSITION_3D), 16 B aligned, read as 16-byte chunks (two doubles).
+// A warp step covers 96 consecutive chunks (64 points) with three fully coalesced loads per lane: chunk 96 j + 32 k + lane.
+// The components held by a chunk depend on (k + 2 * lane) mod 3 only -- not on j -- so every lane keeps six private
+// min/max pairs (one per load slot and half), updates them branch-free with strict compares (NaN never enters,
+// bounds.rs:34-51) and maps them to x/y/z once at the end.  12 B-compares per 48 bytes: the kernel is HBM-bound.
 __global__ void __launch_bounds__(256) bounds_flat_f64_kernel(const double2* __restrict__ data, unsigned long long n_doubles,
                                                               unsigned long long* g_keys) {
-    double mn[3] = {DBL_MAX, DBL_MAX, DBL_MAX}, mx[3] = {-DBL_MAX, -DBL_MAX, -DBL_MAX};
+    double mnA[3], mxA[3], mnB[3], mxB[3];
+#pragma unroll
+    for (int k = 0; k < 3; ++k) { mnA[k] = mnB[k] = DBL_MAX; mxA[k] = mxB[k] = -DBL_MAX; }
     const unsigned long long n_chunks = n_doubles >> 1;
-    const unsigned long long stride = (unsigned long long)gridDim.x * blockDim.x;
-    unsigned long long c = (unsigned long long)blockIdx.x * blockDim.x + threadIdx.x;
-    auto upd = [&](unsigned m, double a, double b) {
-        // m = component of a; component of b = (m+1) mod 3. Strict compares ignore NaN (bounds.rs:34-51)
-        if (m == 0) { if (a < mn[0]) mn[0] = a; if (a > mx[0]) mx[0] = a; if (b < mn[1]) mn[1] = b; if (b > mx[1]) mx[1] = b; }
-        else if (m == 1) { if (a < mn[1]) mn[1] = a; if (a > mx[1]) mx[1] = a; if (b < mn[2]) mn[2] = b; if (b > mx[2]) mx[2] = b; }
-        else { if (a < mn[2]) mn[2] = a; if (a > mx[2]) mx[2] = a; if (b < mn[0]) mn[0] = b; if (b > mx[0]) mx[0] = b; }
+    const unsigned lane = threadIdx.x & 31u;
+    const unsigned long long warps = ((unsigned long long)gridDim.x * blockDim.x) >> 5;
+    const unsigned long long warp = ((unsigned long long)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+    const unsigned long long n_steps = n_chunks / 96;
+    auto upd = [&](int k, const double2 v) {
+        mnA[k] = v.x < mnA[k] ? v.x : mnA[k]; mxA[k] = v.x > mxA[k] ? v.x : mxA[k];
+        mnB[k] = v.y < mnB[k] ? v.y : mnB[k]; mxB[k] = v.y > mxB[k] ? v.y : mxB[k];
     };
-    for (; c + 3 * stride < n_chunks; c += 4 * stride) {
-        double2 v0 = __ldg(data + c), v1 = __ldg(data + c + stride), v2 = __ldg(data + c + 2 * stride),
-                v3 = __ldg(data + c + 3 * stride);
-        upd((unsigned)((2 * c) % 3), v0.x, v0.y);
-        upd((unsigned)((2 * (c + stride)) % 3), v1.x, v1.y);
-        upd((unsigned)((2 * (c + 2 * stride)) % 3), v2.x, v2.y);
-        upd((unsigned)((2 * (c + 3 * stride)) % 3), v3.x, v3.y);
+    unsigned long long j = warp;
+    for (; j + warps < n_steps; j += 2 * warps) {  // two steps (six loads) in flight
+        const double2* p = data + j * 96 + lane;
+        const double2* q = data + (j + warps) * 96 + lane;
+        const double2 a0 = __ldg(p), a1 = __ldg(p + 32), a2 = __ldg(p + 64), b0 = __ldg(q), b1 = __ldg(q + 32), b2 = __ldg(q + 64);
+        upd(0, a0); upd(1, a1); upd(2, a2);
+        upd(0, b0); upd(1, b1); upd(2, b2);
     }
-    for (; c < n_chunks; c += stride) {
-        double2 v = __ldg(data + c);
-        upd((unsigned)((2 * c) % 3), v.x, v.y);
+    for (; j < n_steps; j += warps) {
+        const double2* p = data + j * 96 + lane;
+        upd(0, __ldg(p)); upd(1, __ldg(p + 32)); upd(2, __ldg(p + 64));
     }
-    if ((n_doubles & 1) && blockIdx.x == 0 && threadIdx.x == 0) {  // odd tail double (n_doubles = 3*len)
-        const double a = reinterpret_cast<const double*>(data)[n_doubles - 1];
-        const unsigned m = (unsigned)((n_doubles - 1) % 3);
-        if (a < mn[m]) mn[m] = a;
-        if (a > mx[m]) mx[m] = a;
+    // fold the slots into components: the first double of slot k is component (k + 2 * lane) mod 3, the second the next one
+    double mn[3] = {DBL_MAX, DBL_MAX, DBL_MAX}, mx[3] = {-DBL_MAX, -DBL_MAX, -DBL_MAX};
+#pragma unroll
+    for (int k = 0; k < 3; ++k) {
+        const unsigned m = (k + 2u * lane) % 3u, m2 = (m + 1u) % 3u;
+#pragma unroll
+        for (unsigned c = 0; c < 3; ++c) {
+            if (m == c) { if (mnA[k] < mn[c]) mn[c] = mnA[k]; if (mxA[k] > mx[c]) mx[c] = mxA[k]; }
+            if (m2 == c) { if (mnB[k] < mn[c]) mn[c] = mnB[k]; if (mxB[k] > mx[c]) mx[c] = mxB[k]; }
+        }
+    }
+    // tail: the chunks after the last whole step, one per thread of block 0, and an odd last double
+    if (blockIdx.x == 0) {
+        for (unsigned long long c = n_steps * 96 + threadIdx.x; c < n_chunks; c += blockDim.x) {
+            const double2 v = __ldg(data + c);
+            const unsigned m = (unsigned)((2 * c) % 3), m2 = (m + 1u) % 3u;
+#pragma unroll
+            for (unsigned cc = 0; cc < 3; ++cc) {
+                if (m == cc) { if (v.x < mn[cc]) mn[cc] = v.x; if (v.x > mx[cc]) mx[cc] = v.x; }
+                if (m2 == cc) { if (v.y < mn[cc]) mn[cc] = v.y; if (v.y > mx[cc]) mx[cc] = v.y; }
+            }
+        }
+        if ((n_doubles & 1) && threadIdx.x == 0) {  // n_doubles = 3 * len may be odd
+            const double a = reinterpret_cast<const double*>(data)[n_doubles - 1];
+            const unsigned m = (unsigned)((n_doubles - 1) % 3);
+#pragma unroll
+            for (unsigned cc = 0; cc < 3; ++cc)
+                if (m == cc) { if (a < mn[cc]) mn[cc] = a; if (a > mx[cc]) mx[cc] = a; }
+        }
     }
     unsigned long long kmin[3], kmax[3];
     for (int k = 0; k < 3; ++k) { kmin[k] = key_of_f64(mn[k]); kmax[k] = key_of_f64(mx[k]); }
