@@ -167,6 +167,12 @@ __device__ __forceinline__ T ld_attr(const uint8_t* p, bool aligned) {
     return v;
 }
 
+__device__ __forceinline__ double ld_gather_f64(const uint8_t* p) {
+    double v;
+    asm volatile("ld.global.nc.L2::64B.f64 %0, [%1];" : "=d"(v) : "l"(p));
+    return v;
+}
+
 __device__ __forceinline__ unsigned long long f64_as_u64_sat(double v) {  // Rust `as u64`
     if (!(v > 0.0)) return 0;
     if (v >= 18446744073709551616.0) return ULLONG_MAX;
@@ -198,6 +204,14 @@ __global__ void __launch_bounds__(128) voxel_reduce_kernel(ReduceArgs a) {
         double sx = 0.0, sy = 0.0, sz = 0.0;  // voxel_grid.rs:339-379
         for (uint32_t k = b; k < e; ++k) {
             const uint8_t* p = a.src + (unsigned long long)a.sorted_idx[k] * a.src_stride;
+            if constexpr (sizeof(S) == 8 && KIND == R_MEAN_VEC_F64) {
+                if (al) {  // random 24-byte gathers: ask L2 for 64-byte fills instead of the default (larger) granularity
+                    sx = __dadd_rn(sx, ld_gather_f64(p));
+                    sy = __dadd_rn(sy, ld_gather_f64(p + 8));
+                    sz = __dadd_rn(sz, ld_gather_f64(p + 16));
+                    continue;
+                }
+            }
             sx = __dadd_rn(sx, (double)ld_attr<S>(p, al));
             sy = __dadd_rn(sy, (double)ld_attr<S>(p + sizeof(S), al));
             sz = __dadd_rn(sz, (double)ld_attr<S>(p + 2 * sizeof(S), al));
