@@ -2,6 +2,7 @@
 #include "internal.h"
 
 namespace pb200 {
+extern int64_t g_cost_div, g_cost_pack_base, g_cost_pack_per_src;  // convert.cu cost model
 
 std::atomic<uint64_t> g_launches{0};
 static thread_local char g_err[512] = "";
@@ -153,6 +154,9 @@ int pb200_ctx_set_param(pb200_ctx* ctx, const char* key, int64_t v) {
     else if (k == "convert.ctas_per_sm") ctx->ctas_per_sm = v;
     else if (k == "convert.force_direct") ctx->force_direct = v;
     else if (k == "convert.stage_chunk_mb") ctx->stage_chunk_mb = v;
+    else if (k == "convert.cost_div") g_cost_div = v;
+    else if (k == "convert.cost_pack_base") g_cost_pack_base = v;
+    else if (k == "convert.cost_pack_per_src") g_cost_pack_per_src = v;
     else if (k == "knn.init_radius") ctx->knn_init_radius = v;
     else if (k == "knn.stats") ctx->knn_stats = v;
     else if (k == "knn.per_axis_codes") ctx->knn_per_axis_codes = v;

@@ -10,23 +10,38 @@
 
 namespace pb200 {
 
+// points by return number (raw_writers.rs:221-229,259-263): counts16[b] += #points with ReturnNumber == b, b = 1..15.
+// Per-warp 256-bin histograms in shared memory (one shared atomic per point; a packed byte column is read 16 points per
+// load), folded into 15 global atomics per CTA.
 __global__ void __launch_bounds__(256) return_histogram_kernel(const uint8_t* __restrict__ base, unsigned long long stride,
                                                                unsigned long long n, unsigned long long* __restrict__ counts16) {
-    unsigned int c[16];
-#pragma unroll
-    for (int b = 0; b < 16; ++b) c[b] = 0;
+    __shared__ unsigned int s_h[8][256];
+    for (unsigned i = threadIdx.x; i < 8 * 256; i += blockDim.x) (&s_h[0][0])[i] = 0;
+    __syncthreads();
+    unsigned int* h = s_h[threadIdx.x >> 5];
     const unsigned long long step = (unsigned long long)gridDim.x * blockDim.x;
-    const unsigned long long start = (unsigned long long)blockIdx.x * blockDim.x + threadIdx.x;
-    // all lanes of a warp iterate together (n rounded up per warp) so the ballots stay full-warp
-    for (unsigned long long i = start; i - (threadIdx.x & 31) < n; i += step) {
-        const unsigned int v = i < n ? base[i * stride] : 0xFFFFFFFFu;
+    const unsigned long long tid = (unsigned long long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (stride == 1 && (reinterpret_cast<uintptr_t>(base) & 15) == 0) {
+        const uint4* v4 = reinterpret_cast<const uint4*>(base);
+        const unsigned long long n16 = n >> 4;
+        for (unsigned long long i = tid; i < n16; i += step) {
+            const uint4 v = __ldg(v4 + i);
+            const unsigned int w[4] = {v.x, v.y, v.z, v.w};
 #pragma unroll
-        for (int b = 1; b < 16; ++b) c[b] += __popc(__ballot_sync(0xffffffffu, v == (unsigned)b));
+            for (int k = 0; k < 4; ++k) {
+                atomicAdd(&h[w[k] & 0xFFu], 1u); atomicAdd(&h[(w[k] >> 8) & 0xFFu], 1u);
+                atomicAdd(&h[(w[k] >> 16) & 0xFFu], 1u); atomicAdd(&h[w[k] >> 24], 1u);
+            }
+        }
+        for (unsigned long long i = (n16 << 4) + tid; i < n; i += step) atomicAdd(&h[base[i]], 1u);
+    } else {
+        for (unsigned long long i = tid; i < n; i += step) atomicAdd(&h[base[i * stride]], 1u);
     }
-    if ((threadIdx.x & 31) == 0) {
-#pragma unroll
-        for (int b = 1; b < 16; ++b)
-            if (c[b]) atomicAdd(&counts16[b], (unsigned long long)c[b]);
+    __syncthreads();
+    if (threadIdx.x >= 1 && threadIdx.x < 16) {
+        unsigned long long c = 0;
+        for (int w = 0; w < 8; ++w) c += s_h[w][threadIdx.x];
+        if (c) atomicAdd(&counts16[threadIdx.x], c);
     }
 }
 
