@@ -22,10 +22,13 @@ def timed(fn):
         e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
         e0.record(); fn(); e1.record(); torch.cuda.synchronize(); best = min(best, e0.elapsed_time(e1))
     return best
-for div, pbase, psrc in [(24, 6, 4), (24, 12, 8), (24, 24, 12), (24, 36, 16), (24, 48, 24), (24, 64, 32), (32, 36, 16), (16, 24, 12)]:
-    ctx.set_param("convert.cost_div", div); ctx.set_param("convert.cost_pack_base", pbase); ctx.set_param("convert.cost_pack_per_src", psrc)
-    wr = pb.BufferLayoutConverter.for_layouts_with_default(tgt, raw)
-    wr.set_custom_mapping_with_transformation(pb.attributes.POSITION_3D, pb.ATTRIBUTE_LOCAL_LAS_POSITION, pb.InvScaleOffset(0.001, (500000.0, 5400000.0, 100.0)), True)
-    c1 = timed(lambda: wr.convert_into(aos, back))
+ident = pb.BufferLayoutConverter.for_layouts(tgt, tgt)
+dst2 = pb.HashMapBuffer(tgt, n, "cuda")
+for cbase, cstore in [(6, 1), (4, 1), (8, 1), (12, 1), (6, 2), (6, 3), (10, 2), (3, 1)]:
+    ctx.set_param("convert.cost_copy_base", cbase); ctx.set_param("convert.cost_store", cstore)
+    cv2 = pb.get_default_las_converter(raw, tgt, (0.001,) * 3, (500000.0, 5400000.0, 100.0))
+    ident2 = pb.BufferLayoutConverter.for_layouts(tgt, tgt)
+    c2 = timed(lambda: cv2.convert_into(src, dst2))
+    s2a = timed(lambda: ident2.convert_into(col, aos))
     eg = timed(lambda: las.write_points(col, 0, (0.001,) * 3, (500000.0, 5400000.0, 100.0)))
-    print(f"div={div} pack={pbase}+{psrc}/src: C1-on-GPU {c1:.3f} ms, LAS egress {eg:.3f} ms (50M points)", flush=True)
+    print(f"copy_base={cbase} store={cstore}: C2 {c2:.4f} ms, columnar->interleaved {s2a:.3f} ms, LAS egress {eg:.3f} ms (50M points)", flush=True)

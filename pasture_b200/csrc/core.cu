@@ -2,7 +2,7 @@
 #include "internal.h"
 
 namespace pb200 {
-extern int64_t g_cost_div, g_cost_pack_base, g_cost_pack_per_src;  // convert.cu cost model
+extern int64_t g_cost_div, g_cost_pack_base, g_cost_pack_per_src, g_cost_copy_base, g_cost_store;  // convert.cu cost model
 
 std::atomic<uint64_t> g_launches{0};
 static thread_local char g_err[512] = "";
@@ -157,6 +157,8 @@ int pb200_ctx_set_param(pb200_ctx* ctx, const char* key, int64_t v) {
     else if (k == "convert.cost_div") g_cost_div = v;
     else if (k == "convert.cost_pack_base") g_cost_pack_base = v;
     else if (k == "convert.cost_pack_per_src") g_cost_pack_per_src = v;
+    else if (k == "convert.cost_copy_base") g_cost_copy_base = v;
+    else if (k == "convert.cost_store") g_cost_store = v;
     else if (k == "knn.init_radius") ctx->knn_init_radius = v;
     else if (k == "knn.stats") ctx->knn_stats = v;
     else if (k == "knn.per_axis_codes") ctx->knn_per_axis_codes = v;

@@ -78,8 +78,11 @@ __global__ void __launch_bounds__(256) gather_positions_kernel(const uint8_t* __
     for (uint32_t i = blockIdx.x * blockDim.x + threadIdx.x; i < n_padded; i += gridDim.x * blockDim.x) {
         double x = INFINITY, y = INFINITY, z = INFINITY;
         if (i < n) {
-            const double* p = reinterpret_cast<const double*>(base + (unsigned long long)idx[i] * stride);
-            x = p[0]; y = p[1]; z = p[2];
+            // random 24-byte gathers: 64-byte L2 fills (LDG.E.LTC64B) instead of the default granularity
+            const uint8_t* p = base + (unsigned long long)idx[i] * stride;
+            asm volatile("ld.global.nc.L2::64B.f64 %0, [%1];" : "=d"(x) : "l"(p));
+            asm volatile("ld.global.nc.L2::64B.f64 %0, [%1];" : "=d"(y) : "l"(p + 8));
+            asm volatile("ld.global.nc.L2::64B.f64 %0, [%1];" : "=d"(z) : "l"(p + 16));
         }
         out[3 * (size_t)i] = x;
         out[3 * (size_t)i + 1] = y;
