@@ -114,20 +114,44 @@ class PeerComm:
     def __init__(self, ctx, group=None, _rank=None, _world=None, _connect=True):
         from ._lib import check, lib
         self.ctx = ctx
+        self._h = None
         have = dist.is_available() and dist.is_initialized()
         self.rank = _rank if _rank is not None else (dist.get_rank(group) if have else 0)
         self.world = _world if _world is not None else (dist.get_world_size(group) if have else 1)
-        h = C.c_void_p()
-        check(lib().pb200_comm_create(ctx._h, self.rank, self.world, C.byref(h)))
-        self._h = h
-        if _connect and self.world > 1:
-            mine = (C.c_uint8 * self.HANDLE_BYTES)()
-            check(lib().pb200_comm_handle(self._h, mine))
-            gathered = [None] * self.world
-            dist.all_gather_object(gathered, bytes(mine), group=group)
-            blob = (C.c_uint8 * (self.HANDLE_BYTES * self.world)).from_buffer_copy(b"".join(gathered))
-            check(lib().pb200_comm_connect(self._h, blob))
-            dist.barrier(group)  # nobody starts publishing before every mapping exists
+        collective = _connect and self.world > 1
+        # Every rank takes part in every collective of the set-up, whatever happens locally: a rank that fails must not
+        # leave its peers waiting.  Failures are agreed on at the end (all-reduce MIN of an ok flag) and raised everywhere.
+        error = None
+        mine = (C.c_uint8 * self.HANDLE_BYTES)()
+        try:
+            h = C.c_void_p()
+            check(lib().pb200_comm_create(ctx._h, self.rank, self.world, C.byref(h)))
+            self._h = h
+            if collective:
+                check(lib().pb200_comm_handle(self._h, mine))
+        except Exception as exc:  # noqa: BLE001
+            error = exc
+        if not collective:
+            if error is not None:
+                raise error
+            return
+        gathered = [None] * self.world
+        dist.all_gather_object(gathered, bytes(mine) if error is None else b"", group=group)
+        if error is None and all(len(g) == self.HANDLE_BYTES for g in gathered):
+            try:
+                blob = (C.c_uint8 * (self.HANDLE_BYTES * self.world)).from_buffer_copy(b"".join(gathered))
+                check(lib().pb200_comm_connect(self._h, blob))
+            except Exception as exc:  # noqa: BLE001
+                error = exc
+        elif error is None:
+            error = RuntimeError("a peer could not create its exchange buffer")
+        on_gpu = dist.get_backend(group) == "nccl"
+        flag = torch.tensor([0 if error is not None else 1], dtype=torch.int32,
+                            device=torch.device("cuda", ctx.device) if on_gpu else "cpu")
+        dist.all_reduce(flag, op=dist.ReduceOp.MIN, group=group)  # also the barrier: nobody publishes before all mappings exist
+        if int(flag.item()) == 0:
+            self.close()
+            raise RuntimeError(f"peer-memory communicator set-up failed on at least one rank (this rank: {error})")
 
     @classmethod
     def local_group(cls, contexts):
