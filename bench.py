@@ -116,6 +116,39 @@ class ClockSampler:
                 "samples": len(s)}
 
 
+def oracle_row_rates():
+    """The same CPU port timed on the other SURVEY 8a rows (single thread, bounded samples, a few seconds in total), so
+    that the GPU numbers of benchmarks/bench_configs.py (profiles/configs_r1.jsonl) have the reference algorithm's CPU
+    cost beside them: AABB (bounds.rs), voxel grid as written (quadratic insert, voxel_grid.rs) and as a sort-based
+    restatement, kNN normals by brute force (normal_estimation.rs with an exact kNN)."""
+    import numpy as np
+    import oracle as O
+    rows = {}
+
+    def rate(n, fn):
+        t0 = time.perf_counter()
+        fn()
+        return {"points": n, "seconds": round(time.perf_counter() - t0, 3), "points_per_s": n / max(time.perf_counter() - t0, 1e-9)}
+
+    ol = O.OLayout.from_attributes([("Position3D", O.VEC3F64)])
+
+    def cloud(n):
+        b = O.OBuffer(ol, n, True)
+        b.set_attribute("Position3D", O.gen_terrain_positions(0, n))
+        return b
+
+    b = cloud(5_000_000)
+    rows["aabb (calculate_bounds, C3 stream)"] = rate(5_000_000, lambda: O.calculate_bounds(b))
+    b2 = cloud(2_000_000)
+    rows["voxel grid 0.1 m, sort-based restatement"] = rate(2_000_000, lambda: O.voxelgrid_filter(b2, (0.1, 0.1, 0.1), ol, use_sort=True))
+    b3 = cloud(20_000)
+    rows["voxel grid 0.1 m, as written in the reference (sorted-vector insert per point)"] = rate(
+        20_000, lambda: O.voxelgrid_filter(b3, (0.1, 0.1, 0.1), ol))
+    pts = O.gen_terrain_positions(0, 8_000)
+    rows["normals k=16 with brute-force exact kNN"] = rate(8_000, lambda: O.compute_normals(pts, 16))
+    return rows
+
+
 def oracle_convert_rate(n_points, threads, repeats=1):
     """times the CPU restatement of convert_into_range (attribute-outer / point-inner, function-pointer casts,
     buffer_conversion.rs:546-604) on n_points of the C2 stream; returns (points/s, seconds of the best repeat)"""
@@ -336,7 +369,8 @@ def run_ours(args):
         cpu = {"value": rate, "unit": "points/s", "cores": 1, "kind": "port",
                "sample": f"{sample} points of the C2 stream, single thread (the reference path is single-threaded), {secs:.1f} s",
                "mt_value": rate_mt, "mt_cores": cores,
-               "mt_sample": f"{mt_sample} points, {cores} threads over disjoint point ranges, {secs_mt:.1f} s"}
+               "mt_sample": f"{mt_sample} points, {cores} threads over disjoint point ranges, {secs_mt:.1f} s",
+               "other_rows": oracle_row_rates()}
 
     out = {
         "metric": METRIC, "value": value, "unit": "points/s", "n_gpus": world, "steps": args.steps, "warmup": max(3, args.warmup),
