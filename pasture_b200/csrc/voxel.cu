@@ -53,15 +53,17 @@ __device__ __forceinline__ unsigned long long leaf_index(double p, const double*
                                                          double bmin, double inv_leaf) {
     if (n == 0) return 0;  // voxel_grid.rs:31 `!markers.is_empty()`
     // first index with !(m[i] < p): guess from the regular spacing, then walk on the exact (running-sum) markers
-    double g = (p - bmin) * inv_leaf;
-    long long k = (g > 1.0) ? ((g < 9.0e18) ? (long long)g - 1 : (long long)n - 1) : 0;
-    if (k > (long long)n - 1) k = (long long)n - 1;
-    while (k < (long long)n - 1 && m[k] < p) ++k;
-    while (k > 0 && !(m[k - 1] < p)) --k;
-    unsigned long long i = (unsigned long long)k;
-    // clamp to the better fitting marker: [i] or [i-1] (voxel_grid.rs:41-49)
-    if (i > 0 && __dsub_rn(p, m[i - 1]) < __dsub_rn(m[i], p)) --i;
-    return i;
+    // (the two markers around the candidate stay in registers while the walk slides: typically 3 loads per axis)
+    const double g = (p - bmin) * inv_leaf;
+    const int last = (int)n - 1;  // n <= 2^21 + 1
+    int k = (g > 1.0) ? ((g < 4.0e6) ? (int)g - 1 : last) : 0;
+    if (k > last) k = last;
+    double hi = m[k], lo = k > 0 ? m[k - 1] : 0.0;
+    while (k < last && hi < p) { ++k; lo = hi; hi = m[k]; }
+    while (k > 0 && !(lo < p)) { --k; hi = lo; lo = k > 0 ? m[k - 1] : 0.0; }
+    // clamp to the better fitting marker: [k] or [k-1] (voxel_grid.rs:41-49)
+    if (k > 0 && __dsub_rn(p, lo) < __dsub_rn(hi, p)) --k;
+    return (unsigned long long)k;
 }
 
 // idx_bits > 0: packed mode, keys[i] = voxel key << idx_bits | i (no index array)
@@ -136,10 +138,19 @@ __global__ void __launch_bounds__(HT_THREADS) heads_emit_kernel(const unsigned l
         if (lane == 0) part[r][warp] = __popc(b);
     }
     __syncthreads();
-    if (threadIdx.x == 0) {
-        uint32_t run = tile_offsets[blockIdx.x];
-        for (int r = 0; r < HT_ROWS; ++r)
-            for (int w = 0; w < HT_THREADS / 32; ++w) { const uint32_t c = part[r][w]; part[r][w] = run; run += c; }
+    if (warp == 0) {  // exclusive scan of the 64 (row, warp) counts in row-major order by one warp: two entries per lane
+        static_assert(HT_ROWS * (HT_THREADS / 32) == 64, "two entries per lane");
+        uint32_t* flat = &part[0][0];
+        const uint32_t c0 = flat[lane], c1 = flat[lane + 32];
+        uint32_t x0 = c0, x1 = c1;
+#pragma unroll
+        for (int o = 1; o < 32; o <<= 1) {
+            const uint32_t y0 = __shfl_up_sync(0xffffffffu, x0, o), y1 = __shfl_up_sync(0xffffffffu, x1, o);
+            if ((int)lane >= o) { x0 += y0; x1 += y1; }
+        }
+        const uint32_t first_half = __shfl_sync(0xffffffffu, x0, 31), base_off = tile_offsets[blockIdx.x];
+        flat[lane] = base_off + x0 - c0;
+        flat[lane + 32] = base_off + first_half + x1 - c1;
     }
     __syncthreads();
     const unsigned long long idx_mask = shift ? ((1ull << shift) - 1ull) : 0ull;
