@@ -12,10 +12,12 @@ ap.add_argument("--k", type=int, default=16)
 ap.add_argument("--radii", default="-1")
 ap.add_argument("--per-axis", type=int, default=0)
 ap.add_argument("--stats", type=int, default=1)
+ap.add_argument("--heap", type=int, default=0)
 args = ap.parse_args()
 ctx = get_context()
 src = alg.synth_terrain_positions(args.points)
 ctx.set_param("knn.per_axis_codes", args.per_axis)
+ctx.set_param("knn.heap", args.heap)
 for r in [int(x) for x in args.radii.split(",")]:
     ctx.set_param("knn.init_radius", r)
     for rep in range(2):

@@ -161,6 +161,7 @@ int pb200_ctx_set_param(pb200_ctx* ctx, const char* key, int64_t v) {
     else if (k == "convert.cost_store") g_cost_store = v;
     else if (k == "knn.init_radius") ctx->knn_init_radius = v;
     else if (k == "knn.stats") ctx->knn_stats = v;
+    else if (k == "knn.heap") ctx->knn_heap = v;
     else if (k == "knn.per_axis_codes") ctx->knn_per_axis_codes = v;
     else return set_error(PB200_ERR_INVALID, "unknown parameter %s", key);
     return PB200_OK;

@@ -28,7 +28,7 @@ struct pb200_ctx {
     // tuning knobs (0 = automatic)
     int64_t tile_points = 0, threads = 0, stages = 0, ctas_per_sm = 0, force_direct = 0;
     int64_t stage_chunk_mb = 0;  // staged bytes per chunk of the HOST-memspace pipeline (0 = 128 MB)
-    int64_t knn_init_radius = -1, knn_stats = 0, knn_per_axis_codes = 0;  // experiments / diagnostics
+    int64_t knn_init_radius = -1, knn_stats = 0, knn_per_axis_codes = 0, knn_heap = 1;  // experiments / diagnostics
     // scratch
     void* d_scratch = nullptr;  // small device scratch (counters, partials)
     size_t d_scratch_bytes = 0;

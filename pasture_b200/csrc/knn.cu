@@ -19,6 +19,7 @@
 //        (the eigenvalue shift at :446-449 is a no-op there); fused into the query kernel.
 #include <cfloat>
 #include <cmath>
+#include <type_traits>
 
 #include "internal.h"
 
@@ -234,19 +235,19 @@ __device__ __forceinline__ double norm3(const double* a) {
 }
 
 // neighbours: cnt original indices in kNN order; positions fetched through (base, stride)
-__device__ void estimate_normal(const uint8_t* __restrict__ base, unsigned long long stride, const uint32_t* nb, uint32_t cnt,
-                                double normal[3], double* curvature) {
+__device__ void estimate_normal(const uint8_t* __restrict__ base, unsigned long long stride, const uint32_t* nb, uint32_t nb_stride,
+                                uint32_t cnt, double normal[3], double* curvature) {
     // compute_centroid :198-237 (dense case)
     double t0 = 0.0, t1 = 0.0, t2 = 0.0;
     for (uint32_t j = 0; j < cnt; ++j) {
-        const double* p = reinterpret_cast<const double*>(base + (unsigned long long)nb[j] * stride);
+        const double* p = reinterpret_cast<const double*>(base + (unsigned long long)nb[j * nb_stride] * stride);
         t0 = __dadd_rn(t0, p[0]); t1 = __dadd_rn(t1, p[1]); t2 = __dadd_rn(t2, p[2]);
     }
     const double c0 = t0 / (double)cnt, c1 = t1 / (double)cnt, c2 = t2 / (double)cnt;
     // compute_covariance_matrix :240-305
     double C[9] = {0, 0, 0, 0, 0, 0, 0, 0, 0};
     for (uint32_t j = 0; j < cnt; ++j) {
-        const double* p = reinterpret_cast<const double*>(base + (unsigned long long)nb[j] * stride);
+        const double* p = reinterpret_cast<const double*>(base + (unsigned long long)nb[j * nb_stride] * stride);
         const double d0 = __dsub_rn(p[0], c0), d1 = __dsub_rn(p[1], c1), d2 = __dsub_rn(p[2], c2);
         C[4] = __dadd_rn(C[4], __dmul_rn(d1, d1));
         C[5] = __dadd_rn(C[5], __dmul_rn(d1, d2));
@@ -354,6 +355,73 @@ struct KList {
     }
 };
 
+// The same k-list as a binary MAX-heap in shared memory (slot s of thread t at s * 128 + t: conflict-free whatever slots
+// the lanes touch).  Dynamic indexing costs nothing there, so one instantiation serves every k; replacing the root and
+// sifting down touches log2(k) levels instead of all k slots, and the ~50 registers of a 16-entry register list are free
+// for occupancy.  Order: (d2, original index), the root is the worst kept candidate = the pruning bound.
+struct HeapList {
+    double* d;      // this thread's column of the [k][128] arrays
+    uint32_t* j;
+    uint32_t cnt;
+    double bound;   // d[0] once k candidates are kept, +inf before
+    static constexpr uint32_t STRIDE = 128;
+    __device__ __forceinline__ double& D(uint32_t s) { return d[s * STRIDE]; }
+    __device__ __forceinline__ uint32_t& J(uint32_t s) { return j[s * STRIDE]; }
+    __device__ __forceinline__ void init(uint8_t* smem, uint32_t k) {
+        d = reinterpret_cast<double*>(smem) + threadIdx.x;
+        j = reinterpret_cast<uint32_t*>(smem + (size_t)k * STRIDE * 8) + threadIdx.x;
+        cnt = 0;
+        bound = INFINITY;
+    }
+    __device__ __forceinline__ double worst() const { return bound; }
+    __device__ __forceinline__ bool greater(double da, uint32_t ja, double db, uint32_t jb, const uint32_t* __restrict__ sidx) const {
+        return da > db || (da == db && sidx[ja] > sidx[jb]);
+    }
+    // put (dv, jv) into the hole at slot i of a heap of `size` entries and restore the heap below it
+    __device__ __forceinline__ void sift_down(uint32_t i, double dv, uint32_t jv, uint32_t size, const uint32_t* __restrict__ sidx) {
+        while (true) {
+            uint32_t c = 2 * i + 1;
+            if (c >= size) break;
+            double dc = D(c);
+            uint32_t jc = J(c);
+            if (c + 1 < size) {
+                const double d2c = D(c + 1);
+                const uint32_t j2c = J(c + 1);
+                if (greater(d2c, j2c, dc, jc, sidx)) { ++c; dc = d2c; jc = j2c; }
+            }
+            if (!greater(dc, jc, dv, jv, sidx)) break;
+            D(i) = dc; J(i) = jc;
+            i = c;
+        }
+        D(i) = dv; J(i) = jv;
+    }
+    __device__ __forceinline__ void heapify(uint32_t size, const uint32_t* __restrict__ sidx) {
+        for (int i = (int)(size / 2) - 1; i >= 0; --i) sift_down((uint32_t)i, D((uint32_t)i), J((uint32_t)i), size, sidx);
+    }
+    __device__ __forceinline__ void offer(double d2, uint32_t jj, uint32_t k, double limit, const uint32_t* __restrict__ sidx) {
+        if (!(d2 <= limit)) return;  // also rejects NaN and the +inf padding
+        if (cnt < k) {               // filling: append, build the heap when the k-th candidate arrives
+            D(cnt) = d2; J(cnt) = jj;
+            if (++cnt == k) { heapify(k, sidx); bound = D(0); }
+            return;
+        }
+        if (d2 > bound) return;
+        if (d2 == bound && !(sidx[jj] < sidx[J(0)])) return;
+        sift_down(0, d2, jj, k, sidx);  // the root (worst) drops out
+        bound = D(0);
+    }
+    // heap -> ascending (d2, index) order in slots [0, cnt)
+    __device__ __forceinline__ void finish(uint32_t k, const uint32_t* __restrict__ sidx) {
+        if (cnt < k) heapify(cnt, sidx);
+        for (uint32_t m = cnt; m > 1; --m) {
+            const double dv = D(m - 1);
+            const uint32_t jv = J(m - 1);
+            D(m - 1) = D(0); J(m - 1) = J(0);
+            sift_down(0, dv, jv, m - 1, sidx);
+        }
+    }
+};
+
 // MODE 0: kNN lists, 1: radius search, 2: normals, 3: kNN traversal statistics (diagnostics)
 //
 // PACKET traversal: the 32 queries of a warp are consecutive in Morton order (four buckets), so their search regions
@@ -365,8 +433,12 @@ struct KList {
 // Control flow is also arranged so that the (fully unrolled, KMAX-long) list insertion is instantiated exactly once:
 // buckets to scan are queued as a range [pend_lo, pend_hi) -- the priming range first, then the one or two leaf
 // children of the visited node, which are consecutive buckets by construction (gamma, gamma + 1).
+// KMAX = 0 selects the shared-memory heap (HeapList, any k), KMAX > 0 the register list of that width.
 template <int KMAX, int MODE>
 __global__ void __launch_bounds__(128) lbvh_query_kernel(QueryArgs a) {
+    constexpr bool HEAP = KMAX == 0;
+    constexpr int KREG = HEAP ? 1 : KMAX;
+    extern __shared__ __align__(16) uint8_t knn_smem[];
     __shared__ uint32_t s_stack[4][STACK_DEPTH];  // one warp-uniform stack per warp
     const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
     const uint32_t warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
@@ -380,8 +452,9 @@ __global__ void __launch_bounds__(128) lbvh_query_kernel(QueryArgs a) {
     const uint32_t k = a.k;
     const double limit = MODE == 1 ? a.radius2 : DBL_MAX;
     const uint32_t* __restrict__ sidx = a.sidx;
-    KList<KMAX> list;
-    list.init();
+    typename std::conditional<HEAP, HeapList, KList<KREG>>::type list;
+    if constexpr (HEAP) list.init(knn_smem, k);
+    else list.init();
     // prime the lists from the warp's own buckets and their neighbours in Morton order
     const uint32_t qb0 = (i - lane) / BUCKET, qb1 = qb0 + 32 / BUCKET - 1;
     const uint32_t ib0 = qb0 > a.init_radius ? qb0 - a.init_radius : 0u;
@@ -452,38 +525,57 @@ __global__ void __launch_bounds__(128) lbvh_query_kernel(QueryArgs a) {
     }
     if (!active) return;
     const uint32_t self = sidx[i];
-    if (MODE == 2) {
-        uint32_t nb[KMAX];  // ascending (d2, index) order = the order kd-tree's nearests() returns
-        uint32_t cnt = 0;
-#pragma unroll KMAX <= 32 ? KMAX : 1
-        for (int s = KMAX - 1; s >= 0; --s)
-            if ((uint32_t)s < k && list.j[s] != NONE) nb[cnt++] = list.j[s];
-        double nrm[3], curv;
-        estimate_normal(reinterpret_cast<const uint8_t*>(a.spos), 24ull, nb, cnt, nrm, &curv);
-        a.normals_out[3 * (size_t)self] = nrm[0];
-        a.normals_out[3 * (size_t)self + 1] = nrm[1];
-        a.normals_out[3 * (size_t)self + 2] = nrm[2];
-        a.curvature_out[self] = curv;
-        return;
-    }
     if (MODE == 3) {  // (nodes visited, buckets scanned, candidates offered) per query
         a.idx_out[(size_t)self * 3] = st_nodes;
         a.idx_out[(size_t)self * 3 + 1] = st_buckets;
         a.idx_out[(size_t)self * 3 + 2] = st_offers;
         return;
     }
-    uint32_t cnt = 0;
-#pragma unroll KMAX <= 32 ? KMAX : 1
-    for (int s = 0; s < KMAX; ++s) {
-        if ((uint32_t)s < k) {
-            const uint32_t o = k - 1u - (uint32_t)s;
-            const bool valid = list.j[s] != NONE;
-            cnt += valid ? 1u : 0u;
-            if (a.idx_out) a.idx_out[(size_t)self * k + o] = valid ? sidx[list.j[s]] : NONE;
-            if (a.d2_out) a.d2_out[(size_t)self * k + o] = list.d[s];
+    if constexpr (HEAP) {
+        list.finish(k, sidx);  // ascending (d2, index) order = the order kd-tree's nearests() returns
+        if (MODE == 2) {
+            double nrm[3], curv;
+            estimate_normal(reinterpret_cast<const uint8_t*>(a.spos), 24ull, list.j, HeapList::STRIDE, list.cnt, nrm, &curv);
+            a.normals_out[3 * (size_t)self] = nrm[0];
+            a.normals_out[3 * (size_t)self + 1] = nrm[1];
+            a.normals_out[3 * (size_t)self + 2] = nrm[2];
+            a.curvature_out[self] = curv;
+            return;
         }
+        for (uint32_t s = 0; s < k; ++s) {
+            const bool valid = s < list.cnt;
+            if (a.idx_out) a.idx_out[(size_t)self * k + s] = valid ? sidx[list.J(s)] : NONE;
+            if (a.d2_out) a.d2_out[(size_t)self * k + s] = valid ? list.D(s) : INFINITY;
+        }
+        if (a.counts_out) a.counts_out[self] = list.cnt;
+    } else {
+        if (MODE == 2) {
+            uint32_t nb[KREG];  // ascending (d2, index) order = the order kd-tree's nearests() returns
+            uint32_t cnt = 0;
+#pragma unroll KREG <= 32 ? KREG : 1
+            for (int s = KREG - 1; s >= 0; --s)
+                if ((uint32_t)s < k && list.j[s] != NONE) nb[cnt++] = list.j[s];
+            double nrm[3], curv;
+            estimate_normal(reinterpret_cast<const uint8_t*>(a.spos), 24ull, nb, 1u, cnt, nrm, &curv);
+            a.normals_out[3 * (size_t)self] = nrm[0];
+            a.normals_out[3 * (size_t)self + 1] = nrm[1];
+            a.normals_out[3 * (size_t)self + 2] = nrm[2];
+            a.curvature_out[self] = curv;
+            return;
+        }
+        uint32_t cnt = 0;
+#pragma unroll KREG <= 32 ? KREG : 1
+        for (int s = 0; s < KREG; ++s) {
+            if ((uint32_t)s < k) {
+                const uint32_t o = k - 1u - (uint32_t)s;
+                const bool valid = list.j[s] != NONE;
+                cnt += valid ? 1u : 0u;
+                if (a.idx_out) a.idx_out[(size_t)self * k + o] = valid ? sidx[list.j[s]] : NONE;
+                if (a.d2_out) a.d2_out[(size_t)self * k + o] = list.d[s];
+            }
+        }
+        if (a.counts_out) a.counts_out[self] = cnt;
     }
-    if (a.counts_out) a.counts_out[self] = cnt;
 }
 
 static unsigned grid_for(uint64_t n, int sm, unsigned block = 256) {
@@ -578,6 +670,24 @@ static int build_lbvh(pb200_ctx* ctx, const uint8_t* base, uint64_t stride, uint
     return PB200_OK;
 }
 
+// the shared-memory heap variant: one instantiation per mode, k * 128 * 12 bytes of dynamic shared memory
+static int launch_query_heap(int mode, const QueryArgs& a, cudaStream_t st) {
+    const unsigned blocks = (a.n + 127) / 128;
+    const size_t smem = (size_t)a.k * 128 * 12;
+    static bool attr_set = false;
+    if (!attr_set) {
+        const int max_smem = MAX_K * 128 * 12;
+        PB_CUDA(cudaFuncSetAttribute(lbvh_query_kernel<0, 0>, cudaFuncAttributeMaxDynamicSharedMemorySize, max_smem));
+        PB_CUDA(cudaFuncSetAttribute(lbvh_query_kernel<0, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize, max_smem));
+        PB_CUDA(cudaFuncSetAttribute(lbvh_query_kernel<0, 2>, cudaFuncAttributeMaxDynamicSharedMemorySize, max_smem));
+        attr_set = true;
+    }
+    if (mode == 0) lbvh_query_kernel<0, 0><<<blocks, 128, smem, st>>>(a);
+    else if (mode == 1) lbvh_query_kernel<0, 1><<<blocks, 128, smem, st>>>(a);
+    else lbvh_query_kernel<0, 2><<<blocks, 128, smem, st>>>(a);
+    return PB200_OK;
+}
+
 template <int KMAX>
 static void launch_query(int mode, const QueryArgs& a, cudaStream_t st) {
     const unsigned blocks = (a.n + 127) / 128;
@@ -607,7 +717,7 @@ static int run_query(pb200_ctx* ctx, const pb200_buffer_desc* buf, int mode, uin
     QueryArgs a{};
     a.n = n; a.nb = tree.nb; a.k = k;
     // the warp's own four buckets +- init_radius buckets prime every lane's list before the traversal
-    a.init_radius = (k + 7) / 8;
+    a.init_radius = ctx->knn_heap ? (k + 15) / 16 : (k + 7) / 8;  // measured per list variant (benchmarks/knn_probe.py)
     if (ctx->knn_init_radius >= 0) a.init_radius = (uint32_t)ctx->knn_init_radius;
     a.spos = tree.sorted_pos();
     a.sidx = (const uint32_t*)tree.idx2.p;
@@ -628,7 +738,8 @@ static int run_query(pb200_ctx* ctx, const pb200_buffer_desc* buf, int mode, uin
     PB_TRY(out_ptr(counts_out, d_cnt, (size_t)n * 4, &p)); a.counts_out = (uint32_t*)p;
     PB_TRY(out_ptr(normals_out, d_nrm, (size_t)n * 24, &p)); a.normals_out = (double*)p;
     PB_TRY(out_ptr(curvature_out, d_curv, (size_t)n * 8, &p)); a.curvature_out = (double*)p;
-    if (k <= 4) launch_query<4>(mode, a, ctx->stream);
+    if (ctx->knn_heap && mode != 3) PB_TRY(launch_query_heap(mode, a, ctx->stream));
+    else if (k <= 4) launch_query<4>(mode, a, ctx->stream);
     else if (k <= 16) launch_query<16>(mode, a, ctx->stream);
     else if (k <= 32) launch_query<32>(mode, a, ctx->stream);
     else launch_query<64>(mode, a, ctx->stream);

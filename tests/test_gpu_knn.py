@@ -18,6 +18,15 @@ from tests import util
 pytestmark = pytest.mark.gpu
 
 
+@pytest.fixture(params=["register_list", "smem_heap"], autouse=True)
+def knn_list_variant(request):
+    """every test of this module runs with both k-list implementations (registers / shared-memory heap)"""
+    ctx = pb.get_context()
+    ctx.set_param("knn.heap", 1 if request.param == "smem_heap" else 0)
+    yield request.param
+    ctx.set_param("knn.heap", 1)  # the default
+
+
 def cloud(pts, columnar=True, device="cuda", extra=False):
     attrs = [("Position3D", O.VEC3F64)] + ([("Intensity", O.U16)] if extra else [])
     ol, pl = util.layouts(attrs)
