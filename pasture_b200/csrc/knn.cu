@@ -472,7 +472,7 @@ __global__ void __launch_bounds__(128) lbvh_query_kernel(QueryArgs a) {
 #pragma unroll
             for (int t = 0; t < BUCKET * 3 / 2; ++t) { const double2 v = __ldg(p + t); c[2 * t] = v.x; c[2 * t + 1] = v.y; }
             uint32_t cand = 0;
-            const double bound = list.worst();
+            const double bound = fmin(list.worst(), limit);  // radius search: nothing beyond r^2 is ever needed, full list or not
 #pragma unroll
             for (int t = 0; t < BUCKET; ++t) {
                 const double dx = c[3 * t] - qx, dy = c[3 * t + 1] - qy, dz = c[3 * t + 2] - qz;
@@ -500,7 +500,7 @@ __global__ void __launch_bounds__(128) lbvh_query_kernel(QueryArgs a) {
         const float dr = box_lower_bound(r1.z, r1.w, r2.x, r2.y, r2.z, r2.w, qlx, qly, qlz, qhx, qhy, qhz);
         const uint32_t cl = split & SPLIT_MASK, cr = cl + 1;
         const bool ll = (split & LEFT_LEAF) != 0, rl = (split & RIGHT_LEAF) != 0;
-        const double bound = list.worst();
+        const double bound = fmin(list.worst(), limit);  // radius search: nothing beyond r^2 is ever needed, full list or not
         const bool need_l = active && (double)dl <= bound, need_r = active && (double)dr <= bound;
         const uint32_t bl = __ballot_sync(0xffffffffu, need_l), br = __ballot_sync(0xffffffffu, need_r);
         const uint32_t left_votes = __popc(__ballot_sync(0xffffffffu, need_l && (!need_r || dl <= dr)));

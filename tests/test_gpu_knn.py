@@ -233,3 +233,35 @@ def test_reproject_matches_oracle_on_random_points():
     got = buf.view_attribute(A.POSITION_3D)
     assert np.all(np.abs(got - expect) < 1e-6), np.abs(got - expect).max()
     assert np.array_equal(got[:, 2], pts[:, 2])  # z passes through
+
+
+def test_radius_search_large_cloud_prunes_by_radius():
+    """400 k points, small radius, list never full: the traversal must prune by r^2 (not only by the k-th distance),
+    and the result must match a grid-hash recomputation"""
+    rng = np.random.default_rng(5)
+    n, r, m = 400_000, 0.004, 16
+    pts = rng.random((n, 3))
+    idx, cnt = radius_search(cloud(pts), r, m)
+    idx = idx.cpu().numpy().view(np.uint32)
+    cnt = cnt.cpu().numpy()
+    cell = np.floor(pts / r).astype(np.int64)
+    order = np.lexsort((cell[:, 2], cell[:, 1], cell[:, 0]))
+    keys = (cell[:, 0] << 40) | (cell[:, 1] << 20) | cell[:, 2]
+    skeys = keys[order]
+    for i in range(0, n, 9973):
+        cand = []
+        c = cell[i]
+        for dx in (-1, 0, 1):
+            for dy in (-1, 0, 1):
+                for dz in (-1, 0, 1):
+                    kk = ((c[0] + dx) << 40) | ((c[1] + dy) << 20) | (c[2] + dz)
+                    lo, hi = np.searchsorted(skeys, kk, "left"), np.searchsorted(skeys, kk, "right")
+                    cand.extend(order[lo:hi].tolist())
+        cand = np.array(sorted(cand))
+        d = pts[cand] - pts[i]
+        d2 = (d[:, 0] * d[:, 0] + d[:, 1] * d[:, 1]) + d[:, 2] * d[:, 2]
+        inside = cand[d2 <= r * r]
+        d2i = d2[d2 <= r * r]
+        expect = inside[np.lexsort((inside, d2i))][:m]
+        assert cnt[i] == len(expect)
+        assert np.array_equal(idx[i, : cnt[i]], expect)
