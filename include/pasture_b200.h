@@ -113,6 +113,7 @@ const char* pb200_last_error(void);
 /* number of kernels this library has launched in this process (bench.py `gpu_launches`) */
 uint64_t pb200_kernel_launch_count(void);
 
+/* A context must outlive every converter, communicator and result object created from it (they keep a pointer to it). */
 int pb200_ctx_create(int device, pb200_ctx** out);
 /* borrow an external CUDA stream (cudaStream_t as void*, e.g. torch.cuda.current_stream().cuda_stream) */
 int pb200_ctx_set_stream(pb200_ctx* ctx, void* cuda_stream);

@@ -35,7 +35,8 @@ struct pb200_ctx {
     void* h_scratch = nullptr;  // pinned host scratch for small readbacks
     // staging for HOST memspace buffers
     cudaStream_t copy_in = nullptr, copy_out = nullptr;
-    bool convert_attr_set = false;
+    bool convert_attr_set = false;  // cudaFuncSetAttribute is per device: every context configures its kernels once
+    bool sort_attr_set[2] = {false, false}, knn_attr_set = false;
 };
 
 namespace pb200 {

@@ -671,16 +671,15 @@ static int build_lbvh(pb200_ctx* ctx, const uint8_t* base, uint64_t stride, uint
 }
 
 // the shared-memory heap variant: one instantiation per mode, k * 128 * 12 bytes of dynamic shared memory
-static int launch_query_heap(int mode, const QueryArgs& a, cudaStream_t st) {
+static int launch_query_heap(pb200_ctx* ctx, int mode, const QueryArgs& a, cudaStream_t st) {
     const unsigned blocks = (a.n + 127) / 128;
     const size_t smem = (size_t)a.k * 128 * 12;
-    static bool attr_set = false;
-    if (!attr_set) {
+    if (!ctx->knn_attr_set) {
         const int max_smem = MAX_K * 128 * 12;
         PB_CUDA(cudaFuncSetAttribute(lbvh_query_kernel<0, 0>, cudaFuncAttributeMaxDynamicSharedMemorySize, max_smem));
         PB_CUDA(cudaFuncSetAttribute(lbvh_query_kernel<0, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize, max_smem));
         PB_CUDA(cudaFuncSetAttribute(lbvh_query_kernel<0, 2>, cudaFuncAttributeMaxDynamicSharedMemorySize, max_smem));
-        attr_set = true;
+        ctx->knn_attr_set = true;
     }
     if (mode == 0) lbvh_query_kernel<0, 0><<<blocks, 128, smem, st>>>(a);
     else if (mode == 1) lbvh_query_kernel<0, 1><<<blocks, 128, smem, st>>>(a);
@@ -738,7 +737,7 @@ static int run_query(pb200_ctx* ctx, const pb200_buffer_desc* buf, int mode, uin
     PB_TRY(out_ptr(counts_out, d_cnt, (size_t)n * 4, &p)); a.counts_out = (uint32_t*)p;
     PB_TRY(out_ptr(normals_out, d_nrm, (size_t)n * 24, &p)); a.normals_out = (double*)p;
     PB_TRY(out_ptr(curvature_out, d_curv, (size_t)n * 8, &p)); a.curvature_out = (double*)p;
-    if (ctx->knn_heap && mode != 3) PB_TRY(launch_query_heap(mode, a, ctx->stream));
+    if (ctx->knn_heap && mode != 3) PB_TRY(launch_query_heap(ctx, mode, a, ctx->stream));
     else if (k <= 4) launch_query<4>(mode, a, ctx->stream);
     else if (k <= 16) launch_query<16>(mode, a, ctx->stream);
     else if (k <= 32) launch_query<32>(mode, a, ctx->stream);

@@ -278,7 +278,7 @@ int radix_sort_u64(pb200_ctx* ctx, unsigned long long* keys, unsigned long long*
     uint32_t* tickets = hist + MAX_PASSES * RADIX;
     const bool pairs = vals != nullptr;
     const size_t smem = (size_t)TILE * (pairs ? 12 : 8) + (size_t)WARPS * RADIX * 2 + (size_t)(2 * RADIX + WARPS + 4) * 4;
-    static bool attr_set[2] = {false, false};
+    bool* attr_set = ctx->sort_attr_set;
     if (!attr_set[pairs ? 1 : 0]) {
         if (pairs) PB_CUDA(cudaFuncSetAttribute(radix_onesweep_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
         else PB_CUDA(cudaFuncSetAttribute(radix_onesweep_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
