@@ -98,6 +98,37 @@ def test_compute_fails_loudly_without_gpu():
     assert b"no CPU fallback" in _lib.lib().pb200_last_error()
 
 
+def test_new_entry_points_reject_null_handles():
+    """argument validation of the communicator / sort / sharded-voxel entry points happens before any CUDA call"""
+    L = _lib.lib()
+    h = C.c_void_p()
+    INVALID = -8  # PB200_ERR_INVALID
+    assert L.pb200_comm_create(None, 0, 1, C.byref(h)) == INVALID
+    assert L.pb200_comm_handle(None, None) == INVALID
+    assert L.pb200_comm_connect(None, None) == INVALID
+    assert L.pb200_comm_check(None) == INVALID
+    assert L.pb200_radix_sort_u64(None, None, None, 8, 0, 64) == INVALID
+    assert L.pb200_voxelgrid_merge_partials(None, None, None, None, 0, 1, 1, 1, C.byref(h)) == INVALID
+    assert L.pb200_voxel_partials_get(None, None) == INVALID
+    assert L.pb200_converter_convert_into_range_with_global_bounds(None, None, 0, 0, None, 0, 0, None, None) < 0
+    L.pb200_comm_destroy(None)            # destroying nothing is allowed
+    L.pb200_voxel_partials_destroy(None)
+
+
+def test_sharding_key_ranges_partition_every_key():
+    """host logic of the key-range all-to-all: boundaries are ascending, every packed key has exactly one owner"""
+    from pasture_b200 import sharding
+    rng = np.random.default_rng(4)
+    for cells_x, by, bz, world in [(1, 1, 1, 3), (10, 3, 2, 4), (5001, 13, 8, 8), (7, 4, 4, 2)]:
+        b = sharding.key_range_boundaries(cells_x, by, bz, world)
+        assert len(b) == world - 1 and b == sorted(b)
+        keys = np.sort(rng.integers(0, max(1, cells_x) << (by + bz), 5000)).astype(np.int64)
+        sizes = sharding.split_sizes(torch.from_numpy(keys), b)
+        assert len(sizes) == world and sum(sizes) == len(keys)
+        owner = np.searchsorted(np.array(b, dtype=np.int64), keys, side="right") if b else np.zeros(len(keys), int)
+        assert [int((owner == d).sum()) for d in range(world)] == sizes
+
+
 def test_product_does_not_import_oracle():
     """the product package must never route through oracle/"""
     pkg = os.path.join(ROOT, "pasture_b200")
