@@ -183,6 +183,16 @@ __device__ __forceinline__ double ld_gather_f64(const uint8_t* p) {
     asm volatile("ld.global.nc.L2::64B.f64 %0, [%1];" : "=d"(v) : "l"(p));
     return v;
 }
+// three consecutive doubles at an 8-byte aligned address as one 16-byte and one 8-byte load
+__device__ __forceinline__ void ld_gather_pos24(const uint8_t* p, double& x, double& y, double& z) {
+    if ((reinterpret_cast<uintptr_t>(p) & 15) == 0) {
+        asm volatile("ld.global.nc.L2::64B.v2.f64 {%0, %1}, [%2];" : "=d"(x), "=d"(y) : "l"(p));
+        z = ld_gather_f64(p + 16);
+    } else {
+        x = ld_gather_f64(p);
+        asm volatile("ld.global.nc.L2::64B.v2.f64 {%0, %1}, [%2];" : "=d"(y), "=d"(z) : "l"(p + 8));
+    }
+}
 
 __device__ __forceinline__ unsigned long long f64_as_u64_sat(double v) {  // Rust `as u64`
     if (!(v > 0.0)) return 0;
@@ -216,10 +226,13 @@ __global__ void __launch_bounds__(128) voxel_reduce_kernel(ReduceArgs a) {
         for (uint32_t k = b; k < e; ++k) {
             const uint8_t* p = a.src + (unsigned long long)a.sorted_idx[k] * a.src_stride;
             if constexpr (sizeof(S) == 8 && KIND == R_MEAN_VEC_F64) {
-                if (al) {  // random 24-byte gathers: ask L2 for 64-byte fills instead of the default (larger) granularity
-                    sx = __dadd_rn(sx, ld_gather_f64(p));
-                    sy = __dadd_rn(sy, ld_gather_f64(p + 8));
-                    sz = __dadd_rn(sz, ld_gather_f64(p + 16));
+                if (al) {  // random 24-byte gathers: 64-byte L2 fills, and TWO loads per point (16 + 8 bytes, whichever
+                           // half is 16-byte aligned): the L1 tag stage, not DRAM, limits this kernel once fills are small
+                    double x, y, z;
+                    ld_gather_pos24(p, x, y, z);
+                    sx = __dadd_rn(sx, x);
+                    sy = __dadd_rn(sy, y);
+                    sz = __dadd_rn(sz, z);
                     continue;
                 }
             }
@@ -393,8 +406,9 @@ __global__ void __launch_bounds__(128) voxel_partial_sums_kernel(const uint32_t*
     const uint32_t b = starts[v], e = starts[v + 1];
     double sx = 0.0, sy = 0.0, sz = 0.0;
     for (uint32_t k = b; k < e; ++k) {
-        const double* p = reinterpret_cast<const double*>(pos + (unsigned long long)sorted_idx[k] * stride);
-        sx = __dadd_rn(sx, p[0]); sy = __dadd_rn(sy, p[1]); sz = __dadd_rn(sz, p[2]);
+        double x, y, z;
+        ld_gather_pos24(pos + (unsigned long long)sorted_idx[k] * stride, x, y, z);
+        sx = __dadd_rn(sx, x); sy = __dadd_rn(sy, y); sz = __dadd_rn(sz, z);
     }
     counts[v] = e - b;
     sums[3 * v] = sx; sums[3 * v + 1] = sy; sums[3 * v + 2] = sz;
