@@ -266,14 +266,15 @@ def run_ours(args):
     for _ in range(max(3, args.warmup)):
         step()
     torch.cuda.synchronize()
-    if world > 1:
-        dist.barrier()
-        torch.cuda.synchronize()
 
     # ---- timed region: exactly K steps, CUDA events on the launching stream (torch's current stream) ----
     ev = [torch.cuda.Event(enable_timing=True) for _ in range(args.steps + 1)]
     launches0 = pb.kernel_launch_count()
-    with ClockSampler(dev.index) as clocks:
+    sampler = ClockSampler(dev.index)  # NVML initialisation takes milliseconds and differs per rank: do it BEFORE the barrier
+    with sampler as clocks:
+        if world > 1:  # all ranks enter the timed region together: at N > 1 every step waits for the slowest rank, so a
+            dist.barrier()  # start skew of a few ms would be charged to every rank's K steps
+            torch.cuda.synchronize()
         ev[0].record()
         for i in range(args.steps):
             step()
