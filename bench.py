@@ -41,14 +41,17 @@ def measured_peak_gbs():
         return 6650.0, "fallback (B200_PROFILING.md 6.65 TB/s)"
 
 
-def ncu_traffic_bytes():
-    """dram bytes per launch of the convert kernel from the committed ncu --set full capture, if any"""
-    p = os.path.join(ROOT, "profiles", "convert_c2_ncu_summary.json")
+def ncu_traffic_bytes(fused):
+    """dram bytes per launch of the convert kernel from the committed `ncu --set full` capture of the same workload (a
+    static number read from profiles/, not measured in this run: ncu cannot run inside a timed bench).  C2 and C5 (fused
+    AABB) have separate captures; returns (bytes or None, source label)"""
+    name = "convert_c5_ncu_summary.json" if fused else "convert_c2_ncu_summary.json"
+    p = os.path.join(ROOT, "profiles", name)
     try:
         with open(p) as fh:
-            return float(json.load(fh)["dram_bytes_per_launch"])
+            return float(json.load(fh)["dram_bytes_per_launch"]), f"profiles/{name} (static: committed ncu --set full capture)"
     except Exception:
-        return None
+        return None, f"none (no committed capture profiles/{name})"
 
 
 class ClockSampler:
@@ -149,6 +152,91 @@ def oracle_row_rates():
     return rows
 
 
+# algorithmic bytes per point of every timed phase (SURVEY 8d conventions; DESIGN.md section 4 states them per kernel).
+# V/N = voxels per point enters the C3 phases that write per-voxel results.
+def _c3_phase_bytes(v_over_n, passes):
+    return {"voxel.bounds": 24, "voxel.keys": 24 + 8, "sort.histogram": 8, "sort.pass": 16,
+            "voxel.heads_count+scan": 8, "voxel.heads_emit": 8 + 4 + 12 * v_over_n,
+            "voxel.reduce": 4 + 24 + (24 + 4) * v_over_n, "voxel.emit+reduce": 8 + 24 + (24 + 8) * v_over_n}
+
+
+_C4_PHASE_BYTES = {"knn.bounds": 24, "knn.codes": 24 + 12, "sort.histogram": 8, "sort.pass": 24,
+                   "knn.gather_positions": 4 + 24 + 24, "knn.tree": 8 / 8 + 2 * 64 / 8, "knn.query+normals": 24 + 32}
+
+
+def _phase_table(phases, bytes_of, n, peak):
+    """[(name, ms)] of ONE call -> per-kernel rows; repeated names (sort passes) are summed"""
+    agg = {}
+    for name, ms in phases:
+        a = agg.setdefault(name, {"name": name, "ms": 0.0, "launch_groups": 0})
+        a["ms"] += ms
+        a["launch_groups"] += 1
+    rows = []
+    for name, a in agg.items():
+        b = bytes_of.get(name)
+        if b is not None:
+            a["algorithmic_bytes"] = b * n * a["launch_groups"]
+            a["achieved_GBps"] = a["algorithmic_bytes"] / (a["ms"] * 1e-3) / 1e9 if a["ms"] > 0 else None
+            a["frac"] = a["achieved_GBps"] / peak if a["achieved_GBps"] else None
+        rows.append(a)
+    return rows
+
+
+def other_configs(pb, ctx, dev, peak):
+    """C3 (100 M-point AABB + voxel keys + sort + voxel-grid downsample at 0.1 m, voxel_grid.rs:109-165) and C4 (100 M-point
+    kNN k=16 normal estimation over the device LBVH, normal_estimation.rs:79-130) measured after the headline, each with
+    its own clock sample and the per-phase CUDA-event times of the library's phase timer (pb200_ctx_profile_read)."""
+    import torch
+    from pasture_b200 import algorithms as alg
+    out = []
+    n = POINTS_PER_GPU
+
+    def run(label, fn, bytes_total_per_point, phase_bytes, reps):
+        fn()  # warm-up: first call allocates the temporaries from the driver
+        torch.cuda.synchronize()
+        sampler = ClockSampler(dev.index)
+        times = []
+        with sampler as clocks:
+            for _ in range(reps):
+                e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+                e0.record()
+                res = fn()
+                e1.record()
+                torch.cuda.synchronize()
+                times.append(e0.elapsed_time(e1))
+        ctx.profile(True)
+        res = fn()
+        phases = ctx.profile_read()
+        ctx.profile(False)
+        ms = min(times)
+        row = {"workload": label, "points": n, "ms": ms, "ms_all": times, "points_per_s": n / (ms * 1e-3),
+               "algorithmic_bytes_per_point": bytes_total_per_point,
+               "achieved_GBps": bytes_total_per_point * n / (ms * 1e-3) / 1e9,
+               "frac": bytes_total_per_point * n / (ms * 1e-3) / 1e9 / peak,
+               "kernels": _phase_table(phases, phase_bytes(res) if callable(phase_bytes) else phase_bytes, n, peak),
+               "kernel_ms_sum": sum(m for _, m in phases), "clocks": clocks.summary(),
+               "timing": "CUDA events around the whole library call (best of %d, device-resident input, includes the "
+                         "call's host synchronisations); kernels: one extra profiled call" % reps}
+        return row, res
+
+    src = alg.synth_terrain_positions(n, device=dev)
+    row, res = run("C3: 100M-point AABB + voxel keys + radix sort + voxel-grid downsample (0.1 m) on 1xB200",
+                   lambda: alg.voxelgrid_filter(src, 0.1, 0.1, 0.1), 232,
+                   lambda r: _c3_phase_bytes(r.len() / n, 5), reps=5)
+    row["voxels"] = res.len()
+    out.append(row)
+    del res
+    ctx.trim()
+    row, res = run("C4: 100M-point kNN (k=16) normal estimation over the device LBVH on 1xB200",
+                   lambda: alg.compute_normals(src, 16), 56, _C4_PHASE_BYTES, reps=2)
+    row["note"] = ("not HBM-bound (tree traversal is latency / L1-bound): frac is informational (SURVEY 8d); the LBVH build "
+                   "phases (codes, sort, gather, tree) are HBM-class")
+    out.append(row)
+    del res, src
+    ctx.trim()
+    return out
+
+
 def oracle_convert_rate(n_points, threads, repeats=1):
     """times the CPU restatement of convert_into_range (attribute-outer / point-inner, function-pointer casts,
     buffer_conversion.rs:546-604) on n_points of the C2 stream; returns (points/s, seconds of the best repeat)"""
@@ -219,6 +307,9 @@ def run_ours(args):
     dev = torch.device("cuda", local_rank if world > 1 else 0)
     torch.cuda.set_device(dev)
     ctx = pb.get_context(dev.index)
+    # pinned host buffers of the e2e leg should live on the GPU's NUMA node: bind this rank's thread to the device-local
+    # CPUs before anything is allocated (no effect on single-node VMs; recorded in e2e.host_binding)
+    host_binding = None if args.no_bind else ctx.bind_host_thread()
     for kv in args.param:
         k, v = kv.split("=")
         ctx.set_param(k, int(v))
@@ -313,39 +404,63 @@ def run_ours(args):
     avg_kernel_ms = sum(step_ms) / len(step_ms)
     best_kernel_ms = min(step_ms)
     achieved = (BYTES_IN + BYTES_OUT) * n / (avg_kernel_ms * 1e-3) / 1e9
-    traffic = ncu_traffic_bytes()
+    traffic, traffic_src = ncu_traffic_bytes(fused)
     roofline = {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
-                "traffic": traffic, "peak_source": peak_src, "algorithmic_bytes_per_launch": (BYTES_IN + BYTES_OUT) * n,
+                "traffic": traffic, "traffic_source": traffic_src, "peak_source": peak_src, "algorithmic_bytes_per_launch": (BYTES_IN + BYTES_OUT) * n,
                 "avg_launch_ms": avg_kernel_ms, "best_launch_ms": best_kernel_ms,
                 "frac_of_8TBps_nominal": achieved / 8000.0, "kernel": "convert_tiles_kernel",
                 "note": "rank 0; at N>1 the launch also holds the fused AABB and its exchange" if world > 1 else "rank 0"}
 
     # ---- end to end through the C ABI with HOST buffers (pinned): H2D + kernel + D2H every step ------------
-    # every rank runs it at the same time (each GPU has its own PCIe link), time = max over ranks
+    # every rank runs it at the same time (all GPUs share the host's memory system), time = max over ranks.
+    # Right before it, benchmarks/pcie_probe.py measures what plain pinned cudaMemcpyAsync of the same byte counts achieves
+    # in the same process layout (all ranks concurrently): its both-directions time is the floor of an e2e step, and
+    # e2e.roofline.frac = floor / measured says how much of the remaining time is the library's.
     e2e = None
     if not args.no_e2e:
         n_e2e = args.e2e_points
+        probe = None
+        if not args.no_pcie_probe:
+            from benchmarks.pcie_probe import probe as pcie_probe
+            probe = pcie_probe(dev, n_e2e * BYTES_IN, n_e2e * BYTES_OUT, reps=3, dist=dist if world > 1 else None)
         h_src = pb.VectorBuffer(pl_raw, n_e2e, "cpu", pinned=True)
         h_src.data[: n_e2e * BYTES_IN].copy_(src.data[: n_e2e * BYTES_IN])
         h_dst = pb.HashMapBuffer(pl_def, n_e2e, "cpu", pinned=True)
         torch.cuda.synchronize()
         r = range(0, n_e2e)
         cv.convert_into_range(h_src, r, h_dst, r)  # warm-up (allocates the staging buffers)
-        e2e_steps = max(1, min(args.steps, 5))
+        e2e_steps = max(1, min(args.steps, 10))
+        per_step = []
         if world > 1:
             dist.barrier()
         t0 = time.perf_counter()
         for _ in range(e2e_steps):
+            ts = time.perf_counter()
             cv.convert_into_range(h_src, r, h_dst, r)  # returns after the D2H of the last chunk
+            per_step.append((time.perf_counter() - ts) * 1e3)
         dt = time.perf_counter() - t0
         if world > 1:
             t = torch.tensor([dt], dtype=torch.float64, device=dev)
             dist.all_reduce(t, op=dist.ReduceOp.MAX)
             dt = float(t.item())
+        per_step.sort()
         e2e = {"value": world * n_e2e * e2e_steps / dt, "unit": "points/s", "h2d_bytes_per_step": n_e2e * BYTES_IN,
                "d2h_bytes_per_step": n_e2e * BYTES_OUT, "ms_per_step": dt / e2e_steps * 1e3, "points_per_step": n_e2e,
+               "steps": e2e_steps,
+               "step_ms_rank0": {"min": per_step[0], "median": per_step[len(per_step) // 2], "max": per_step[-1]},
+               "host_binding": host_binding,
                "note": "per rank: pinned host VectorBuffer -> pb200_converter_convert_into_range (HOST memspace, chunked "
                        "H2D/kernel/D2H overlap) -> pinned host HashMapBuffer; all ranks concurrently, max over ranks"}
+        if probe is not None:
+            floor_ms = probe["both_ms"]
+            e2e["roofline"] = {
+                "bound": "pcie/host-memory", "floor_ms": floor_ms, "frac": floor_ms / (dt / e2e_steps * 1e3),
+                "peak_gbs_h2d": probe["h2d_alone_gbs"], "peak_gbs_d2h": probe["d2h_alone_gbs"],
+                "concurrent_gbs_h2d": probe["both_h2d_gbs"], "concurrent_gbs_d2h": probe["both_d2h_gbs"],
+                "solo_floor_ms": probe.get("solo_both_ms"),
+                "source": "benchmarks/pcie_probe.py run in this process right before the e2e leg: plain pinned "
+                          "cudaMemcpyAsync of the same H2D and D2H byte counts on two streams, all ranks concurrently, "
+                          "per-rank GB/s, max time over ranks (solo = rank 0 alone)"}
         # the host result must equal the device result
         for i in (0, len(pl_def) - 1):
             a = h_dst.columns[i][: n_e2e * pl_def.at(i).size()]
@@ -353,10 +468,44 @@ def run_ours(args):
             assert torch.equal(a, b), f"e2e column {i} differs from the device-resident result"
         del h_src, h_dst
 
+    # ---- N > 1: what the line needs to be read on its own ---------------------------------------------------------
+    # per-rank step times (which rank the others wait for) and, on every rank, the single-GPU cost of the fused AABB
+    # (C2 with and without min/max tracking, no exchange): the N = 1 -> N >= 2 step is that, not communication.
+    attribution = None
+    if world > 1:
+        def local_ms(fn, reps=20):
+            for _ in range(3):
+                fn()
+            torch.cuda.synchronize()
+            e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            e0.record()
+            for _ in range(reps):
+                fn()
+            e1.record()
+            torch.cuda.synchronize()
+            return e0.elapsed_time(e1) / reps
+        plain_ms = local_ms(lambda: cv.convert_into_range(src, rng_all, dst, rng_all))
+        fused_ms = local_ms(lambda: cv.convert_into_range_with_bounds_device(src, rng_all, dst, rng_all, minmax6))
+        ss = sorted(step_ms)
+        mine = {"rank": rank, "step_ms": {"min": ss[0], "median": ss[len(ss) // 2], "max": ss[-1]},
+                "c2_plain_ms": plain_ms, "c2_fused_aabb_ms": fused_ms}
+        allr = [None] * world
+        dist.all_gather_object(allr, mine)
+        attribution = {"per_rank": allr, "fused_aabb_ms": allr[0]["c2_fused_aabb_ms"], "plain_ms": allr[0]["c2_plain_ms"],
+                       "note": "c2_plain_ms / c2_fused_aabb_ms: the same conversion on this rank alone without / with the fused "
+                               "AABB (no exchange, not coupled to the peers), 20 launches after the timed region"}
+
     if rank != 0:
         if world > 1:
             dist.destroy_process_group()
         return
+
+    # ---- the other single-GPU configurations of BASELINE.json at full size (outside the headline's timed region) ----
+    other = None
+    if world == 1 and not args.no_other_configs:
+        del src, dst
+        torch.cuda.empty_cache()
+        other = other_configs(pb, ctx, dev, peak)
 
     # ---- CPU baseline: the oracle port on this box's host cores, bounded sample ---------------------------
     cpu = None
@@ -386,6 +535,10 @@ def run_ours(args):
         "roofline": roofline, "cpu_baseline": cpu, "e2e": e2e, "gpu_launches": int(launches),
         "clocks": clocks.summary(),
     }
+    if attribution is not None:
+        out["scaling_attribution"] = attribution
+    if other is not None:
+        out["other_configs"] = other
     print(json.dumps(out))
     if world > 1:
         dist.destroy_process_group()
@@ -402,6 +555,9 @@ def main():
     ap.add_argument("--fused-bounds", action="store_true", help="N=1: also fuse the AABB (always on for N>1)")
     ap.add_argument("--nccl-bounds", action="store_true", help="N>1: exchange the AABB with an NCCL all-reduce instead of peer memory")
     ap.add_argument("--no-e2e", action="store_true")
+    ap.add_argument("--no-pcie-probe", action="store_true", help="skip the pinned-copy probe that gives e2e.roofline")
+    ap.add_argument("--no-bind", action="store_true", help="do not bind the rank to its GPU's NUMA-local CPUs")
+    ap.add_argument("--no-other-configs", action="store_true", help="N=1: skip the C3 / C4 legs (other_configs)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--param", action="append", default=[], help="tuning knob key=value (pb200_ctx_set_param), e.g. convert.threads=512")
     args = ap.parse_args()

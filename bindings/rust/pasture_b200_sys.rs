@@ -91,6 +91,8 @@ extern "C" {
     pub fn pb200_ctx_trim(ctx: *mut pb200_ctx) -> c_int;
     pub fn pb200_ctx_set_param(ctx: *mut pb200_ctx, key: *const c_char, value: i64) -> c_int;
     pub fn pb200_ctx_destroy(ctx: *mut pb200_ctx);
+    pub fn pb200_ctx_profile_read(ctx: *mut pb200_ctx, out: *mut c_char, capacity: u64) -> c_int;
+    pub fn pb200_ctx_bind_host_thread(ctx: *mut pb200_ctx, numa_node_out: *mut c_int, n_cpus_out: *mut c_int) -> c_int;
     pub fn pb200_host_alloc(bytes: u64, out: *mut *mut c_void) -> c_int;
     pub fn pb200_host_free(p: *mut c_void) -> c_int;
     pub fn pb200_device_alloc(ctx: *mut pb200_ctx, bytes: u64, out: *mut *mut c_void) -> c_int;
@@ -155,8 +157,8 @@ extern "C" {
 
     pub fn pb200_pnts_compatible_layout(point_layout: *const pb200_layout, num_points: u64, out_attrs: *mut pb200_attr, n_out: *mut u32,
                                         body_bytes: *mut u64) -> c_int;
-    pub fn pb200_pnts_read_points(ctx: *mut pb200_ctx, body: *const c_void, attrs: *const pb200_attr, n_attrs: u32, first_point: u64,
-                                  count: u64, dst: *const pb200_buffer_desc, rtc_center: *const f64) -> c_int;
+    pub fn pb200_pnts_read_points(ctx: *mut pb200_ctx, body: *const c_void, body_size: u64, attrs: *const pb200_attr, n_attrs: u32,
+                                  first_point: u64, count: u64, dst: *const pb200_buffer_desc, rtc_center: *const f64) -> c_int;
     pub fn pb200_pnts_write_points(ctx: *mut pb200_ctx, src: *const pb200_buffer_desc, body_out: *mut c_void, body_capacity: u64) -> c_int;
     pub fn pb200_ransac_rank_samples(ctx: *mut pb200_ctx, buf: *const pb200_buffer_desc, kind: c_int, samples: *const u64, n_models: u64,
                                      distance_threshold: f64, models_out: *mut f64, rankings_out: *mut u64) -> c_int;

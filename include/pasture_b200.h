@@ -122,9 +122,20 @@ int pb200_ctx_synchronize(pb200_ctx* ctx);
 /* hand the temporaries cached between calls (sort buffers, trees; stream-ordered pool) back to the driver */
 int pb200_ctx_trim(pb200_ctx* ctx);
 /* tuning knobs of the tile pipeline: "convert.tile_points", "convert.threads", "convert.stages",
- * "convert.ctas_per_sm", "convert.force_direct" */
+ * "convert.ctas_per_sm", "convert.force_direct", "profile.phases" */
 int pb200_ctx_set_param(pb200_ctx* ctx, const char* key, int64_t value);
+/* Phase timer: after pb200_ctx_set_param(ctx, "profile.phases", 1) the library brackets the phases of its calls
+ * (voxel.keys, sort.pass, voxel.reduce, knn.query, ...) with CUDA events on the context's stream.  This call synchronises,
+ * writes one "name<TAB>milliseconds" line per recorded phase (call order) into out, clears the records and returns
+ * their number.  Measurement tooling (bench.py other_configs); off by default. */
+int pb200_ctx_profile_read(pb200_ctx* ctx, char* out, uint64_t capacity);
 void pb200_ctx_destroy(pb200_ctx* ctx);
+/* Bind the CALLING THREAD to the CPUs that are NUMA-local to the context's device (sysfs local_cpulist of the GPU's PCI
+ * function, intersected with the thread's current affinity) so that the pinned host buffers it allocates afterwards, and
+ * the copies it issues, stay on the GPU's socket.  *numa_node_out = the device's node (-1 unknown), *n_cpus_out = CPUs
+ * bound (0: affinity left unchanged, e.g. no sysfs).  Multi-GPU hosts: call it once per rank before allocating HOST
+ * buffers (what the reference's chunk loop, pasture-io/src/las/raw_readers.rs:309-348, reads from and writes to). */
+int pb200_ctx_bind_host_thread(pb200_ctx* ctx, int* numa_node_out, int* n_cpus_out);
 
 /* pinned host / device memory helpers (ExternalMemoryBuffer-style foreign memory, point_buffer.rs:1479-1503) */
 int pb200_host_alloc(uint64_t bytes, void** out);
@@ -335,9 +346,10 @@ int pb200_pnts_compatible_layout(const pb200_layout* point_layout, uint64_t num_
 /* PntsReader::read_into (pnts_reader.rs:294-367): points [first_point, first_point+count) of the body (same memory
  * space as dst) go to dst[0, count); file attributes the target does not have are skipped, target attributes the file
  * does not have are left alone, differing datatypes are cast. rtc_center (nullable, 3 doubles) = PntsReadPositionsMode::
- * Absolute: added to POSITION_3D of every point of dst (Vec3f32 via f64, or Vec3f64; else PB200_ERR_UNSUPPORTED, :247-283). */
-int pb200_pnts_read_points(pb200_ctx* ctx, const void* body, const pb200_attr* attrs, uint32_t n_attrs, uint64_t first_point,
-                           uint64_t count, const pb200_buffer_desc* dst, const double* rtc_center);
+ * Absolute: added to POSITION_3D of every point of dst (Vec3f32 via f64, or Vec3f64; else PB200_ERR_UNSUPPORTED, :247-283).
+ * body_size = bytes readable at `body`; an array that would run past it is PB200_ERR_RANGE (UnexpectedEof in the reference). */
+int pb200_pnts_read_points(pb200_ctx* ctx, const void* body, uint64_t body_size, const pb200_attr* attrs, uint32_t n_attrs,
+                           uint64_t first_point, uint64_t count, const pb200_buffer_desc* dst, const double* rtc_center);
 /* PntsWriter::write + write_feature_table_body (pnts_writer.rs:353-401, :310-341): all points of src, converted to
  * the compatible layout, as the FeatureTable body (zero padded arrays) at body_out (src's memory space). */
 int pb200_pnts_write_points(pb200_ctx* ctx, const pb200_buffer_desc* src, void* body_out, uint64_t body_capacity);

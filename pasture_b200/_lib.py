@@ -67,7 +67,9 @@ SIGNATURES = {
     "pb200_ctx_synchronize": (i32, [vp]),
     "pb200_ctx_trim": (i32, [vp]),
     "pb200_ctx_set_param": (i32, [vp, C.c_char_p, i64]),
+    "pb200_ctx_profile_read": (i32, [vp, C.c_char_p, u64]),
     "pb200_ctx_destroy": (None, [vp]),
+    "pb200_ctx_bind_host_thread": (i32, [vp, C.POINTER(i32), C.POINTER(i32)]),
     "pb200_host_alloc": (i32, [u64, PVP]),
     "pb200_host_free": (i32, [vp]),
     "pb200_device_alloc": (i32, [vp, u64, PVP]),
@@ -111,7 +113,7 @@ SIGNATURES = {
     "pb200_transform_attribute": (i32, [vp, BD, C.c_char_p, u32, C.POINTER(Transform)]),
     "pb200_view_attribute_with_conversion": (i32, [vp, BD, C.c_char_p, u32, vp]),
     "pb200_pnts_compatible_layout": (i32, [vp, u64, vp, C.POINTER(u32), C.POINTER(u64)]),
-    "pb200_pnts_read_points": (i32, [vp, vp, vp, u32, u64, u64, BD, vp]),
+    "pb200_pnts_read_points": (i32, [vp, vp, u64, vp, u32, u64, u64, BD, vp]),
     "pb200_pnts_write_points": (i32, [vp, BD, vp, u64]),
     "pb200_ransac_rank_samples": (i32, [vp, BD, i32, vp, u64, C.c_double, vp, vp]),
     "pb200_ransac_rank_models": (i32, [vp, BD, i32, vp, u64, C.c_double, vp]),

@@ -7,7 +7,7 @@ import torch
 
 from ._lib import BufferDesc, ProjOp, VoxelPartialsDesc, check, lib
 from .containers import _NP, _VEC3, HashMapBuffer, VectorBuffer
-from .context import get_context
+from .context import context_for, get_context
 from .layout import DT
 
 
@@ -39,7 +39,7 @@ class AABB:
 
 def calculate_bounds(buffer, ctx=None):
     """bounds.rs:11-28 -> AABB or None"""
-    ctx = ctx or get_context()
+    ctx = context_for(ctx, buffer)
     d = buffer.desc()
     mn, mx, some = (C.c_double * 3)(), (C.c_double * 3)(), C.c_int(0)
     check(lib().pb200_calculate_bounds(ctx._h, C.byref(d), mn, mx, C.byref(some)))
@@ -48,7 +48,7 @@ def calculate_bounds(buffer, ctx=None):
 
 def minmax_attribute(buffer, attribute, ctx=None):
     """minmax.rs:13-51 -> (min, max) of attribute.datatype() or None"""
-    ctx = ctx or get_context()
+    ctx = context_for(ctx, buffer)
     d = buffer.desc()
     mn, mx, some = np.zeros(32, np.uint8), np.zeros(32, np.uint8), C.c_int(0)
     check(lib().pb200_minmax_attribute(ctx._h, C.byref(d), attribute.name().encode(), int(attribute.datatype()),
@@ -68,7 +68,7 @@ def expand_bits_by_3(v):
 
 
 def morton_codes(buffer, bmin, bmax, ctx=None):
-    ctx = ctx or get_context()
+    ctx = context_for(ctx, buffer)
     d = buffer.desc()
     out = torch.zeros(max(1, buffer.len()), dtype=torch.int64, device=buffer.device)
     check(lib().pb200_morton_codes(ctx._h, C.byref(d), (C.c_double * 3)(*bmin), (C.c_double * 3)(*bmax),
@@ -79,7 +79,7 @@ def morton_codes(buffer, bmin, bmax, ctx=None):
 def voxelgrid_filter(buffer, leafsize_x, leafsize_y, leafsize_z, filtered_layout=None, out_buffer_type=HashMapBuffer,
                      device=None, ctx=None, return_keys=False):
     """voxel_grid.rs:109-165. Returns the filtered buffer (library result copied into a buffer of out_buffer_type)."""
-    ctx = ctx or get_context()
+    ctx = context_for(ctx, buffer)
     layout = filtered_layout or buffer.point_layout()
     dev = torch.device(device) if device is not None else buffer.device
     kind = 0 if out_buffer_type is VectorBuffer else 1
@@ -113,7 +113,7 @@ def voxelgrid_filter(buffer, leafsize_x, leafsize_y, leafsize_z, filtered_layout
 def radix_sort(keys, vals=None, begin_bit=0, end_bit=64, ctx=None):
     """K8: stable LSD radix sort of a CUDA int64 tensor (u64 bit patterns) by the bits [begin_bit, end_bit), in place,
     optionally carrying an int32 payload (stability: equal keys keep their input order)"""
-    ctx = ctx or get_context()
+    ctx = context_for(ctx, keys)
     assert keys.dtype == torch.int64 and keys.is_contiguous() and keys.is_cuda
     assert vals is None or (vals.dtype == torch.int32 and vals.is_contiguous() and vals.numel() == keys.numel())
     check(lib().pb200_radix_sort_u64(ctx._h, C.c_void_p(keys.data_ptr()), C.c_void_p(vals.data_ptr()) if vals is not None else None,
@@ -165,7 +165,7 @@ def _take_partials(ctx, h, want_centroids):
 def voxelgrid_partials(buffer, leafsize_x, leafsize_y, leafsize_z, global_bounds, ctx=None):
     """one shard's contribution to a sharded voxel grid: partial sums on the grid of `global_bounds` (an AABB or a
     (min, max) pair covering the WHOLE cloud, e.g. the all-reduced shard bounds)"""
-    ctx = ctx or get_context()
+    ctx = context_for(ctx, buffer)
     mn, mx = (global_bounds.min(), global_bounds.max()) if isinstance(global_bounds, AABB) else global_bounds
     gmin, gmax = (C.c_double * 3)(*mn), (C.c_double * 3)(*mx)
     d = buffer.desc()
@@ -177,7 +177,7 @@ def voxelgrid_partials(buffer, leafsize_x, leafsize_y, leafsize_z, global_bounds
 def voxelgrid_merge_partials(keys, counts, sums, bits, cells=(0, 0, 0), ctx=None):
     """merge concatenated partials (device tensors; equal keys are added in the order given = source-rank order)
     -> (VoxelPartials with the totals, centroids [V, 3])"""
-    ctx = ctx or get_context()
+    ctx = context_for(ctx, keys)
     keys, counts, sums = keys.contiguous(), counts.contiguous(), sums.contiguous()
     assert keys.dtype == torch.int64 and counts.dtype == torch.int32 and sums.dtype == torch.float64
     h = C.c_void_p()
@@ -200,7 +200,7 @@ def _copy(ctx, dst, src, nbytes, memspace):
 
 def knn(buffer, k, with_distances=True, ctx=None):
     """KdTree::nearests for every point against the cloud (normal_estimation.rs:103,108) -> (idx [n,k] int64-view of u32, d2 [n,k])"""
-    ctx = ctx or get_context()
+    ctx = context_for(ctx, buffer)
     n = buffer.len()
     dev = buffer.device
     idx = torch.zeros((max(1, n), k), dtype=torch.int32, device=dev)
@@ -212,7 +212,7 @@ def knn(buffer, k, with_distances=True, ctx=None):
 
 
 def radius_search(buffer, radius, max_neighbors, ctx=None):
-    ctx = ctx or get_context()
+    ctx = context_for(ctx, buffer)
     n = buffer.len()
     dev = buffer.device
     idx = torch.zeros((max(1, n), max_neighbors), dtype=torch.int32, device=dev)
@@ -225,7 +225,7 @@ def radius_search(buffer, radius, max_neighbors, ctx=None):
 
 def compute_normals(point_cloud, k_nn, ctx=None):
     """normal_estimation.rs:79-130 -> (normals [n,3] f64, curvature [n] f64) tensors on the buffer's device"""
-    ctx = ctx or get_context()
+    ctx = context_for(ctx, point_cloud)
     n = point_cloud.len()
     dev = point_cloud.device
     normals = torch.zeros((max(1, n), 3), dtype=torch.float64, device=dev)
@@ -261,7 +261,7 @@ class Line:
 
 def ransac_rank_samples(buffer, kind, samples, distance_threshold, ctx=None):
     """generate_{plane,line}_model (:98-138) for given draws -> (models [m, 4|6] f64, rankings [m] u64) numpy"""
-    ctx = ctx or get_context()
+    ctx = context_for(ctx, buffer)
     s = np.ascontiguousarray(samples, dtype=np.uint64)
     m = s.shape[0]
     models = np.zeros((m, 4 if kind == RANSAC_PLANE else 6), dtype=np.float64)
@@ -273,7 +273,7 @@ def ransac_rank_samples(buffer, kind, samples, distance_threshold, ctx=None):
 
 
 def ransac_rank_models(buffer, kind, models, distance_threshold, ctx=None):
-    ctx = ctx or get_context()
+    ctx = context_for(ctx, buffer)
     mm = np.ascontiguousarray(models, dtype=np.float64)
     ranks = np.zeros(mm.shape[0], dtype=np.uint64)
     d = buffer.desc()
@@ -284,7 +284,7 @@ def ransac_rank_models(buffer, kind, models, distance_threshold, ctx=None):
 
 def ransac_inliers(buffer, kind, model, distance_threshold, ctx=None):
     """indices (int64 tensor on the buffer's device, ascending) of the points within the threshold of `model`"""
-    ctx = ctx or get_context()
+    ctx = context_for(ctx, buffer)
     mm = np.ascontiguousarray(model, dtype=np.float64)
     n = buffer.len()
     idx = torch.zeros(max(1, n), dtype=torch.int64, device=buffer.device)
@@ -296,7 +296,7 @@ def ransac_inliers(buffer, kind, model, distance_threshold, ctx=None):
 
 
 def _ransac(buffer, kind, distance_threshold, num_of_iterations, seed, ctx):
-    ctx = ctx or get_context()
+    ctx = context_for(ctx, buffer)
     if seed is None:  # the reference draws from thread_rng(): every call tries different models
         seed = int.from_bytes(__import__("os").urandom(8), "little")
     n = buffer.len()
@@ -334,14 +334,14 @@ class Projection:
 
 
 def reproject_point_cloud_within(point_cloud, source_crs, target_crs, ctx=None):  # reprojection.rs:132-146
-    ctx = ctx or get_context()
+    ctx = context_for(ctx, point_cloud)
     p = Projection(source_crs, target_crs)
     d = point_cloud.desc()
     check(lib().pb200_reproject(ctx._h, C.byref(d), None, p.ops, p.n_ops))
 
 
 def reproject_point_cloud_between(source_point_cloud, target_point_cloud, source_crs, target_crs, ctx=None):  # :201-227
-    ctx = ctx or get_context()
+    ctx = context_for(ctx, source_point_cloud)
     p = Projection(source_crs, target_crs)
     sd, dd = source_point_cloud.desc(), target_point_cloud.desc()
     check(lib().pb200_reproject(ctx._h, C.byref(sd), C.byref(dd), p.ops, p.n_ops))
@@ -350,7 +350,7 @@ def reproject_point_cloud_between(source_point_cloud, target_point_cloud, source
 def synth_las_fmt0_records(n, first_index=0, seed=42, device="cuda", ctx=None):
     """C2/C5 input stream generated in HBM: VectorBuffer of raw LAS format-0 records"""
     from .layout import PointLayout
-    ctx = ctx or get_context()
+    ctx = ctx.bind_current_stream() if ctx is not None else get_context(device)
     buf = VectorBuffer(PointLayout.las_raw(0), n, device)
     check(lib().pb200_synth_las_fmt0_records(ctx._h, C.c_void_p(buf.data.data_ptr()), first_index, n, seed))
     return buf
@@ -359,7 +359,7 @@ def synth_las_fmt0_records(n, first_index=0, seed=42, device="cuda", ctx=None):
 def synth_terrain_positions(n, first_index=0, seed=42, device="cuda", ctx=None):
     """C3/C4 input stream: HashMapBuffer with one packed Vec3f64 POSITION_3D column"""
     from .layout import PointLayout, attributes
-    ctx = ctx or get_context()
+    ctx = ctx.bind_current_stream() if ctx is not None else get_context(device)
     buf = HashMapBuffer(PointLayout.from_attributes([attributes.POSITION_3D]), n, device)
     check(lib().pb200_synth_terrain_positions(ctx._h, C.c_void_p(buf.columns[0].data_ptr()), first_index, n, seed))
     return buf

@@ -258,8 +258,8 @@ def filter_into(source, target, mask, ctx=None):
     """HashMapBuffer::filter_into (point_buffer.rs:1086): the predicate `Fn(usize) -> bool` is given as a mask over
     the point indices. Returns the number of matches."""
     from ._lib import check, lib
-    from .context import get_context
-    ctx = ctx or get_context()
+    from .context import context_for, get_context
+    ctx = context_for(ctx, source)
     m = _mask_tensor(mask, source.len(), source.device)
     sd, dd = source.desc(), target.desc()
     count = C.c_uint64(0)

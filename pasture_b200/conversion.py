@@ -8,7 +8,7 @@ import ctypes as C
 from ._lib import Transform as _CTransform
 from ._lib import check, lib
 from .containers import HashMapBuffer, VectorBuffer
-from .context import get_context
+from .context import context_for, get_context
 
 T_NONE, T_SCALE_OFFSET, T_INV_SCALE_OFFSET, T_ADD, T_SHIFT_MASK = range(5)
 
@@ -64,6 +64,7 @@ class BufferLayoutConverter:
 
     @classmethod
     def _create(cls, from_layout, to_layout, with_default, ctx):
+        # a converter belongs to ONE device (its context); pass ctx=get_context(device) for buffers on another GPU
         ctx = ctx or get_context()
         h = C.c_void_p()
         check(lib().pb200_converter_create(ctx._h, from_layout._h, to_layout._h, 1 if with_default else 0, C.byref(h)))
@@ -105,6 +106,7 @@ class BufferLayoutConverter:
                                        range(0, source_buffer.len()), count_out_of_range)
 
     def convert_into_range(self, source_buffer, source_range, target_buffer, target_range, count_out_of_range=False):  # :292
+        context_for(self._ctx, source_buffer, target_buffer)
         sd, dd = source_buffer.desc(), target_buffer.desc()
         oor = C.c_uint64(0)
         check(lib().pb200_converter_convert_into_range(self._h, C.byref(sd), source_range.start, source_range.stop,
@@ -114,6 +116,7 @@ class BufferLayoutConverter:
 
     def convert_into_range_with_bounds(self, source_buffer, source_range, target_buffer, target_range):
         """convert_into_range fused with calculate_bounds over the produced POSITION_3D; returns (min, max) or None"""
+        context_for(self._ctx, source_buffer, target_buffer)
         sd, dd = source_buffer.desc(), target_buffer.desc()
         mn, mx, some = (C.c_double * 3)(), (C.c_double * 3)(), C.c_int(0)
         check(lib().pb200_converter_convert_into_range_with_bounds(
@@ -123,6 +126,7 @@ class BufferLayoutConverter:
 
     def convert_into_range_with_bounds_device(self, source_buffer, source_range, target_buffer, target_range, minmax6):
         """as above, but leaves [min xyz, -max xyz] in the CUDA tensor `minmax6` (6 x f64) without synchronising"""
+        context_for(self._ctx, source_buffer, target_buffer)
         sd, dd = source_buffer.desc(), target_buffer.desc()
         return check(lib().pb200_converter_convert_into_range_with_bounds_device(
             self._h, C.byref(sd), source_range.start, source_range.stop, C.byref(dd), target_range.start,
@@ -132,6 +136,7 @@ class BufferLayoutConverter:
         """collective over `comm` (sharding.PeerComm): converts this rank's range and leaves the bounds of ALL ranks'
         produced POSITION_3D as [min xyz, -max xyz] in the CUDA tensor `minmax6` -- one kernel, no NCCL call: the
         exchange happens over peer memory in the kernel's last CTA"""
+        context_for(self._ctx, source_buffer, target_buffer)
         sd, dd = source_buffer.desc(), target_buffer.desc()
         return check(lib().pb200_converter_convert_into_range_with_global_bounds(
             self._h, C.byref(sd), source_range.start, source_range.stop, C.byref(dd), target_range.start,
@@ -149,7 +154,7 @@ def get_default_las_converter(raw_las_layout, target_layout, scale, offset, ctx=
 
 def transform_attribute(buffer, attribute, transform, ctx=None):
     """BorrowedMutBuffer::transform_attribute (point_buffer.rs:391-404), in place"""
-    ctx = ctx or get_context()
+    ctx = context_for(ctx, buffer)
     d = buffer.desc()
     t = transform._c()
     check(lib().pb200_transform_attribute(ctx._h, C.byref(d), attribute.name().encode(), int(attribute.datatype()), C.byref(t)))
@@ -162,7 +167,7 @@ def view_attribute_with_conversion(buffer, attribute, ctx=None):
     import torch
 
     from .containers import _typed
-    ctx = ctx or get_context()
+    ctx = context_for(ctx, buffer)
     n, size = buffer.len(), attribute.size()
     out = torch.zeros(max(1, n * size), dtype=torch.uint8, device=buffer.device)
     d = buffer.desc()

@@ -1,6 +1,10 @@
 // core.cu -- errors, context, memory helpers and the PointLayout descriptor (host side)
 #include "internal.h"
 
+#include <sched.h>
+
+#include <cctype>
+
 namespace pb200 {
 extern int64_t g_cost_div, g_cost_pack_base, g_cost_pack_per_src, g_cost_copy_base, g_cost_store;  // convert.cu cost model
 
@@ -88,6 +92,8 @@ int pb200_ctx_create(int device, pb200_ctx** out) {
                          e == cudaSuccess ? "device count 0" : cudaGetErrorString(e));
     }
     if (device < 0 || device >= n) return set_error(PB200_ERR_NO_DEVICE, "device %d out of range (%d devices)", device, n);
+    struct Restore { int prev = -1; ~Restore() { if (prev >= 0) cudaSetDevice(prev); } } restore;
+    if (cudaGetDevice(&restore.prev) != cudaSuccess) { restore.prev = -1; cudaGetLastError(); }
     PB_CUDA(cudaSetDevice(device));
     pb200_ctx* c = new pb200_ctx();
     c->device = device;
@@ -118,7 +124,7 @@ int pb200_ctx_create(int device, pb200_ctx** out) {
 }
 
 int pb200_ctx_set_stream(pb200_ctx* ctx, void* s) {
-    PB_TRY(ensure_device(ctx));
+    PB_DEVICE(ctx);
     if (ctx->owns_stream && ctx->stream) {
         cudaStreamSynchronize(ctx->stream);
         cudaStreamDestroy(ctx->stream);
@@ -131,13 +137,13 @@ int pb200_ctx_set_stream(pb200_ctx* ctx, void* s) {
 void* pb200_ctx_get_stream(pb200_ctx* ctx) { return ctx ? (void*)ctx->stream : nullptr; }
 
 int pb200_ctx_synchronize(pb200_ctx* ctx) {
-    PB_TRY(ensure_device(ctx));
+    PB_DEVICE(ctx);
     PB_CUDA(cudaStreamSynchronize(ctx->stream));
     return PB200_OK;
 }
 
 int pb200_ctx_trim(pb200_ctx* ctx) {
-    PB_TRY(ensure_device(ctx));
+    PB_DEVICE(ctx);
     PB_CUDA(cudaStreamSynchronize(ctx->stream));
     cudaMemPool_t pool;
     PB_CUDA(cudaDeviceGetDefaultMemPool(&pool, ctx->device));
@@ -159,24 +165,100 @@ int pb200_ctx_set_param(pb200_ctx* ctx, const char* key, int64_t v) {
     else if (k == "convert.cost_pack_per_src") g_cost_pack_per_src = v;
     else if (k == "convert.cost_copy_base") g_cost_copy_base = v;
     else if (k == "convert.cost_store") g_cost_store = v;
+    else if (k == "profile.phases") ctx->profile = v;
     else if (k == "knn.init_radius") ctx->knn_init_radius = v;
-    else if (k == "knn.stats") ctx->knn_stats = v;
+    else if (k == "knn.stats") {
+#ifdef PB200_KNN_DIAGNOSTICS
+        ctx->knn_stats = v;
+#else
+        if (v) return set_error(PB200_ERR_UNSUPPORTED, "knn.stats needs a diagnostics build (make -C pasture_b200/csrc KNN_DIAGNOSTICS=1): "
+                                "the release library never writes traversal counters into pb200_knn's idx_out");
+#endif
+    }
     else if (k == "knn.heap") ctx->knn_heap = v;
     else if (k == "knn.per_axis_codes") ctx->knn_per_axis_codes = v;
     else return set_error(PB200_ERR_INVALID, "unknown parameter %s", key);
     return PB200_OK;
 }
 
+int pb200_ctx_profile_read(pb200_ctx* ctx, char* out, uint64_t capacity) {
+    PB_DEVICE(ctx);
+    PB_CUDA(cudaStreamSynchronize(ctx->stream));
+    uint64_t used = 0;
+    int n = 0;
+    if (out && capacity) out[0] = 0;
+    for (auto& r : ctx->phases) {
+        float ms = 0.f;
+        if (cudaEventElapsedTime(&ms, r.e0, r.e1) == cudaSuccess && out && used + 96 < capacity) {
+            used += (uint64_t)snprintf(out + used, (size_t)(capacity - used), "%s\t%.6f\n", r.name, (double)ms);
+            ++n;
+        }
+        cudaEventDestroy(r.e0);
+        cudaEventDestroy(r.e1);
+    }
+    cudaGetLastError();
+    ctx->phases.clear();
+    return n;
+}
+
 void pb200_ctx_destroy(pb200_ctx* ctx) {
     if (!ctx) return;
     cudaSetDevice(ctx->device);
     if (ctx->stream) cudaStreamSynchronize(ctx->stream);
+    for (auto& r : ctx->phases) { cudaEventDestroy(r.e0); cudaEventDestroy(r.e1); }
     if (ctx->d_scratch) cudaFree(ctx->d_scratch);
     if (ctx->h_scratch) cudaFreeHost(ctx->h_scratch);
     if (ctx->owns_stream && ctx->stream) cudaStreamDestroy(ctx->stream);
     if (ctx->copy_in) cudaStreamDestroy(ctx->copy_in);
     if (ctx->copy_out) cudaStreamDestroy(ctx->copy_out);
     delete ctx;
+}
+
+// Host memory that a GPU reads or writes over PCIe should live on the NUMA node the GPU hangs off: with several GPUs per
+// box, pinned buffers that all sit on one socket (wherever the launcher happened to start the processes) make every
+// copy of the far GPUs cross the inter-socket link.  Linux places pages on the node of the thread that first touches
+// them (cudaHostAlloc touches at allocation), so binding the calling thread to the device's local CPUs BEFORE it
+// allocates its pinned buffers is enough; no libnuma needed.  sysfs: /sys/bus/pci/devices/<bus id>/{local_cpulist,numa_node}.
+int pb200_ctx_bind_host_thread(pb200_ctx* ctx, int* numa_node_out, int* n_cpus_out) {
+    PB_DEVICE(ctx);
+    if (numa_node_out) *numa_node_out = -1;
+    if (n_cpus_out) *n_cpus_out = 0;
+    char bus[32] = "";
+    PB_CUDA(cudaDeviceGetPCIBusId(bus, (int)sizeof bus, ctx->device));
+    for (char* c = bus; *c; ++c) *c = (char)tolower((unsigned char)*c);
+    char path[128];
+    snprintf(path, sizeof path, "/sys/bus/pci/devices/%s/numa_node", bus);
+    if (FILE* f = fopen(path, "r")) {
+        int node = -1;
+        if (fscanf(f, "%d", &node) == 1 && numa_node_out) *numa_node_out = node;
+        fclose(f);
+    }
+    snprintf(path, sizeof path, "/sys/bus/pci/devices/%s/local_cpulist", bus);
+    FILE* f = fopen(path, "r");
+    if (!f) return PB200_OK;  // no sysfs (or a VM that hides the topology): leave the thread where it is
+    char list[4096] = "";
+    const bool got = fgets(list, sizeof list, f) != nullptr;
+    fclose(f);
+    if (!got) return PB200_OK;
+    cpu_set_t allowed, want;
+    CPU_ZERO(&allowed);
+    CPU_ZERO(&want);
+    if (sched_getaffinity(0, sizeof allowed, &allowed) != 0) return PB200_OK;
+    int n = 0;
+    for (const char* p = list; *p;) {  // "0-31,64-95"
+        while (*p && !isdigit((unsigned char)*p)) ++p;
+        if (!*p) break;
+        char* e = nullptr;
+        long a = strtol(p, &e, 10), b = a;
+        p = e;
+        if (*p == '-') { b = strtol(p + 1, &e, 10); p = e; }
+        for (long c = a; c <= b && c < CPU_SETSIZE; ++c)
+            if (c >= 0 && CPU_ISSET((int)c, &allowed)) { CPU_SET((int)c, &want); ++n; }
+    }
+    if (n == 0) return PB200_OK;  // the cpuset of this process has no CPU near the device
+    if (sched_setaffinity(0, sizeof want, &want) != 0) return PB200_OK;
+    if (n_cpus_out) *n_cpus_out = n;
+    return PB200_OK;
 }
 
 int pb200_host_alloc(uint64_t bytes, void** out) {
@@ -189,12 +271,12 @@ int pb200_host_free(void* p) {
     return PB200_OK;
 }
 int pb200_device_alloc(pb200_ctx* ctx, uint64_t bytes, void** out) {
-    PB_TRY(ensure_device(ctx));
+    PB_DEVICE(ctx);
     PB_CUDA(cudaMalloc(out, bytes ? bytes : 1));
     return PB200_OK;
 }
 int pb200_device_free(pb200_ctx* ctx, void* p) {
-    PB_TRY(ensure_device(ctx));
+    PB_DEVICE(ctx);
     if (p) {
         PB_CUDA(cudaStreamSynchronize(ctx->stream));
         PB_CUDA(cudaFree(p));
@@ -202,24 +284,24 @@ int pb200_device_free(pb200_ctx* ctx, void* p) {
     return PB200_OK;
 }
 int pb200_memcpy_h2d(pb200_ctx* ctx, void* d, const void* s, uint64_t bytes) {
-    PB_TRY(ensure_device(ctx));
+    PB_DEVICE(ctx);
     PB_CUDA(cudaMemcpyAsync(d, s, bytes, cudaMemcpyHostToDevice, ctx->stream));
     PB_CUDA(cudaStreamSynchronize(ctx->stream));
     return PB200_OK;
 }
 int pb200_memcpy_d2h(pb200_ctx* ctx, void* d, const void* s, uint64_t bytes) {
-    PB_TRY(ensure_device(ctx));
+    PB_DEVICE(ctx);
     PB_CUDA(cudaMemcpyAsync(d, s, bytes, cudaMemcpyDeviceToHost, ctx->stream));
     PB_CUDA(cudaStreamSynchronize(ctx->stream));
     return PB200_OK;
 }
 int pb200_memcpy_d2d(pb200_ctx* ctx, void* d, const void* s, uint64_t bytes) {
-    PB_TRY(ensure_device(ctx));
+    PB_DEVICE(ctx);
     PB_CUDA(cudaMemcpyAsync(d, s, bytes, cudaMemcpyDeviceToDevice, ctx->stream));
     return PB200_OK;
 }
 int pb200_memset_device(pb200_ctx* ctx, void* d, int value, uint64_t bytes) {
-    PB_TRY(ensure_device(ctx));
+    PB_DEVICE(ctx);
     PB_CUDA(cudaMemsetAsync(d, value, bytes, ctx->stream));
     return PB200_OK;
 }

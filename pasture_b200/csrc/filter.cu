@@ -155,7 +155,7 @@ int pb200_filter_into(pb200_ctx* ctx, const pb200_buffer_desc* src, const uint8_
     if (n == 0) return PB200_OK;
     if (!mask) return set_error(PB200_ERR_INVALID, "null mask");
     if (n > 0xFFFFFFFFull) return set_error(PB200_ERR_UNSUPPORTED, "more than 2^32-1 points per call");
-    PB_TRY(ensure_device(ctx));
+    PB_DEVICE(ctx);
     cudaStream_t st = ctx->stream;
     const pb200_layout& L = *src->layout;
     // device views of the source (the mask lives in the source's memory space)

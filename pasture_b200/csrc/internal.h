@@ -35,6 +35,10 @@ struct pb200_ctx {
     void* h_scratch = nullptr;  // pinned host scratch for small readbacks
     // staging for HOST memspace buffers
     cudaStream_t copy_in = nullptr, copy_out = nullptr;
+    // phase timer ("profile.phases" = 1): CUDA event pairs around the phases of a call, read by pb200_ctx_profile_read
+    int64_t profile = 0;
+    struct PhaseRec { const char* name; cudaEvent_t e0, e1; };
+    std::vector<PhaseRec> phases;
     bool convert_attr_set = false;  // cudaFuncSetAttribute is per device: every context configures its kernels once
     bool sort_attr_set[2] = {false, false}, knn_attr_set = false;
 };
@@ -77,6 +81,22 @@ inline bool dtype_equal(const pb200_attr& a, const pb200_attr& b) {
     return true;
 }
 int ensure_device(pb200_ctx* ctx);
+// Every entry point makes its context's device current for the duration of the call and puts the caller's device back
+// on return (a host framework such as torch keeps its own notion of the current device).
+struct DeviceGuard {
+    int prev = -1, rc = 0;
+    explicit DeviceGuard(pb200_ctx* ctx) {
+        if (cudaGetDevice(&prev) != cudaSuccess) { prev = -1; cudaGetLastError(); }
+        rc = ensure_device(ctx);
+        if (rc == 0 && ctx && prev == ctx->device) prev = -1;  // nothing to restore
+    }
+    ~DeviceGuard() { if (prev >= 0) cudaSetDevice(prev); }
+    DeviceGuard(const DeviceGuard&) = delete;
+    DeviceGuard& operator=(const DeviceGuard&) = delete;
+};
+#define PB_DEVICE(ctx)                         \
+    pb200::DeviceGuard _pb_device_guard(ctx);  \
+    if (_pb_device_guard.rc < 0) return _pb_device_guard.rc
 // device scratch of at least `bytes` (grown lazily); contents undefined
 int scratch(pb200_ctx* ctx, size_t bytes, void** out);
 int validate_desc(const pb200_buffer_desc* d, const char* what);
@@ -98,6 +118,26 @@ struct DevTmp {
         return cudaMallocAsync(&p, bytes ? bytes : 1, s);
     }
 };
+
+// Scoped phase timer: PB_PHASE(ctx, "voxel.reduce") brackets the kernels launched in the enclosing scope with two events
+// on the context's stream when profiling is on (no cost otherwise).  bench.py turns the records into per-kernel
+// milliseconds and roofline fractions of the C3 / C4 configurations.
+struct PhaseScope {
+    pb200_ctx* c;
+    int idx = -1;
+    PhaseScope(pb200_ctx* ctx, const char* name) : c(ctx) {
+        if (!c || !c->profile) return;
+        pb200_ctx::PhaseRec r{name, nullptr, nullptr};
+        if (cudaEventCreate(&r.e0) != cudaSuccess || cudaEventCreate(&r.e1) != cudaSuccess) { cudaGetLastError(); return; }
+        cudaEventRecord(r.e0, c->stream);
+        idx = (int)c->phases.size();
+        c->phases.push_back(r);
+    }
+    ~PhaseScope() { if (idx >= 0) cudaEventRecord(c->phases[(size_t)idx].e1, c->stream); }
+};
+#define PB_PHASE_CAT2(a, b) a##b
+#define PB_PHASE_CAT(a, b) PB_PHASE_CAT2(a, b)
+#define PB_PHASE(ctx, name) pb200::PhaseScope PB_PHASE_CAT(_phase_, __LINE__)(ctx, name)
 
 // radix_sort.cu: stable LSD radix sort by the key bits [begin_bit, end_bit); keys/vals are clobbered, the result is in
 // (keys, vals) or (keys_alt, vals_alt) as *in_alt says; vals may be null (keys only); n < 2^30

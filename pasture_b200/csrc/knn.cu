@@ -626,7 +626,7 @@ static int build_lbvh(pb200_ctx* ctx, const uint8_t* base, uint64_t stride, uint
     d.columns = nullptr;
     double bmin[3], bmax[3];
     int some = 0;
-    PB_TRY(pb200_calculate_bounds(ctx, &d, bmin, bmax, &some));
+    { PB_PHASE(ctx, "knn.bounds"); PB_TRY(pb200_calculate_bounds(ctx, &d, bmin, bmax, &some)); }
     // Quantisation for the tree's Morton order: ONE scale for all axes (cubic cells), so that neighbours on the curve
     // are neighbours in space even for 2.5-D clouds whose z extent is a fraction of x/y.  (pb200_morton_codes, the
     // public Z-row entry point, quantises per axis inside the AABB.)
@@ -641,19 +641,26 @@ static int build_lbvh(pb200_ctx* ctx, const uint8_t* base, uint64_t stride, uint
     PB_CUDA(t->codes.alloc(st, (size_t)n * 8)); PB_CUDA(t->codes2.alloc(st, (size_t)n * 8));
     PB_CUDA(t->idx.alloc(st, (size_t)n * 4)); PB_CUDA(t->idx2.alloc(st, (size_t)n * 4));
     PB_CUDA(t->spos.alloc(st, (size_t)n_padded * 24));
-    lbvh_codes_kernel<<<grid_for(n, ctx->sm_count), 256, 0, st>>>(base, stride, n, bmin[0], bmin[1], bmin[2], s[0], s[1], s[2],
-                                                                  (unsigned long long*)t->codes.p, (uint32_t*)t->idx.p);
-    g_launches++;
+    {
+        PB_PHASE(ctx, "knn.codes");
+        lbvh_codes_kernel<<<grid_for(n, ctx->sm_count), 256, 0, st>>>(base, stride, n, bmin[0], bmin[1], bmin[2], s[0], s[1], s[2],
+                                                                      (unsigned long long*)t->codes.p, (uint32_t*)t->idx.p);
+        g_launches++;
+    }
     {   // K8: own one-sweep radix sort over the 63 code bits; the sorted codes / indices must end up in codes2 / idx2
         bool in_alt = false;
         PB_TRY(radix_sort_u64(ctx, (unsigned long long*)t->codes.p, (unsigned long long*)t->codes2.p, (uint32_t*)t->idx.p,
                               (uint32_t*)t->idx2.p, n, 0, 63, &in_alt));
         if (!in_alt) { std::swap(t->codes.p, t->codes2.p); std::swap(t->idx.p, t->idx2.p); }
     }
-    gather_positions_kernel<<<grid_for(n_padded, ctx->sm_count), 256, 0, st>>>(base, stride, (const uint32_t*)t->idx2.p, n, n_padded,
-                                                                               (double*)t->spos.p);
-    g_launches++;
+    {
+        PB_PHASE(ctx, "knn.gather_positions");
+        gather_positions_kernel<<<grid_for(n_padded, ctx->sm_count), 256, 0, st>>>(base, stride, (const uint32_t*)t->idx2.p, n, n_padded,
+                                                                                   (double*)t->spos.p);
+        g_launches++;
+    }
     if (nb >= 2) {
+        PB_PHASE(ctx, "knn.tree");
         PB_CUDA(t->nodes.alloc(st, (size_t)(nb - 1) * sizeof(Node)));
         PB_CUDA(t->parent.alloc(st, (size_t)(nb - 1) * 4)); PB_CUDA(t->leaf_parent.alloc(st, (size_t)nb * 4));
         PB_CUDA(t->counters.alloc(st, (size_t)(nb - 1) * 4));
@@ -690,8 +697,10 @@ static int launch_query_heap(pb200_ctx* ctx, int mode, const QueryArgs& a, cudaS
 template <int KMAX>
 static void launch_query(int mode, const QueryArgs& a, cudaStream_t st) {
     const unsigned blocks = (a.n + 127) / 128;
-    if (mode == 3) { if constexpr (KMAX == 16) lbvh_query_kernel<16, 3><<<blocks, 128, 0, st>>>(a); }
-    else if (mode == 0) lbvh_query_kernel<KMAX, 0><<<blocks, 128, 0, st>>>(a);
+#ifdef PB200_KNN_DIAGNOSTICS
+    if (mode == 3) { if constexpr (KMAX == 16) lbvh_query_kernel<16, 3><<<blocks, 128, 0, st>>>(a); return; }
+#endif
+    if (mode == 0) lbvh_query_kernel<KMAX, 0><<<blocks, 128, 0, st>>>(a);
     else if (mode == 1) lbvh_query_kernel<KMAX, 1><<<blocks, 128, 0, st>>>(a);
     else lbvh_query_kernel<KMAX, 2><<<blocks, 128, 0, st>>>(a);
 }
@@ -700,7 +709,7 @@ static void launch_query(int mode, const QueryArgs& a, cudaStream_t st) {
 static int run_query(pb200_ctx* ctx, const pb200_buffer_desc* buf, int mode, uint32_t k, double radius, uint32_t* idx_out,
                      double* d2_out, uint32_t* counts_out, double* normals_out, double* curvature_out) {
     PB_TRY(validate_desc(buf, "buffer"));
-    PB_TRY(ensure_device(ctx));
+    PB_DEVICE(ctx);
     if (buf->len > 0x7FFFFFF0ull) return set_error(PB200_ERR_UNSUPPORTED, "more than 2^31-16 points per call");
     if (k == 0 || k > MAX_K) return set_error(PB200_ERR_UNSUPPORTED, "k must be in 1..%d", MAX_K);
     const uint32_t n = (uint32_t)buf->len;
@@ -737,12 +746,15 @@ static int run_query(pb200_ctx* ctx, const pb200_buffer_desc* buf, int mode, uin
     PB_TRY(out_ptr(counts_out, d_cnt, (size_t)n * 4, &p)); a.counts_out = (uint32_t*)p;
     PB_TRY(out_ptr(normals_out, d_nrm, (size_t)n * 24, &p)); a.normals_out = (double*)p;
     PB_TRY(out_ptr(curvature_out, d_curv, (size_t)n * 8, &p)); a.curvature_out = (double*)p;
-    if (ctx->knn_heap && mode != 3) PB_TRY(launch_query_heap(ctx, mode, a, ctx->stream));
-    else if (k <= 4) launch_query<4>(mode, a, ctx->stream);
-    else if (k <= 16) launch_query<16>(mode, a, ctx->stream);
-    else if (k <= 32) launch_query<32>(mode, a, ctx->stream);
-    else launch_query<64>(mode, a, ctx->stream);
-    g_launches++;
+    {
+        PB_PHASE(ctx, mode == 2 ? "knn.query+normals" : "knn.query");
+        if (ctx->knn_heap && mode != 3) PB_TRY(launch_query_heap(ctx, mode, a, ctx->stream));
+        else if (k <= 4) launch_query<4>(mode, a, ctx->stream);
+        else if (k <= 16) launch_query<16>(mode, a, ctx->stream);
+        else if (k <= 32) launch_query<32>(mode, a, ctx->stream);
+        else launch_query<64>(mode, a, ctx->stream);
+        g_launches++;
+    }
     PB_CUDA(cudaGetLastError());
     if (host) {
         if (idx_out) PB_CUDA(cudaMemcpyAsync(idx_out, a.idx_out, (size_t)n * k * 4, cudaMemcpyDeviceToHost, ctx->stream));
@@ -764,7 +776,10 @@ extern "C" {
 
 int pb200_knn(pb200_ctx* ctx, const pb200_buffer_desc* buf, uint32_t k, uint32_t* idx_out, double* d2_out) {
     if (!ctx || !idx_out) return set_error(PB200_ERR_INVALID, "null argument");
-    const int mode = (ctx->knn_stats && k > 4 && k <= 16) ? 3 : 0;  // diagnostics: idx_out[3*i..] = traversal counters
+    int mode = 0;
+#ifdef PB200_KNN_DIAGNOSTICS  // diagnostic builds only (make KNN_DIAGNOSTICS=1): idx_out[3*i..] = traversal counters
+    if (ctx->knn_stats && k > 4 && k <= 16) mode = 3;
+#endif
     return run_query(ctx, buf, mode, k, 0.0, idx_out, d2_out, nullptr, nullptr, nullptr);
 }
 

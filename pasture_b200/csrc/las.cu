@@ -108,8 +108,11 @@ int pb200_las_read_points(pb200_ctx* ctx, const void* file_bytes, uint64_t size,
     if (first_point > h.number_of_points || count > h.number_of_points - first_point)
         return set_error(PB200_ERR_RANGE, "requested points %llu..%llu but the file holds %llu", (unsigned long long)first_point,
                          (unsigned long long)(first_point + count), (unsigned long long)h.number_of_points);
-    if ((uint64_t)h.offset_to_point_data + h.number_of_points * h.record_length > size)
+    // number_of_points is a 64-bit field of an untrusted header: no products that can wrap
+    if (h.record_length == 0 || (uint64_t)h.offset_to_point_data > size ||
+        h.number_of_points > (size - (uint64_t)h.offset_to_point_data) / h.record_length)
         return set_error(PB200_ERR_RANGE, "file is truncated: point block exceeds the buffer");
+    if (dst_begin > dst->len || count > dst->len - dst_begin) return set_error(PB200_ERR_RANGE, "point_buffer.len() must be >= count");
     if (dst->len < dst_begin + count) return set_error(PB200_ERR_RANGE, "point_buffer.len() must be >= count");  // raw_readers.rs:374-376
     pb200_layout* raw = nullptr;
     PB_TRY(raw_layout_with_extra_bytes(h.point_format, h.extra_bytes, &raw));
@@ -143,7 +146,7 @@ int pb200_las_write_points(pb200_ctx* ctx, const pb200_buffer_desc* src, uint64_
     const uint64_t n = end - begin;
     if (n == 0) return PB200_OK;
     if (!out_records) return set_error(PB200_ERR_INVALID, "null output");
-    PB_TRY(ensure_device(ctx));
+    PB_DEVICE(ctx);
     pb200_layout* raw = nullptr;
     PB_TRY(pb200_las_raw_layout(point_format, &raw));
     const bool extended = point_format >= 6;
@@ -184,8 +187,10 @@ int pb200_las_write_points(pb200_ctx* ctx, const pb200_buffer_desc* src, uint64_
     dst.len = n;
     dst.aos = out_records;
     dst.columns = nullptr;
-    if (out_memspace == PB200_DEVICE) PB_CUDA(cudaMemsetAsync(out_records, 0, (size_t)(n * raw->size), ctx->stream));
-    else memset(out_records, 0, (size_t)(n * raw->size));
+    if (out_memspace == PB200_DEVICE) {
+        const cudaError_t me = cudaMemsetAsync(out_records, 0, (size_t)(n * raw->size), ctx->stream);
+        if (me != cudaSuccess) return done(cuda_error(me, "cudaMemsetAsync(out_records)"));
+    } else memset(out_records, 0, (size_t)(n * raw->size));
     rc = pb200_converter_convert_into_range(cv, src, begin, end, &dst, 0, n, &stats->out_of_range);
     if (rc < 0) return done(rc);
     // running bounds of the written world-space positions (raw_writers.rs:28-47) and points by return

@@ -67,11 +67,23 @@ static int body_desc(const pb200_attr* attrs, uint32_t n_attrs, const void* body
     return PB200_OK;
 }
 
-int pb200_pnts_read_points(pb200_ctx* ctx, const void* body, const pb200_attr* attrs, uint32_t n_attrs, uint64_t first_point,
-                           uint64_t count, const pb200_buffer_desc* dst, const double* rtc_center) {
+int pb200_pnts_read_points(pb200_ctx* ctx, const void* body, uint64_t body_size, const pb200_attr* attrs, uint32_t n_attrs,
+                           uint64_t first_point, uint64_t count, const pb200_buffer_desc* dst, const double* rtc_center) {
     if (!ctx || !attrs || (!body && count)) return set_error(PB200_ERR_INVALID, "null argument");
     PB_TRY(validate_desc(dst, "point buffer"));
     if (n_attrs > PB200_MAX_ATTRIBUTES) return set_error(PB200_ERR_INVALID, "too many attributes");
+    // offsets and POINTS_LENGTH come from an untrusted JSON header: every array must lie inside the body (the reference's
+    // reader fails with UnexpectedEof when it runs off the file, pnts_reader.rs:313-345); overflow-safe arithmetic
+    for (uint32_t i = 0; i < n_attrs && count; ++i) {
+        const uint64_t sz = pb200_dtype_size(attrs[i].dtype, attrs[i].extra_size);
+        const uint64_t off = attrs[i].offset;
+        if (first_point > UINT64_MAX - count) return set_error(PB200_ERR_RANGE, "point range overflows");
+        const uint64_t last = first_point + count;
+        if (off > body_size || (sz && last > (body_size - off) / sz))
+            return set_error(PB200_ERR_RANGE, "unexpected end of file: array of attribute %s (offset %llu, %llu points of %llu bytes) "
+                             "runs past the %llu-byte FeatureTable image", attrs[i].name, (unsigned long long)off,
+                             (unsigned long long)last, (unsigned long long)sz, (unsigned long long)body_size);
+    }
     if (count > dst->len) return set_error(PB200_ERR_RANGE, "point buffer holds %llu points, %llu requested", (unsigned long long)dst->len, (unsigned long long)count);
     // RTC_CENTER goes onto POSITION_3D of the WHOLE target buffer, whatever was read (pnts_reader.rs:247-283, :360-363)
     const int pos_t = pb200_layout_index_by_name(dst->layout, "Position3D");

@@ -285,13 +285,17 @@ int radix_sort_u64(pb200_ctx* ctx, unsigned long long* keys, unsigned long long*
         attr_set[pairs ? 1 : 0] = true;
     }
     unsigned long long hb = (n + 511) / 512, cap = (unsigned long long)ctx->sm_count * 4;
-    radix_histogram_kernel<<<(unsigned)(hb < cap ? hb : cap), 512, 0, st>>>(keys, n, ps, hist);
-    radix_bases_kernel<<<ps.n_passes, RADIX, 0, st>>>(hist);
-    g_launches += 2;
+    {
+        PB_PHASE(ctx, "sort.histogram");
+        radix_histogram_kernel<<<(unsigned)(hb < cap ? hb : cap), 512, 0, st>>>(keys, n, ps, hist);
+        radix_bases_kernel<<<ps.n_passes, RADIX, 0, st>>>(hist);
+        g_launches += 2;
+    }
     unsigned long long *src = keys, *dst = keys_alt;
     uint32_t *vsrc = vals, *vdst = vals_alt;
     for (int p = 0; p < ps.n_passes; ++p) {
         uint32_t* status = (uint32_t*)d_status.p + (size_t)p * n_tiles * RADIX;
+        PB_PHASE(ctx, "sort.pass");
         if (pairs)
             radix_onesweep_kernel<true><<<n_tiles, THREADS, smem, st>>>(src, dst, vsrc, vdst, (uint32_t)n, ps.shift[p], ps.mask[p],
                                                                         hist + p * RADIX, status, tickets + p);
@@ -313,7 +317,7 @@ using namespace pb200;
 
 extern "C" int pb200_radix_sort_u64(pb200_ctx* ctx, uint64_t* keys, uint32_t* vals, uint64_t n, int begin_bit, int end_bit) {
     if (!ctx || (!keys && n)) return set_error(PB200_ERR_INVALID, "null argument");
-    PB_TRY(ensure_device(ctx));
+    PB_DEVICE(ctx);
     if (n <= 1) return PB200_OK;
     DevTmp k2, v2;
     PB_CUDA(k2.alloc(ctx->stream, n * 8));

@@ -304,7 +304,7 @@ int pb200_ransac_rank_samples(pb200_ctx* ctx, const pb200_buffer_desc* buf, int 
     const int per = kind == 0 ? 3 : 2;
     for (uint64_t i = 0; i < n_models * per; ++i)
         if (samples[i] >= buf->len) return set_error(PB200_ERR_RANGE, "sample index %llu out of bounds", (unsigned long long)samples[i]);
-    PB_TRY(ensure_device(ctx));
+    PB_DEVICE(ctx);
     Positions P;
     PB_TRY(ransac_positions(ctx, buf, &P));
     PB_TRY(models_from_sample_indices(ctx, P, kind, samples, n_models, models_out));
@@ -319,7 +319,7 @@ int pb200_ransac_rank_models(pb200_ctx* ctx, const pb200_buffer_desc* buf, int k
     if (n_models == 0) return PB200_OK;
     if (n_models > (1u << 24)) return set_error(PB200_ERR_UNSUPPORTED, "more than 2^24 models per call");
     if (buf->len == 0) { memset(rankings_out, 0, 8 * (size_t)n_models); return PB200_OK; }
-    PB_TRY(ensure_device(ctx));
+    PB_DEVICE(ctx);
     Positions P;
     PB_TRY(ransac_positions(ctx, buf, &P));
     return rank_models(ctx, P, buf->len, kind, models, n_models, distance_threshold, rankings_out);
@@ -332,7 +332,7 @@ int pb200_ransac_inliers(pb200_ctx* ctx, const pb200_buffer_desc* buf, int kind,
     if (kind != PB200_RANSAC_PLANE && kind != PB200_RANSAC_LINE) return set_error(PB200_ERR_INVALID, "bad kind");
     *num_inliers = 0;
     if (buf->len == 0) return PB200_OK;
-    PB_TRY(ensure_device(ctx));
+    PB_DEVICE(ctx);
     Positions P;
     PB_TRY(ransac_positions(ctx, buf, &P));
     return model_inliers(ctx, P, buf->len, kind, model, distance_threshold, buf->memspace == PB200_HOST, indices_out, capacity, num_inliers);
@@ -345,7 +345,7 @@ int pb200_ransac(pb200_ctx* ctx, const pb200_buffer_desc* buf, int kind, double 
     PB_TRY(check_kind_len(kind, buf));
     if (num_of_iterations == 0) return set_error(PB200_ERR_INVALID, "num_of_iterations must be > 0 (max_by(..).unwrap() on an empty iterator panics)");
     if (num_of_iterations > (1u << 24)) return set_error(PB200_ERR_UNSUPPORTED, "more than 2^24 iterations per call");
-    PB_TRY(ensure_device(ctx));
+    PB_DEVICE(ctx);
     const uint64_t n = buf->len;
     const int per = kind == 0 ? 3 : 2, w = kind == 0 ? 4 : 6;
     std::vector<uint64_t> samples((size_t)num_of_iterations * per);

@@ -184,7 +184,7 @@ static void launch_minmax(uint32_t comp, const uint8_t* base, uint64_t stride, u
 
 // Reduce attribute `idx` of `buf` (device or host memory) to 2*nc keys (host array `keys_out`).
 static int reduce_attribute_keys(pb200_ctx* ctx, const pb200_buffer_desc* buf, int idx, unsigned long long* keys_out) {
-    PB_TRY(ensure_device(ctx));
+    PB_DEVICE(ctx);
     const pb200_attr& a = buf->layout->attrs[(size_t)idx];
     const bool vec = is_cast_vec3(a.dtype);
     const uint32_t comp = vec ? vec3_component(a.dtype) : a.dtype;
@@ -372,7 +372,7 @@ int pb200_morton_codes(pb200_ctx* ctx, const pb200_buffer_desc* buf, const doubl
                        uint64_t* codes_out) {
     if (!ctx || !bmin || !bmax || !codes_out) return set_error(PB200_ERR_INVALID, "null argument");
     PB_TRY(validate_desc(buf, "buffer"));
-    PB_TRY(ensure_device(ctx));
+    PB_DEVICE(ctx);
     int pi = pb200_layout_index_of(buf->layout, "Position3D", PB200_VEC3F64);
     if (pi < 0) return set_error(PB200_ERR_ATTR_NOT_FOUND, "buffer has no Vec3f64 Position3D attribute");
     if (buf->memspace != PB200_DEVICE) return set_error(PB200_ERR_UNSUPPORTED, "pb200_morton_codes needs device memory");

@@ -153,7 +153,7 @@ int pb200_reproject(pb200_ctx* ctx, const pb200_buffer_desc* src, const pb200_bu
     if (dst_or_null) PB_TRY(validate_desc(dst, "target point cloud"));
     if (src->len != dst->len) return set_error(PB200_ERR_RANGE, "The point clouds don't have the same size!");  // reprojection.rs:212-214
     if (n_ops > (uint32_t)MAX_PROJ_OPS) return set_error(PB200_ERR_INVALID, "too many pipeline operations");
-    PB_TRY(ensure_device(ctx));
+    PB_DEVICE(ctx);
     const int si = pb200_layout_index_of(src->layout, "Position3D", PB200_VEC3F64);
     const int di = pb200_layout_index_of(dst->layout, "Position3D", PB200_VEC3F64);
     if (si < 0 || di < 0) return set_error(PB200_ERR_ATTR_NOT_FOUND, "buffer has no Vec3f64 Position3D attribute");

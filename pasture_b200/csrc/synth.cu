@@ -54,7 +54,7 @@ using namespace pb200;
 extern "C" {
 
 int pb200_synth_las_fmt0_records(pb200_ctx* ctx, void* device_out, uint64_t first_index, uint64_t n, uint64_t seed) {
-    PB_TRY(ensure_device(ctx));
+    PB_DEVICE(ctx);
     if (!device_out || ((uintptr_t)device_out & 3)) return set_error(PB200_ERR_INVALID, "output must be a 4-byte aligned device pointer");
     if (n == 0) return PB200_OK;
     unsigned long long want = (n + 255) / 256, cap = (unsigned long long)ctx->sm_count * 16;
@@ -64,7 +64,7 @@ int pb200_synth_las_fmt0_records(pb200_ctx* ctx, void* device_out, uint64_t firs
 }
 
 int pb200_synth_terrain_positions(pb200_ctx* ctx, void* device_out, uint64_t first_index, uint64_t n, uint64_t seed) {
-    PB_TRY(ensure_device(ctx));
+    PB_DEVICE(ctx);
     if (!device_out || ((uintptr_t)device_out & 7)) return set_error(PB200_ERR_INVALID, "output must be an 8-byte aligned device pointer");
     if (n == 0) return PB200_OK;
     unsigned long long want = (n + 255) / 256, cap = (unsigned long long)ctx->sm_count * 16;

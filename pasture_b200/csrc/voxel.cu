@@ -504,8 +504,11 @@ static int build_voxel_index(pb200_ctx* ctx, const uint8_t* ppos, uint64_t pstri
     if (((uintptr_t)ppos & 7) || (pstride & 7)) return set_error(PB200_ERR_UNSUPPORTED, "POSITION_3D must be 8-byte aligned in memory");
     const unsigned long long cap = (unsigned long long)ctx->sm_count * 16;
     const unsigned blocks = (unsigned)(((n + 255) / 256) < cap ? ((n + 255) / 256) : cap);
-    voxel_key_kernel<<<blocks, 256, 0, st>>>(ppos, pstride, n, grid, shift, (unsigned long long*)d_keys.p, (uint32_t*)d_idx.p);
-    g_launches++;
+    {
+        PB_PHASE(ctx, "voxel.keys");
+        voxel_key_kernel<<<blocks, 256, 0, st>>>(ppos, pstride, n, grid, shift, (unsigned long long*)d_keys.p, (uint32_t*)d_idx.p);
+        g_launches++;
+    }
     // K8: own one-sweep radix sort (radix_sort.cu); cub only for clouds beyond its 2^30-key limit
     if (n < (1ull << 30)) {
         bool in_alt = false;
@@ -536,9 +539,12 @@ static int build_voxel_index(pb200_ctx* ctx, const uint8_t* ppos, uint64_t pstri
     const uint32_t n_tiles = (uint32_t)((n + HT_TILE - 1) / HT_TILE);
     PB_CUDA(d_tiles.alloc(st, ((size_t)n_tiles + 1) * 4));
     uint32_t* d_total = (uint32_t*)d_tiles.p + n_tiles;
-    heads_count_kernel<<<n_tiles, HT_THREADS, 0, st>>>((const unsigned long long*)d_keys2.p, n, shift, (uint32_t*)d_tiles.p);
-    PB_TRY(exclusive_scan_u32(ctx, (uint32_t*)d_tiles.p, n_tiles, d_total));
-    g_launches += 2;
+    {
+        PB_PHASE(ctx, "voxel.heads_count+scan");
+        heads_count_kernel<<<n_tiles, HT_THREADS, 0, st>>>((const unsigned long long*)d_keys2.p, n, shift, (uint32_t*)d_tiles.p);
+        PB_TRY(exclusive_scan_u32(ctx, (uint32_t*)d_tiles.p, n_tiles, d_total));
+        g_launches += 2;
+    }
     uint32_t* h_total = (uint32_t*)ctx->h_scratch;
     PB_CUDA(cudaMemcpyAsync(h_total, d_total, 4, cudaMemcpyDeviceToHost, st));
     PB_CUDA(cudaStreamSynchronize(st));
@@ -547,9 +553,12 @@ static int build_voxel_index(pb200_ctx* ctx, const uint8_t* ppos, uint64_t pstri
     DevTmp &d_starts = vi->starts, &d_vkeys = vi->voxel_keys;
     PB_CUDA(d_starts.alloc(st, (V + 1) * 4));
     PB_CUDA(d_vkeys.alloc(st, V * 8 + 8));
-    heads_emit_kernel<<<n_tiles, HT_THREADS, 0, st>>>((const unsigned long long*)d_keys2.p, n, shift, (const uint32_t*)d_tiles.p, (uint32_t)V,
-                                                      (uint32_t*)d_starts.p, (unsigned long long*)d_vkeys.p, packed ? (uint32_t*)d_idx2.p : nullptr);
-    g_launches++;
+    {
+        PB_PHASE(ctx, "voxel.heads_emit");
+        heads_emit_kernel<<<n_tiles, HT_THREADS, 0, st>>>((const unsigned long long*)d_keys2.p, n, shift, (const uint32_t*)d_tiles.p, (uint32_t)V,
+                                                          (uint32_t*)d_starts.p, (unsigned long long*)d_vkeys.p, packed ? (uint32_t*)d_idx2.p : nullptr);
+        g_launches++;
+    }
 
     PB_CUDA(cudaGetLastError());
     return PB200_OK;
@@ -567,7 +576,7 @@ int pb200_voxelgrid_filter(pb200_ctx* ctx, const pb200_buffer_desc* src, double 
     if (!ctx || !dst_layout || !out) return set_error(PB200_ERR_INVALID, "null argument");
     *out = nullptr;
     PB_TRY(validate_desc(src, "source buffer"));
-    PB_TRY(ensure_device(ctx));
+    PB_DEVICE(ctx);
     if (dst_kind != PB200_INTERLEAVED && dst_kind != PB200_COLUMNAR) return set_error(PB200_ERR_INVALID, "bad dst_kind");
     const int pi = pb200_layout_index_of(src->layout, "Position3D", PB200_VEC3F64);
     if (pi < 0)  // voxel_grid.rs:116-121
@@ -637,7 +646,7 @@ int pb200_voxelgrid_filter(pb200_ctx* ctx, const pb200_buffer_desc* src, double 
     dsrc.columns = dcol_ptrs.data();
     double bmin[3], bmax[3];
     int some = 0;
-    PB_TRY(pb200_calculate_bounds(ctx, &dsrc, bmin, bmax, &some));
+    { PB_PHASE(ctx, "voxel.bounds"); PB_TRY(pb200_calculate_bounds(ctx, &dsrc, bmin, bmax, &some)); }
     if (!some) return set_error(PB200_ERR_INVALID, "calculate_bounds returned None");
     uint64_t pstride = 0;
     const uint8_t* ppos = attr_ptr(pi, &pstride);
@@ -717,6 +726,7 @@ int pb200_voxelgrid_filter(pb200_ctx* ctx, const pb200_buffer_desc* src, double 
                                                            (dt == PB200_I8 || dt == PB200_I16) ? 32768ll : 0ll);
             g_launches += 3;
         } else {
+            PB_PHASE(ctx, "voxel.reduce");
             launch_reduce(*rules[a], ra, st);
         }
     }
@@ -806,7 +816,7 @@ int pb200_voxelgrid_partials(pb200_ctx* ctx, const pb200_buffer_desc* src, doubl
     if (!ctx || !out || !global_min || !global_max) return set_error(PB200_ERR_INVALID, "null argument");
     *out = nullptr;
     PB_TRY(validate_desc(src, "source buffer"));
-    PB_TRY(ensure_device(ctx));
+    PB_DEVICE(ctx);
     const double leaf[3] = {lx, ly, lz};
     for (int c = 0; c < 3; ++c) {
         if (!(leaf[c] > 0.0)) return set_error(PB200_ERR_INVALID, "leaf sizes must be positive (the reference would not terminate)");
@@ -860,7 +870,7 @@ int pb200_voxelgrid_merge_partials(pb200_ctx* ctx, const uint64_t* keys, const u
     if (m && (!keys || !counts || !sums)) return set_error(PB200_ERR_INVALID, "null partial arrays");
     if (m > 0xFFFFFFFEull) return set_error(PB200_ERR_UNSUPPORTED, "more than 2^32-2 partial voxels per call");
     if (bits_x + bits_y + bits_z > 64 || bits_x + bits_y + bits_z == 0) return set_error(PB200_ERR_INVALID, "bad key widths");
-    PB_TRY(ensure_device(ctx));
+    PB_DEVICE(ctx);
     cudaStream_t st = ctx->stream;
     pb200_voxel_partials* res = new pb200_voxel_partials();
     res->ctx = ctx;
@@ -922,7 +932,7 @@ int pb200_voxel_partials_get(const pb200_voxel_partials* p, pb200_voxel_partials
 int pb200_voxel_partials_centroids(const pb200_voxel_partials* p, double* positions_out) {
     if (!p || (!positions_out && p->len)) return set_error(PB200_ERR_INVALID, "null argument");
     if (p->len == 0) return PB200_OK;
-    PB_TRY(ensure_device(p->ctx));
+    PB_DEVICE(p->ctx);
     const unsigned long long cap = (unsigned long long)p->ctx->sm_count * 16;
     const unsigned blocks = (unsigned)(((p->len + 255) / 256) < cap ? ((p->len + 255) / 256) : cap);
     partials_centroid_kernel<<<blocks, 256, 0, p->ctx->stream>>>((const uint32_t*)p->counts, (const double*)p->sums, p->len, positions_out);
@@ -955,7 +965,7 @@ int pb200_result_buffer_desc(const pb200_result_buffer* r, pb200_buffer_desc* ou
 int pb200_result_buffer_voxel_keys(const pb200_result_buffer* r, uint64_t* keys_out) {
     if (!r || !keys_out) return set_error(PB200_ERR_INVALID, "null argument");
     if (r->len == 0) return PB200_OK;
-    PB_TRY(ensure_device(r->ctx));
+    PB_DEVICE(r->ctx);
     std::vector<unsigned long long> packed(r->len);
     PB_CUDA(cudaMemcpyAsync(packed.data(), r->d_packed_keys, r->len * 8, cudaMemcpyDeviceToHost, r->ctx->stream));
     PB_CUDA(cudaStreamSynchronize(r->ctx->stream));

@@ -7,7 +7,7 @@ import numpy as np
 import torch
 
 from ._lib import LasHeader, LasWriteStats, check, lib
-from .context import get_context
+from .context import context_for, get_context
 from .layout import PointLayout
 
 
@@ -26,7 +26,7 @@ def default_point_layout(file_bytes):
 
 def read_points(file_bytes, point_buffer, count=None, first_point=0, buffer_offset=0, ctx=None):
     """PointReader::read_into: fills point_buffer[buffer_offset ...] (any layout, host or device) from the LAS image"""
-    ctx = ctx or get_context()
+    ctx = context_for(ctx, point_buffer)
     buf = np.frombuffer(file_bytes, dtype=np.uint8)
     h = parse_header(file_bytes)
     n = int(h.number_of_points) - first_point if count is None else int(count)
@@ -37,7 +37,7 @@ def read_points(file_bytes, point_buffer, count=None, first_point=0, buffer_offs
 
 def write_points(point_buffer, point_format, scale, offset, point_range=None, device=None, ctx=None):
     """RawLASWriter::write (default layout): -> (records: uint8 tensor (n, record_length), stats dict)"""
-    ctx = ctx or get_context()
+    ctx = context_for(ctx, point_buffer)
     r = point_range if point_range is not None else range(0, point_buffer.len())
     n = len(r)
     rec = PointLayout.las_raw(point_format).size_of_point_entry()

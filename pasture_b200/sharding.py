@@ -156,7 +156,19 @@ class PeerComm:
     @classmethod
     def local_group(cls, contexts):
         """one process, several contexts (streams / devices): ranks are the list positions"""
+        import os
         from ._lib import check, lib
+        per_device = {}
+        for c in contexts:
+            per_device[c.device] = per_device.get(c.device, 0) + 1
+        crowd = max(per_device.values()) if per_device else 0
+        if crowd > 1:
+            # the fused kernels of these ranks spin-wait for each other INSIDE the kernel: they must run concurrently, so
+            # their streams must not share a hardware work queue (default: 8 connections, streams alias beyond that)
+            have = int(os.environ.get("CUDA_DEVICE_MAX_CONNECTIONS", "8") or 8)
+            if have < 2 * crowd:
+                raise RuntimeError(f"{crowd} logical ranks share one device: set CUDA_DEVICE_MAX_CONNECTIONS >= {2 * crowd} "
+                                   f"(now {have}) before CUDA is initialised, or the ranks' kernels can serialise and time out")
         comms = [cls(c, _rank=r, _world=len(contexts), _connect=False) for r, c in enumerate(contexts)]
         ptrs = (C.c_void_p * len(comms))()
         for r, cm in enumerate(comms):

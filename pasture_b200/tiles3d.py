@@ -10,7 +10,7 @@ import torch
 
 from ._lib import Attr, check, lib
 from .containers import HashMapBuffer, VectorBuffer
-from .context import get_context
+from .context import context_for, get_context
 from .layout import DT, FieldAlignment, PointAttributeDefinition, PointLayout, attributes
 
 COLOR_RGBA = PointAttributeDefinition("ColorRGBA", DT.Vec4u8)  # pnts_types.rs:11-14
@@ -65,6 +65,10 @@ class PntsReader:
         magic, _version, _byte_length, ft_json, _ft_bin, _bt_json, _bt_bin = struct.unpack("<4s6I", head[:PNTS_HEADER_BYTE_LENGTH])
         if magic != b"pnts":  # verify_magic, pnts_types.rs:58-63
             raise ValueError(f"No valid PNTS file, expected first four bytes to be equal to 'pnts', but was '{magic}' instead")
+        if PNTS_HEADER_BYTE_LENGTH + ft_json > self._blob.numel():
+            raise EOFError("unexpected end of file inside the FeatureTable JSON header")
+        if PNTS_HEADER_BYTE_LENGTH + ft_json > len(head):  # device-resident image: fetch the whole JSON, however long
+            head = bytes(self._blob[: PNTS_HEADER_BYTE_LENGTH + ft_json].cpu().numpy())
         header = json.loads(head[PNTS_HEADER_BYTE_LENGTH:PNTS_HEADER_BYTE_LENGTH + ft_json].decode("utf-8"))
         if not isinstance(header, dict):
             raise ValueError("FeatureTable JSON header was no JSON object")
@@ -111,7 +115,7 @@ class PntsReader:
         return self.layout
 
     def read_into(self, point_buffer, count, ctx=None):  # pnts_reader.rs:294-367
-        ctx = ctx or get_context()
+        ctx = context_for(ctx, point_buffer)
         remaining = self.metadata.points_length - self.current_point_index
         num_to_read = min(remaining, int(count))
         if num_to_read == 0:
@@ -123,7 +127,7 @@ class PntsReader:
         if self._mode == ABSOLUTE and self.metadata.rtc_center is not None:
             rtc = (C.c_double * 3)(*self.metadata.rtc_center)
         d = point_buffer.desc()
-        check(lib().pb200_pnts_read_points(ctx._h, C.c_void_p(blob.data_ptr()), arr, len(entries), self.current_point_index,
+        check(lib().pb200_pnts_read_points(ctx._h, C.c_void_p(blob.data_ptr()), blob.numel(), arr, len(entries), self.current_point_index,
                                            num_to_read, C.byref(d), rtc))
         self.current_point_index += num_to_read
         return num_to_read
@@ -164,7 +168,7 @@ class PntsWriter:
         return self.default_layout
 
     def write(self, points, ctx=None):  # :353-401
-        ctx = ctx or get_context()
+        ctx = context_for(ctx, points)
         if points.point_layout() != self.expected_layout:
             raise ValueError("PointLayout of buffer does not match the PointLayout that this PntsWriter was constructed with!")
         n = points.len()

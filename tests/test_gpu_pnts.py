@@ -196,7 +196,7 @@ def test_full_size_roundtrip():
     dst = HashMapBuffer(pl, n, "cuda")
     d = dst.desc()
     rtc = (C.c_double * 3)(1e6, -2e6, 0.5)
-    check(lib().pb200_pnts_read_points(pb.get_context()._h, C.c_void_p(body.data_ptr()), arr, 2, 0, n, C.byref(d), rtc))
+    check(lib().pb200_pnts_read_points(pb.get_context()._h, C.c_void_p(body.data_ptr()), body.numel(), arr, 2, 0, n, C.byref(d), rtc))
     got = dst.columns[0][: 24 * n].view(torch.float64).reshape(n, 3)
     want = f32.to(torch.float64) + torch.tensor([1e6, -2e6, 0.5], dtype=torch.float64, device="cuda")
     assert torch.equal(got, want)
