@@ -167,6 +167,7 @@ _C4_PHASE_BYTES = {"knn.bounds": 24, "knn.codes": 24 + 12, "sort.histogram": 8, 
 def _phase_table(phases, bytes_of, n, peak):
     """[(name, ms)] of ONE call -> per-kernel rows; repeated names (sort passes) are summed"""
     agg = {}
+    phases = [(nm, ms) for nm, ms in phases if not nm.endswith(".call") and not nm.startswith(("host.", "pool."))]  # kernels only
     for name, ms in phases:
         a = agg.setdefault(name, {"name": name, "ms": 0.0, "launch_groups": 0})
         a["ms"] += ms
@@ -214,7 +215,11 @@ def other_configs(pb, ctx, dev, peak):
                "achieved_GBps": bytes_total_per_point * n / (ms * 1e-3) / 1e9,
                "frac": bytes_total_per_point * n / (ms * 1e-3) / 1e9 / peak,
                "kernels": _phase_table(phases, phase_bytes(res) if callable(phase_bytes) else phase_bytes, n, peak),
-               "kernel_ms_sum": sum(m for _, m in phases), "clocks": clocks.summary(),
+               "kernel_ms_sum": sum(m for nm, m in phases if not nm.endswith(".call") and not nm.startswith(("host.", "pool."))),
+               "pool_MB": {nm: m for nm, m in phases if nm.startswith("pool.")},
+               "call_ms_profiled": next((m for nm, m in phases if nm.endswith(".call")), None),
+               "host_timeline_us": [(nm, round(a), round(b)) for nm, a, b in ctx.last_profile_host_us],
+               "clocks": clocks.summary(),
                "timing": "CUDA events around the whole library call (best of %d, device-resident input, includes the "
                          "call's host synchronisations); kernels: one extra profiled call" % reps}
         return row, res

@@ -54,9 +54,11 @@ class Context:
         buf = C.create_string_buffer(1 << 16)
         check(lib().pb200_ctx_profile_read(self._h, buf, len(buf)))
         out = []
+        self.last_profile_host_us = []
         for line in buf.value.decode().splitlines():
-            name, ms = line.split("\t")
-            out.append((name, float(ms)))
+            f = line.split("\t")
+            out.append((f[0], float(f[1])))
+            self.last_profile_host_us.append((f[0], float(f[2]), float(f[3])))  # host time of scope entry / exit
         return out
 
     def bind_host_thread(self):

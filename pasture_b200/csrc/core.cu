@@ -9,6 +9,54 @@ namespace pb200 {
 extern int64_t g_cost_div, g_cost_pack_base, g_cost_pack_per_src, g_cost_copy_base, g_cost_store;  // convert.cu cost model
 
 std::atomic<uint64_t> g_launches{0};
+thread_local pb200_ctx* tl_ctx = nullptr;
+
+cudaError_t cache_alloc(pb200_ctx* ctx, void** out, size_t bytes) {
+    *out = nullptr;
+    // size classes: multiples of 2 MiB from 2 MiB up, powers of two (>= 512 B) below
+    size_t need = bytes ? bytes : 1;
+    if (need >= ((size_t)2 << 20)) need = (need + ((size_t)2 << 20) - 1) & ~(((size_t)2 << 20) - 1);
+    else { size_t c = 512; while (c < need) c <<= 1; need = c; }
+    auto& fb = ctx->cache_free_blocks;
+    size_t best = fb.size();
+    const size_t limit = need + need / 4 + ((size_t)2 << 20);
+    for (size_t i = 0; i < fb.size(); ++i)
+        if (fb[i].second >= need && fb[i].second <= limit && (best == fb.size() || fb[i].second < fb[best].second)) best = i;
+    if (best != fb.size()) {
+        *out = fb[best].first;
+        ctx->cache_live[*out] = fb[best].second;
+        fb[best] = fb.back();
+        fb.pop_back();
+        return cudaSuccess;
+    }
+    void* p = nullptr;
+    cudaError_t e = cudaMalloc(&p, need);
+    if (e == cudaErrorMemoryAllocation) {  // give the idle blocks back and try once more
+        cudaGetLastError();
+        cudaStreamSynchronize(ctx->stream);
+        for (auto& b : fb) { cudaFree(b.first); ctx->cache_reserved -= b.second; }
+        fb.clear();
+        e = cudaMalloc(&p, need);
+    }
+    if (e != cudaSuccess) return e;
+    ctx->cache_reserved += need;
+    ctx->cache_live[p] = need;
+    *out = p;
+    return cudaSuccess;
+}
+
+void cache_free(pb200_ctx* ctx, void* p) {
+    if (!p) return;
+    auto it = ctx->cache_live.find(p);
+    if (it == ctx->cache_live.end()) { cudaFreeAsync(p, ctx->stream); return; }  // not ours: driver pool memory
+    ctx->cache_free_blocks.emplace_back(p, it->second);
+    ctx->cache_live.erase(it);
+}
+
+void cache_trim(pb200_ctx* ctx) {
+    for (auto& b : ctx->cache_free_blocks) { cudaFree(b.first); ctx->cache_reserved -= b.second; }
+    ctx->cache_free_blocks.clear();
+}
 static thread_local char g_err[512] = "";
 
 int set_error(int code, const char* fmt, ...) {
@@ -111,6 +159,8 @@ int pb200_ctx_create(int device, pb200_ctx** out) {
     PB_CUDA(cudaStreamCreateWithFlags(&c->copy_in, cudaStreamNonBlocking));
     PB_CUDA(cudaStreamCreateWithFlags(&c->copy_out, cudaStreamNonBlocking));
     PB_CUDA(cudaHostAlloc(&c->h_scratch, 4096, cudaHostAllocDefault));
+    c->h_stage_bytes = (size_t)1 << 20;
+    PB_CUDA(cudaHostAlloc(&c->h_stage, c->h_stage_bytes, cudaHostAllocDefault));
     {   // keep freed temporaries (DevTmp) in the pool between calls; pb200_ctx_trim hands them back
         cudaMemPool_t pool;
         if (cudaDeviceGetDefaultMemPool(&pool, device) == cudaSuccess) {
@@ -125,9 +175,19 @@ int pb200_ctx_create(int device, pb200_ctx** out) {
 
 int pb200_ctx_set_stream(pb200_ctx* ctx, void* s) {
     PB_DEVICE(ctx);
+    if ((cudaStream_t)s == ctx->stream) return PB200_OK;
     if (ctx->owns_stream && ctx->stream) {
         cudaStreamSynchronize(ctx->stream);
         cudaStreamDestroy(ctx->stream);
+    } else if (ctx->stream || !ctx->cache_free_blocks.empty()) {
+        // cached blocks may still be in use by work queued on the old stream: the new stream starts behind it
+        cudaEvent_t ev;
+        if (cudaEventCreateWithFlags(&ev, cudaEventDisableTiming) == cudaSuccess) {
+            cudaEventRecord(ev, ctx->stream);
+            cudaStreamWaitEvent((cudaStream_t)s, ev, 0);
+            cudaEventDestroy(ev);
+        }
+        cudaGetLastError();
     }
     ctx->stream = (cudaStream_t)s;
     ctx->owns_stream = false;
@@ -145,6 +205,7 @@ int pb200_ctx_synchronize(pb200_ctx* ctx) {
 int pb200_ctx_trim(pb200_ctx* ctx) {
     PB_DEVICE(ctx);
     PB_CUDA(cudaStreamSynchronize(ctx->stream));
+    cache_trim(ctx);
     cudaMemPool_t pool;
     PB_CUDA(cudaDeviceGetDefaultMemPool(&pool, ctx->device));
     PB_CUDA(cudaMemPoolTrimTo(pool, 0));
@@ -166,6 +227,7 @@ int pb200_ctx_set_param(pb200_ctx* ctx, const char* key, int64_t v) {
     else if (k == "convert.cost_copy_base") g_cost_copy_base = v;
     else if (k == "convert.cost_store") g_cost_store = v;
     else if (k == "profile.phases") ctx->profile = v;
+    else if (k == "sort.force_8bit") ctx->sort_force_8bit = v;
     else if (k == "knn.init_radius") ctx->knn_init_radius = v;
     else if (k == "knn.stats") {
 #ifdef PB200_KNN_DIAGNOSTICS
@@ -190,11 +252,25 @@ int pb200_ctx_profile_read(pb200_ctx* ctx, char* out, uint64_t capacity) {
     for (auto& r : ctx->phases) {
         float ms = 0.f;
         if (cudaEventElapsedTime(&ms, r.e0, r.e1) == cudaSuccess && out && used + 96 < capacity) {
-            used += (uint64_t)snprintf(out + used, (size_t)(capacity - used), "%s\t%.6f\n", r.name, (double)ms);
+            // name, device milliseconds between the two events, host time of scope entry / exit relative to the first record
+            used += (uint64_t)snprintf(out + used, (size_t)(capacity - used), "%s\t%.6f\t%.1f\t%.1f\n", r.name, (double)ms,
+                                       r.host_t0_us - ctx->phases[0].host_t0_us, r.host_t1_us - ctx->phases[0].host_t0_us);
             ++n;
         }
         cudaEventDestroy(r.e0);
         cudaEventDestroy(r.e1);
+    }
+    {   // where the temporaries live: the device's stream-ordered pool
+        cudaMemPool_t pool;
+        uint64_t reserved = 0, used = 0, high = 0;
+        if (cudaDeviceGetDefaultMemPool(&pool, ctx->device) == cudaSuccess && out && used + 160 < capacity) {
+            cudaMemPoolGetAttribute(pool, cudaMemPoolAttrReservedMemCurrent, &reserved);
+            cudaMemPoolGetAttribute(pool, cudaMemPoolAttrUsedMemCurrent, &used);
+            cudaMemPoolGetAttribute(pool, cudaMemPoolAttrReservedMemHigh, &high);
+            size_t len = strlen(out);
+            snprintf(out + len, (size_t)(capacity - len), "pool.driver_reserved_MB\t%.1f\t0\t0\npool.cache_reserved_MB\t%.1f\t0\t0\npool.cache_idle_blocks\t%.1f\t0\t0\n",
+                     reserved / 1048576.0, ctx->cache_reserved / 1048576.0, (double)ctx->cache_free_blocks.size());
+        }
     }
     cudaGetLastError();
     ctx->phases.clear();
@@ -206,8 +282,11 @@ void pb200_ctx_destroy(pb200_ctx* ctx) {
     cudaSetDevice(ctx->device);
     if (ctx->stream) cudaStreamSynchronize(ctx->stream);
     for (auto& r : ctx->phases) { cudaEventDestroy(r.e0); cudaEventDestroy(r.e1); }
+    cache_trim(ctx);
+    for (auto& kv : ctx->cache_live) cudaFree(kv.first);  // blocks whose owners outlived the context
     if (ctx->d_scratch) cudaFree(ctx->d_scratch);
     if (ctx->h_scratch) cudaFreeHost(ctx->h_scratch);
+    if (ctx->h_stage) cudaFreeHost(ctx->h_stage);
     if (ctx->owns_stream && ctx->stream) cudaStreamDestroy(ctx->stream);
     if (ctx->copy_in) cudaStreamDestroy(ctx->copy_in);
     if (ctx->copy_out) cudaStreamDestroy(ctx->copy_out);

@@ -3,11 +3,13 @@
 #include <cuda_runtime.h>
 
 #include <atomic>
+#include <chrono>
 #include <cstdarg>
 #include <cstdint>
 #include <cstdio>
 #include <cstring>
 #include <string>
+#include <unordered_map>
 #include <utility>
 #include <vector>
 
@@ -27,20 +29,28 @@ struct pb200_ctx {
     size_t smem_optin = 0;
     // tuning knobs (0 = automatic)
     int64_t tile_points = 0, threads = 0, stages = 0, ctas_per_sm = 0, force_direct = 0;
+    int64_t sort_force_8bit = 0;  // experiments: keep 8-bit digits even where 9-bit ones save a pass
     int64_t stage_chunk_mb = 0;  // staged bytes per chunk of the HOST-memspace pipeline (0 = 128 MB)
     int64_t knn_init_radius = -1, knn_stats = 0, knn_per_axis_codes = 0, knn_heap = 1;  // experiments / diagnostics
     // scratch
     void* d_scratch = nullptr;  // small device scratch (counters, partials)
     size_t d_scratch_bytes = 0;
     void* h_scratch = nullptr;  // pinned host scratch for small readbacks
+    void* h_stage = nullptr;    // pinned host staging for small uploads (voxel marker tables)
+    size_t h_stage_bytes = 0;
     // staging for HOST memspace buffers
     cudaStream_t copy_in = nullptr, copy_out = nullptr;
     // phase timer ("profile.phases" = 1): CUDA event pairs around the phases of a call, read by pb200_ctx_profile_read
     int64_t profile = 0;
-    struct PhaseRec { const char* name; cudaEvent_t e0, e1; };
+    struct PhaseRec { const char* name; cudaEvent_t e0, e1; double host_t0_us, host_t1_us; };
     std::vector<PhaseRec> phases;
+    // device-memory cache (core.cu cache_alloc / cache_free): temporaries and library-owned results of repeated calls are
+    // recycled here instead of going through the driver
+    std::vector<std::pair<void*, size_t>> cache_free_blocks;
+    std::unordered_map<void*, size_t> cache_live;
+    size_t cache_reserved = 0;
     bool convert_attr_set = false;  // cudaFuncSetAttribute is per device: every context configures its kernels once
-    bool sort_attr_set[2] = {false, false}, knn_attr_set = false;
+    bool sort_attr_set[2] = {false, false}, knn_attr_set = false, voxel_attr_set = false;
 };
 
 namespace pb200 {
@@ -81,16 +91,33 @@ inline bool dtype_equal(const pb200_attr& a, const pb200_attr& b) {
     return true;
 }
 int ensure_device(pb200_ctx* ctx);
+// Device memory for temporaries and library-owned results.  cudaMallocAsync from the driver's stream-ordered pool cost
+// 1.2-1.4 ms per GB on B200 even when the pool already held the memory (measured: 2.3 ms for the two 0.8 GB key arrays
+// of a 100 M-point voxel grid, 2.8 ms for its 1.2 GB of results; the pool re-maps on every request), i.e. 5 ms of a 13 ms
+// call.  The context therefore keeps freed blocks itself: best fit among them (at most 25 % + 2 MiB larger than the request),
+// cudaMalloc only when nothing fits.  Safe without synchronisation because all work of a context is ordered on ONE
+// stream (a block is only handed out again to work queued behind its last user; pb200_ctx_set_stream orders the new
+// stream behind the old one).  pb200_ctx_trim gives everything back.
+cudaError_t cache_alloc(pb200_ctx* ctx, void** out, size_t bytes);
+void cache_free(pb200_ctx* ctx, void* p);
+void cache_trim(pb200_ctx* ctx);
+extern thread_local pb200_ctx* tl_ctx;  // context of the API call running on this thread (set by DeviceGuard)
 // Every entry point makes its context's device current for the duration of the call and puts the caller's device back
 // on return (a host framework such as torch keeps its own notion of the current device).
 struct DeviceGuard {
     int prev = -1, rc = 0;
+    pb200_ctx* prev_ctx = nullptr;
     explicit DeviceGuard(pb200_ctx* ctx) {
         if (cudaGetDevice(&prev) != cudaSuccess) { prev = -1; cudaGetLastError(); }
         rc = ensure_device(ctx);
         if (rc == 0 && ctx && prev == ctx->device) prev = -1;  // nothing to restore
+        prev_ctx = tl_ctx;
+        if (ctx) tl_ctx = ctx;
     }
-    ~DeviceGuard() { if (prev >= 0) cudaSetDevice(prev); }
+    ~DeviceGuard() {
+        tl_ctx = prev_ctx;
+        if (prev >= 0) cudaSetDevice(prev);
+    }
     DeviceGuard(const DeviceGuard&) = delete;
     DeviceGuard& operator=(const DeviceGuard&) = delete;
 };
@@ -101,39 +128,52 @@ struct DeviceGuard {
 int scratch(pb200_ctx* ctx, size_t bytes, void** out);
 int validate_desc(const pb200_buffer_desc* d, const char* what);
 
-// Stream-ordered temporary (cudaMallocAsync from the device's default pool, whose release threshold the context raises
-// so that the multi-GB sort / tree buffers of repeated calls are recycled instead of going back to the driver).
-// Freed behind the work already queued on the stream: no host synchronisation is needed before it goes out of scope.
+// Temporary device memory of one API call, taken from the context's cache (cache_alloc) and handed back when it goes out
+// of scope: no host synchronisation, the work already queued on the context's stream that uses it runs before any later
+// user of the block.  Outside an API call (no current context) it falls back to the driver's stream-ordered pool.
 struct DevTmp {
     void* p = nullptr;
     cudaStream_t st = nullptr;
+    pb200_ctx* owner = nullptr;
     DevTmp() = default;
     DevTmp(const DevTmp&) = delete;
     DevTmp& operator=(const DevTmp&) = delete;
     ~DevTmp() { release(); }
-    void release() { if (p) cudaFreeAsync(p, st); p = nullptr; }
+    void release() {
+        if (p) { if (owner) cache_free(owner, p); else cudaFreeAsync(p, st); }
+        p = nullptr;
+    }
     cudaError_t alloc(cudaStream_t s, size_t bytes) {
         release();
         st = s;
+        owner = tl_ctx;
+        if (owner) return cache_alloc(owner, &p, bytes ? bytes : 1);
         return cudaMallocAsync(&p, bytes ? bytes : 1, s);
     }
 };
 
 // Scoped phase timer: PB_PHASE(ctx, "voxel.reduce") brackets the kernels launched in the enclosing scope with two events
-// on the context's stream when profiling is on (no cost otherwise).  bench.py turns the records into per-kernel
-// milliseconds and roofline fractions of the C3 / C4 configurations.
+// on the context's stream when profiling is on (no cost otherwise) and notes the host time of scope entry / exit.
+// bench.py turns the records into per-kernel milliseconds and roofline fractions of the C3 / C4 configurations.
 struct PhaseScope {
     pb200_ctx* c;
     int idx = -1;
     PhaseScope(pb200_ctx* ctx, const char* name) : c(ctx) {
         if (!c || !c->profile) return;
-        pb200_ctx::PhaseRec r{name, nullptr, nullptr};
+        pb200_ctx::PhaseRec r{name, nullptr, nullptr, now_us(), 0.0};
         if (cudaEventCreate(&r.e0) != cudaSuccess || cudaEventCreate(&r.e1) != cudaSuccess) { cudaGetLastError(); return; }
         cudaEventRecord(r.e0, c->stream);
         idx = (int)c->phases.size();
         c->phases.push_back(r);
     }
-    ~PhaseScope() { if (idx >= 0) cudaEventRecord(c->phases[(size_t)idx].e1, c->stream); }
+    ~PhaseScope() {
+        if (idx < 0) return;
+        cudaEventRecord(c->phases[(size_t)idx].e1, c->stream);
+        c->phases[(size_t)idx].host_t1_us = now_us();
+    }
+    static double now_us() {
+        return std::chrono::duration<double, std::micro>(std::chrono::steady_clock::now().time_since_epoch()).count();
+    }
 };
 #define PB_PHASE_CAT2(a, b) a##b
 #define PB_PHASE_CAT(a, b) PB_PHASE_CAT2(a, b)

@@ -18,7 +18,10 @@ namespace pb200 {
 
 namespace rs {
 
-constexpr int RADIX_BITS = 8, RADIX = 1 << RADIX_BITS;
+// Digits are 8 or 9 bits wide: a 9-bit pass (512 bins, one look-back thread per bin = the whole CTA) costs about the same
+// as an 8-bit one, so whenever ceil(bits / 9) < ceil(bits / 8) the plan uses 9-bit digits and saves a whole sweep over the
+// data (the 34 voxel-key bits of C3: 9+9+8+8 = 4 passes instead of 5; the 63 Morton bits: 7 instead of 8).
+constexpr int MAX_RADIX_BITS = 9, MAX_RADIX = 1 << MAX_RADIX_BITS;
 constexpr int THREADS = 512, WARPS = THREADS / 32, IPT = 16, TILE = THREADS * IPT;  // 8192 keys per tile
 constexpr int MAX_PASSES = 8;
 constexpr int LOOK = 8;  // predecessors fetched per look-back batch
@@ -32,7 +35,8 @@ struct Passes {
 
 __global__ void __launch_bounds__(512) radix_histogram_kernel(const unsigned long long* __restrict__ keys, unsigned long long n,
                                                               Passes ps, uint32_t* __restrict__ hist /* [passes][256] */) {
-    __shared__ uint32_t s_hist[MAX_PASSES * RADIX];
+    __shared__ uint32_t s_hist[MAX_PASSES * MAX_RADIX];
+    constexpr int RADIX = MAX_RADIX;  // histogram rows are MAX_RADIX wide whatever the digit width of a pass
     for (int i = threadIdx.x; i < ps.n_passes * RADIX; i += blockDim.x) s_hist[i] = 0;
     __syncthreads();
     auto count = [&](unsigned long long k) {
@@ -56,7 +60,8 @@ __global__ void __launch_bounds__(512) radix_histogram_kernel(const unsigned lon
 }
 
 // exclusive scan of every pass's histogram in place: hist[p][d] -> first output position of digit d in pass p
-__global__ void __launch_bounds__(RADIX) radix_bases_kernel(uint32_t* __restrict__ hist) {
+__global__ void __launch_bounds__(MAX_RADIX) radix_bases_kernel(uint32_t* __restrict__ hist) {
+    constexpr int RADIX = MAX_RADIX;
     __shared__ uint32_t s[RADIX];
     uint32_t* h = hist + blockIdx.x * RADIX;
     const uint32_t v = h[threadIdx.x];
@@ -71,12 +76,14 @@ __global__ void __launch_bounds__(RADIX) radix_bases_kernel(uint32_t* __restrict
     h[threadIdx.x] = s[threadIdx.x] - v;
 }
 
-template <bool PAIRS>
+template <bool PAIRS, int RB>
 __global__ void __launch_bounds__(THREADS, 2)
 radix_onesweep_kernel(const unsigned long long* __restrict__ keys_in, unsigned long long* __restrict__ keys_out,
                       const uint32_t* __restrict__ vals_in, uint32_t* __restrict__ vals_out, uint32_t n, int shift, uint32_t mask,
-                      const uint32_t* __restrict__ bin_base /* [256] of this pass */, uint32_t* __restrict__ status /* [tiles][256] */,
+                      const uint32_t* __restrict__ bin_base /* [RADIX] of this pass */, uint32_t* __restrict__ status /* [tiles][RADIX] */,
                       uint32_t* __restrict__ ticket) {
+    constexpr int RADIX = 1 << RB;
+    static_assert(RADIX <= THREADS, "one look-back thread per digit");
     extern __shared__ __align__(16) uint8_t rs_smem[];
     unsigned long long* s_keys = reinterpret_cast<unsigned long long*>(rs_smem);                  // [TILE]
     uint32_t* s_vals = reinterpret_cast<uint32_t*>(rs_smem + (size_t)TILE * 8);                    // [TILE] (pairs only)
@@ -209,6 +216,7 @@ radix_onesweep_kernel(const unsigned long long* __restrict__ keys_in, unsigned l
     }
 }
 
+
 }  // namespace rs
 
 // exclusive scan of n counts in place by ONE CTA (tile counts: a 100 M-point cloud has 48 829 voxel-boundary tiles and
@@ -248,6 +256,48 @@ int exclusive_scan_u32(pb200_ctx* ctx, uint32_t* counts, uint32_t n, uint32_t* t
     return PB200_OK;
 }
 
+// digit plan for the bits [begin_bit, end_bit): 9-bit digits only when they save a pass
+static void plan_passes(const pb200_ctx* ctx, int begin_bit, int end_bit, rs::Passes* out, int* width) {
+    using namespace rs;
+    Passes& ps = *out;
+    const int bits = end_bit - begin_bit;
+    const int p8 = (bits + 7) / 8, p9 = (bits + 8) / 9;
+    const bool wide = p9 < p8 && !ctx->sort_force_8bit;
+    ps.n_passes = wide ? p9 : p8;
+    {   // spread the bits: the first passes are 9 bits wide as long as the rest still fills 8-bit passes, the last may be narrower
+        int left = bits;
+        for (int p = 0; p < ps.n_passes; ++p) {
+            int w = wide ? ((left - 8 * (ps.n_passes - p - 1)) >= 9 ? 9 : 8) : 8;
+            if (w > left) w = left;
+            width[p] = w;
+            left -= w;
+        }
+    }
+    for (int p = 0; p < MAX_PASSES; ++p) { ps.shift[p] = 0; ps.mask[p] = 0; }
+    for (int p = 0, sh = begin_bit; p < ps.n_passes; ++p) {
+        ps.shift[p] = sh;
+        ps.mask[p] = (1u << width[p]) - 1u;
+        sh += width[p];
+    }
+}
+
+// digit histograms of all passes of a sort over [begin_bit, end_bit), scanned into bin bases; layout [MAX_PASSES][MAX_RADIX]
+// followed by one ticket counter per pass.
+static int compute_hist(pb200_ctx* ctx, const unsigned long long* keys, uint64_t n, const rs::Passes& ps, DevTmp* d_hist) {
+    using namespace rs;
+    cudaStream_t st = ctx->stream;
+    const size_t hist_bytes = (size_t)MAX_PASSES * MAX_RADIX * 4 + (MAX_PASSES + 4) * 4;
+    PB_CUDA(d_hist->alloc(st, hist_bytes));
+    PB_CUDA(cudaMemsetAsync(d_hist->p, 0, hist_bytes, st));
+    unsigned long long hb = (n + 511) / 512, cap = (unsigned long long)ctx->sm_count * 4;
+    PB_PHASE(ctx, "sort.histogram");
+    radix_histogram_kernel<<<(unsigned)(hb < cap ? hb : cap), 512, 0, st>>>(keys, n, ps, (uint32_t*)d_hist->p);
+    radix_bases_kernel<<<ps.n_passes, MAX_RADIX, 0, st>>>((uint32_t*)d_hist->p);
+    g_launches += 2;
+    PB_CUDA(cudaGetLastError());
+    return PB200_OK;
+}
+
 // Sorts n keys by the bits [begin_bit, end_bit).  `keys` / `vals` are clobbered; the result ends up in (keys, vals) or in
 // (keys_alt, vals_alt): *in_alt tells which.  vals / vals_alt may be null (keys only).
 int radix_sort_u64(pb200_ctx* ctx, unsigned long long* keys, unsigned long long* keys_alt, uint32_t* vals, uint32_t* vals_alt,
@@ -259,49 +309,42 @@ int radix_sort_u64(pb200_ctx* ctx, unsigned long long* keys, unsigned long long*
     if (end_bit - begin_bit > 64 || begin_bit < 0 || end_bit > 64) return set_error(PB200_ERR_INVALID, "radix sort: bad bit range");
     cudaStream_t st = ctx->stream;
     Passes ps;
-    ps.n_passes = (end_bit - begin_bit + RADIX_BITS - 1) / RADIX_BITS;
-    for (int p = 0; p < MAX_PASSES; ++p) { ps.shift[p] = 0; ps.mask[p] = 0; }
-    for (int p = 0; p < ps.n_passes; ++p) {
-        ps.shift[p] = begin_bit + p * RADIX_BITS;
-        const int bits = end_bit - ps.shift[p] < RADIX_BITS ? end_bit - ps.shift[p] : RADIX_BITS;
-        ps.mask[p] = (1u << bits) - 1u;
-    }
+    int width[MAX_PASSES];
+    plan_passes(ctx, begin_bit, end_bit, &ps, width);
     const uint32_t n_tiles = (uint32_t)((n + TILE - 1) / TILE);
-    DevTmp d_hist, d_status;
-    const size_t hist_bytes = (size_t)MAX_PASSES * RADIX * 4 + MAX_PASSES * 4;  // histograms + one ticket per pass
-    const size_t status_bytes = (size_t)ps.n_passes * n_tiles * RADIX * 4;
-    PB_CUDA(d_hist.alloc(st, hist_bytes));
+    DevTmp d_hist_own, d_status;
+    DevTmp* d_hist = &d_hist_own;
+    PB_TRY(compute_hist(ctx, keys, n, ps, d_hist));
+    const size_t status_bytes = (size_t)ps.n_passes * n_tiles * MAX_RADIX * 4;
     PB_CUDA(d_status.alloc(st, status_bytes));
-    PB_CUDA(cudaMemsetAsync(d_hist.p, 0, hist_bytes, st));
     PB_CUDA(cudaMemsetAsync(d_status.p, 0, status_bytes, st));
-    uint32_t* hist = (uint32_t*)d_hist.p;
-    uint32_t* tickets = hist + MAX_PASSES * RADIX;
+    uint32_t* hist = (uint32_t*)d_hist->p;
+    uint32_t* tickets = hist + MAX_PASSES * MAX_RADIX;
     const bool pairs = vals != nullptr;
-    const size_t smem = (size_t)TILE * (pairs ? 12 : 8) + (size_t)WARPS * RADIX * 2 + (size_t)(2 * RADIX + WARPS + 4) * 4;
+    auto smem_for = [&](int rb) { return (size_t)TILE * (pairs ? 12 : 8) + (size_t)WARPS * (1 << rb) * 2 + (size_t)(2 * (1 << rb) + WARPS + 4) * 4; };
     bool* attr_set = ctx->sort_attr_set;
     if (!attr_set[pairs ? 1 : 0]) {
-        if (pairs) PB_CUDA(cudaFuncSetAttribute(radix_onesweep_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-        else PB_CUDA(cudaFuncSetAttribute(radix_onesweep_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        if (pairs) {
+            PB_CUDA(cudaFuncSetAttribute(radix_onesweep_kernel<true, 8>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_for(8)));
+            PB_CUDA(cudaFuncSetAttribute(radix_onesweep_kernel<true, 9>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_for(9)));
+        } else {
+            PB_CUDA(cudaFuncSetAttribute(radix_onesweep_kernel<false, 8>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_for(8)));
+            PB_CUDA(cudaFuncSetAttribute(radix_onesweep_kernel<false, 9>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_for(9)));
+        }
         attr_set[pairs ? 1 : 0] = true;
-    }
-    unsigned long long hb = (n + 511) / 512, cap = (unsigned long long)ctx->sm_count * 4;
-    {
-        PB_PHASE(ctx, "sort.histogram");
-        radix_histogram_kernel<<<(unsigned)(hb < cap ? hb : cap), 512, 0, st>>>(keys, n, ps, hist);
-        radix_bases_kernel<<<ps.n_passes, RADIX, 0, st>>>(hist);
-        g_launches += 2;
     }
     unsigned long long *src = keys, *dst = keys_alt;
     uint32_t *vsrc = vals, *vdst = vals_alt;
     for (int p = 0; p < ps.n_passes; ++p) {
-        uint32_t* status = (uint32_t*)d_status.p + (size_t)p * n_tiles * RADIX;
+        uint32_t* status = (uint32_t*)d_status.p + (size_t)p * n_tiles * MAX_RADIX;
         PB_PHASE(ctx, "sort.pass");
-        if (pairs)
-            radix_onesweep_kernel<true><<<n_tiles, THREADS, smem, st>>>(src, dst, vsrc, vdst, (uint32_t)n, ps.shift[p], ps.mask[p],
-                                                                        hist + p * RADIX, status, tickets + p);
-        else
-            radix_onesweep_kernel<false><<<n_tiles, THREADS, smem, st>>>(src, dst, nullptr, nullptr, (uint32_t)n, ps.shift[p], ps.mask[p],
-                                                                         hist + p * RADIX, status, tickets + p);
+        const int rb = width[p] > 8 ? 9 : 8;
+        const size_t smem = smem_for(rb);
+#define PB_SWEEP(P, RB) radix_onesweep_kernel<P, RB><<<n_tiles, THREADS, smem, st>>>(src, dst, vsrc, vdst, (uint32_t)n, ps.shift[p], ps.mask[p], \
+                                                                                  hist + p * MAX_RADIX, status, tickets + p)
+        if (pairs) { if (rb == 9) PB_SWEEP(true, 9); else PB_SWEEP(true, 8); }
+        else { if (rb == 9) PB_SWEEP(false, 9); else PB_SWEEP(false, 8); }
+#undef PB_SWEEP
         g_launches++;
         unsigned long long* t = src; src = dst; dst = t;
         uint32_t* tv = vsrc; vsrc = vdst; vdst = tv;
@@ -310,6 +353,7 @@ int radix_sort_u64(pb200_ctx* ctx, unsigned long long* keys, unsigned long long*
     *in_alt = (ps.n_passes & 1) != 0;
     return PB200_OK;
 }
+
 
 }  // namespace pb200
 

@@ -43,26 +43,32 @@ struct pb200_voxel_partials {
 namespace pb200 {
 
 struct AxisGrid {
-    const double* markers[3];
+    const double2* pairs[3];  // pairs[c][i] = (marker i-1 or 0.0, marker i): both neighbours of a candidate in ONE 16-byte load
     unsigned long long n[3];
     double bmin[3], inv_leaf[3];
     unsigned bits_y, bits_z;
 };
 
-__device__ __forceinline__ unsigned long long leaf_index(double p, const double* __restrict__ m, unsigned long long n,
+__device__ __forceinline__ unsigned long long leaf_index(double p, const double2* __restrict__ m, unsigned long long n,
                                                          double bmin, double inv_leaf) {
     if (n == 0) return 0;  // voxel_grid.rs:31 `!markers.is_empty()`
-    // first index with !(m[i] < p): guess from the regular spacing, then walk on the exact (running-sum) markers
-    // (the two markers around the candidate stay in registers while the walk slides: typically 3 loads per axis)
+    // The reference scans for the first index k with !(marker[k] < p) (clamped to the last marker), then steps back to the
+    // nearer marker.  Here: guess k from the regular spacing and fetch (marker[k-1], marker[k]) with one 16-byte load; the
+    // guess is accepted if the exact (running-sum) markers bracket p, which is the case except for rounding drift, NaN and
+    // the clamped ends -- only then walk like the reference.  Lookups of a warp scatter over the tables (x and y of a
+    // cloud are unrelated to the point order), so the kernel is bound by the L1 tag rate: one load per axis instead of
+    // three is what it is about.
     const double g = (p - bmin) * inv_leaf;
     const int last = (int)n - 1;  // n <= 2^21 + 1
-    int k = (g > 1.0) ? ((g < 4.0e6) ? (int)g - 1 : last) : 0;
+    int k = (g > 0.0) ? ((g < 4.0e6) ? (int)g : last) : 0;
     if (k > last) k = last;
-    double hi = m[k], lo = k > 0 ? m[k - 1] : 0.0;
-    while (k < last && hi < p) { ++k; lo = hi; hi = m[k]; }
-    while (k > 0 && !(lo < p)) { --k; hi = lo; lo = k > 0 ? m[k - 1] : 0.0; }
+    double2 lh = m[k];  // lo = marker[k-1] (0.0 for k = 0), hi = marker[k]
+    if (!((k == 0 || lh.x < p) && (k == last || !(lh.y < p)))) {
+        while (k < last && lh.y < p) lh = m[++k];
+        while (k > 0 && !(lh.x < p)) lh = m[--k];
+    }
     // clamp to the better fitting marker: [k] or [k-1] (voxel_grid.rs:41-49)
-    if (k > 0 && __dsub_rn(p, lo) < __dsub_rn(hi, p)) --k;
+    if (k > 0 && __dsub_rn(p, lh.x) < __dsub_rn(lh.y, p)) --k;
     return (unsigned long long)k;
 }
 
@@ -73,9 +79,9 @@ __global__ void __launch_bounds__(256) voxel_key_kernel(const uint8_t* __restric
     const unsigned long long step = (unsigned long long)gridDim.x * blockDim.x;
     for (unsigned long long i = (unsigned long long)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += step) {
         const double* p = reinterpret_cast<const double*>(pos_base + i * stride);
-        const unsigned long long ix = leaf_index(p[0], g.markers[0], g.n[0], g.bmin[0], g.inv_leaf[0]);
-        const unsigned long long iy = leaf_index(p[1], g.markers[1], g.n[1], g.bmin[1], g.inv_leaf[1]);
-        const unsigned long long iz = leaf_index(p[2], g.markers[2], g.n[2], g.bmin[2], g.inv_leaf[2]);
+        const unsigned long long ix = leaf_index(p[0], g.pairs[0], g.n[0], g.bmin[0], g.inv_leaf[0]);
+        const unsigned long long iy = leaf_index(p[1], g.pairs[1], g.n[1], g.bmin[1], g.inv_leaf[1]);
+        const unsigned long long iz = leaf_index(p[2], g.pairs[2], g.n[2], g.bmin[2], g.inv_leaf[2]);
         const unsigned long long key = (((ix << g.bits_y) | iy) << g.bits_z) | iz;
         if (idx_bits) keys[i] = (key << idx_bits) | i;
         else { keys[i] = key; idx[i] = (uint32_t)i; }
@@ -192,6 +198,131 @@ __device__ __forceinline__ void ld_gather_pos24(const uint8_t* p, double& x, dou
         x = ld_gather_f64(p);
         asm volatile("ld.global.nc.L2::64B.v2.f64 {%0, %1}, [%2];" : "=d"(y), "=d"(z) : "l"(p + 8));
     }
+}
+
+// ---- K8b + K9 fused: voxel boundaries AND the per-voxel position reduction in one pass over the sorted keys ----------
+// One CTA per tile of ER_TILE sorted keys (same striped ownership as the heads kernels).  Every THREAD gathers the
+// positions of its own ER_ROWS points -- ER_GB independent 24-byte gathers in flight per thread, all 256 threads busy: the
+// memory-level parallelism the thread-per-voxel kernel lacked (it walked its points one dependent gather at a time and sat
+// at 6 % issue utilisation) -- and parks them in shared memory.  Then the thread that owns a voxel's FIRST point adds the
+// voxel's points up from shared memory in sorted = input order, i.e. with exactly the roundings of the reference's
+// sequential loop (voxel_grid.rs:339-386).  A voxel that runs past the tile end is finished by its owner straight from
+// global memory (one thread per tile at most).  Writes centroids (OUT = 0) or sums + counts (OUT = 1, shard partials),
+// the voxel keys, and -- only when other attributes need them (EMIT_INDEX) -- segment starts and unpacked indices.
+constexpr int ER_THREADS = HT_THREADS, ER_ROWS = HT_ROWS, ER_TILE = HT_TILE, ER_GB = 4;
+constexpr size_t ER_SMEM = (size_t)ER_TILE * 24 + 64 * 4;
+
+template <int OUT, bool EMIT_INDEX>
+__global__ void __launch_bounds__(ER_THREADS, 3)
+voxel_emit_reduce_kernel(const unsigned long long* __restrict__ keys, unsigned long long n, unsigned shift,
+                         const uint32_t* __restrict__ tile_offsets, uint32_t n_voxels, const uint32_t* __restrict__ idx_in,
+                         const uint8_t* __restrict__ pos, unsigned long long pstride, uint32_t* __restrict__ starts, unsigned long long* __restrict__ voxel_keys, uint32_t* __restrict__ idx_out,
+                         double* __restrict__ out3, uint32_t* __restrict__ counts) {
+    extern __shared__ __align__(16) uint8_t er_smem[];
+    double* sx = reinterpret_cast<double*>(er_smem);
+    double* sy = sx + ER_TILE;
+    double* sz = sy + ER_TILE;
+    uint32_t* s_flags = reinterpret_cast<uint32_t*>(sz + ER_TILE);  // [64]: bit l of word r * 8 + w <-> element r * 256 + w * 32 + l
+    const uint32_t lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    const unsigned long long base = (unsigned long long)blockIdx.x * ER_TILE;
+    const uint32_t npts = (uint32_t)((n - base) < (unsigned long long)ER_TILE ? (n - base) : (unsigned long long)ER_TILE);
+    const unsigned long long idx_mask = shift ? ((1ull << shift) - 1ull) : 0ull;
+    unsigned long long k[ER_ROWS];
+    const uint32_t flags = tile_heads(keys, n, shift, base, k);
+    // per (row, warp) head counts: lane (r * 8 + w) & 31 of EVERY warp holds entry r * 8 + w (entries 0..31 in c0, 32..63 in c1)
+    uint32_t lane_rank[ER_ROWS];
+#pragma unroll
+    for (int r = 0; r < ER_ROWS; ++r) {
+        const uint32_t b = __ballot_sync(0xffffffffu, (flags >> r) & 1u);
+        lane_rank[r] = __popc(b & ((1u << lane) - 1u));
+        if (lane == 0) s_flags[r * 8 + warp] = b;
+    }
+    // gather this thread's points, ER_GB at a time, into shared memory (element e = r * 256 + t: conflict-free)
+#pragma unroll
+    for (int r0 = 0; r0 < ER_ROWS; r0 += ER_GB) {
+        double x[ER_GB], y[ER_GB], z[ER_GB];
+#pragma unroll
+        for (int g = 0; g < ER_GB; ++g) {
+            const int r = r0 + g;
+            const uint32_t e = (uint32_t)r * ER_THREADS + threadIdx.x;
+            x[g] = y[g] = z[g] = 0.0;
+            if (e < npts) {
+                const uint32_t j = shift ? (uint32_t)(k[r] & idx_mask) : idx_in[base + e];
+                if (EMIT_INDEX && shift) idx_out[base + e] = j;
+                ld_gather_pos24(pos + (unsigned long long)j * pstride, x[g], y[g], z[g]);
+            }
+        }
+#pragma unroll
+        for (int g = 0; g < ER_GB; ++g) {
+            const uint32_t e = (uint32_t)(r0 + g) * ER_THREADS + threadIdx.x;
+            sx[e] = x[g]; sy[e] = y[g]; sz[e] = z[g];
+        }
+    }
+    __syncthreads();
+    // exclusive scan of the 64 (row, warp) head counts, done by every warp for itself (two entries per lane)
+    const uint32_t c0 = __popc(s_flags[lane]), c1 = __popc(s_flags[lane + 32]);
+    uint32_t x0 = c0, x1 = c1;
+#pragma unroll
+    for (int o = 1; o < 32; o <<= 1) {
+        const uint32_t y0 = __shfl_up_sync(0xffffffffu, x0, o), y1 = __shfl_up_sync(0xffffffffu, x1, o);
+        if ((int)lane >= o) { x0 += y0; x1 += y1; }
+    }
+    const uint32_t first_half = __shfl_sync(0xffffffffu, x0, 31), tile_off = tile_offsets[blockIdx.x];
+    const uint32_t ex0 = tile_off + x0 - c0, ex1 = tile_off + first_half + x1 - c1;
+#pragma unroll
+    for (int r = 0; r < ER_ROWS; ++r) {
+        const uint32_t entry = (uint32_t)r * 8u + warp;  // warp-uniform
+        const uint32_t row_base = __shfl_sync(0xffffffffu, entry < 32u ? ex0 : ex1, entry & 31u);
+        if (!((flags >> r) & 1u)) continue;
+        const uint32_t e = (uint32_t)r * ER_THREADS + threadIdx.x;
+        // end of this voxel inside the tile: the next head bit after e, else the tile end
+        uint32_t end = npts;
+        {
+            const uint32_t j = e + 1u;
+            if (j < (uint32_t)ER_TILE) {
+                uint32_t w = j >> 5, m = s_flags[w] >> (j & 31u);
+                if (m) end = j + (uint32_t)__ffs((int)m) - 1u;
+                else {
+                    for (++w; w < 64u; ++w) {
+                        m = s_flags[w];
+                        if (m) { end = w * 32u + (uint32_t)__ffs((int)m) - 1u; break; }
+                    }
+                }
+            }
+            end = end < npts ? end : npts;
+        }
+        double ax = 0.0, ay = 0.0, az = 0.0;
+        for (uint32_t j = e; j < end; ++j) {
+            ax = __dadd_rn(ax, sx[j]);
+            ay = __dadd_rn(ay, sy[j]);
+            az = __dadd_rn(az, sz[j]);
+        }
+        unsigned long long cnt = end - e;
+        const unsigned long long vkey = k[r] >> shift;
+        if (end == npts) {  // the voxel may continue in the following tiles: finish it from global memory
+            for (unsigned long long g = base + npts; g < n; ++g, ++cnt) {
+                const unsigned long long kk = keys[g];
+                if ((kk >> shift) != vkey) break;
+                const uint32_t j = shift ? (uint32_t)(kk & idx_mask) : idx_in[g];
+                double px, py, pz;
+                ld_gather_pos24(pos + (unsigned long long)j * pstride, px, py, pz);
+                ax = __dadd_rn(ax, px);
+                ay = __dadd_rn(ay, py);
+                az = __dadd_rn(az, pz);
+            }
+        }
+        const uint32_t rank = row_base + lane_rank[r];
+        voxel_keys[rank] = vkey;
+        if (EMIT_INDEX) starts[rank] = (uint32_t)(base + e);
+        if (OUT == 0) {  // voxel_grid.rs:382-386
+            const double c = (double)cnt;
+            out3[3 * (size_t)rank] = ax / c; out3[3 * (size_t)rank + 1] = ay / c; out3[3 * (size_t)rank + 2] = az / c;
+        } else if (OUT == 1) {
+            out3[3 * (size_t)rank] = ax; out3[3 * (size_t)rank + 1] = ay; out3[3 * (size_t)rank + 2] = az;
+            counts[rank] = (uint32_t)cnt;
+        }
+    }
+    if (EMIT_INDEX && blockIdx.x == 0 && threadIdx.x == 0) starts[n_voxels] = (uint32_t)n;
 }
 
 __device__ __forceinline__ unsigned long long f64_as_u64_sat(double v) {  // Rust `as u64`
@@ -396,24 +527,6 @@ static unsigned bits_for(unsigned long long count) {  // bits needed for indices
 }
 
 // ---- sharded voxel grid: partial sums per shard, merge of exchanged partials ------------------------
-// per voxel of one shard: point count and position sums in point order (the division happens after the merge)
-__global__ void __launch_bounds__(128) voxel_partial_sums_kernel(const uint32_t* __restrict__ starts, const uint32_t* __restrict__ sorted_idx,
-                                                                 unsigned long long n_voxels, const uint8_t* __restrict__ pos,
-                                                                 unsigned long long stride, uint32_t* __restrict__ counts,
-                                                                 double* __restrict__ sums) {
-    const unsigned long long v = (unsigned long long)blockIdx.x * blockDim.x + threadIdx.x;
-    if (v >= n_voxels) return;
-    const uint32_t b = starts[v], e = starts[v + 1];
-    double sx = 0.0, sy = 0.0, sz = 0.0;
-    for (uint32_t k = b; k < e; ++k) {
-        double x, y, z;
-        ld_gather_pos24(pos + (unsigned long long)sorted_idx[k] * stride, x, y, z);
-        sx = __dadd_rn(sx, x); sy = __dadd_rn(sy, y); sz = __dadd_rn(sz, z);
-    }
-    counts[v] = e - b;
-    sums[3 * v] = sx; sums[3 * v + 1] = sy; sums[3 * v + 2] = sz;
-}
-
 __global__ void __launch_bounds__(256) iota_kernel(uint32_t* __restrict__ out, unsigned long long n) {
     const unsigned long long step = (unsigned long long)gridDim.x * blockDim.x;
     for (unsigned long long i = (unsigned long long)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += step) out[i] = (uint32_t)i;
@@ -451,14 +564,19 @@ __global__ void __launch_bounds__(256) partials_centroid_kernel(const uint32_t* 
 // voxel boundaries.  With the AABB of the WHOLE cloud every shard of a sharded cloud derives the same markers and
 // therefore the same global voxel keys.
 struct VoxelIndex {
-    DevTmp sorted_keys, sorted_idx, starts, voxel_keys;  // N, N, V+1, V
-    uint64_t V = 0;
-    unsigned bits_x = 0, bits_y = 0, bits_z = 0;
+    DevTmp sorted_keys, sorted_idx, starts, voxel_keys, tiles;  // N, N, V+1, V, tiles+1
+    uint64_t V = 0, n = 0;
+    unsigned bits_x = 0, bits_y = 0, bits_z = 0, shift = 0;
+    bool packed = false;
+    uint32_t n_tiles = 0;
     uint64_t cells[3] = {0, 0, 0};
+    const uint8_t* ppos = nullptr;  // positions the sorted indices refer to
+    uint64_t pstride = 0;
 };
 
-static int build_voxel_index(pb200_ctx* ctx, const uint8_t* ppos, uint64_t pstride, uint64_t n, const double bmin[3],
-                             const double bmax[3], const double leaf[3], VoxelIndex* vi) {
+// Step 1: markers on the host (voxel_grid.rs:63-77), keys, sort, heads per tile + scan -> V is known on the host.
+static int voxel_index_sort(pb200_ctx* ctx, const uint8_t* ppos, uint64_t pstride, uint64_t n, const double bmin[3],
+                            const double bmax[3], const double leaf[3], VoxelIndex* vi) {
     cudaStream_t st = ctx->stream;
     std::vector<double> markers[3];
     for (int c = 0; c < 3; ++c) {  // voxel_grid.rs:63-77 running sum
@@ -471,21 +589,33 @@ static int build_voxel_index(pb200_ctx* ctx, const uint8_t* ppos, uint64_t pstri
     }
     const unsigned bits_x = bits_for(markers[0].size()), bits_y = bits_for(markers[1].size()), bits_z = bits_for(markers[2].size());
     vi->bits_x = bits_x; vi->bits_y = bits_y; vi->bits_z = bits_z;
+    vi->n = n; vi->ppos = ppos; vi->pstride = pstride;
     for (int c = 0; c < 3; ++c) vi->cells[c] = markers[c].size();
     DevTmp d_markers;
     const size_t nm_total = markers[0].size() + markers[1].size() + markers[2].size();
-    PB_CUDA(d_markers.alloc(st, nm_total * sizeof(double) + 8));
+    PB_CUDA(d_markers.alloc(st, (nm_total + 1) * sizeof(double2)));
     AxisGrid grid;
     {
+        PB_PHASE(ctx, "host.markers_upload");
+        // (marker[i-1], marker[i]) pairs, staged in pinned memory when they fit (a pageable source would be copied
+        // synchronously through the driver's own staging buffer)
+        std::vector<double2> pairs_host;
+        double2* hp = nullptr;
+        if ((nm_total + 1) * sizeof(double2) <= ctx->h_stage_bytes) hp = (double2*)ctx->h_stage;
+        else { pairs_host.resize(nm_total + 1); hp = pairs_host.data(); }
         size_t off = 0;
         for (int c = 0; c < 3; ++c) {
-            grid.markers[c] = (const double*)d_markers.p + off;
+            grid.pairs[c] = (const double2*)d_markers.p + off;
             grid.n[c] = markers[c].size();
             grid.bmin[c] = bmin[c];
             grid.inv_leaf[c] = 1.0 / leaf[c];
-            if (!markers[c].empty())
-                PB_CUDA(cudaMemcpyAsync((double*)d_markers.p + off, markers[c].data(), markers[c].size() * sizeof(double), cudaMemcpyHostToDevice, st));
+            for (size_t i = 0; i < markers[c].size(); ++i) hp[off + i] = make_double2(i ? markers[c][i - 1] : 0.0, markers[c][i]);
             off += markers[c].size();
+        }
+        if (nm_total) {
+            // (h_stage is free: every call that uploads from it synchronises on its voxel count further down)
+            PB_CUDA(cudaMemcpyAsync(d_markers.p, hp, nm_total * sizeof(double2), cudaMemcpyHostToDevice, st));
+            if (hp != (double2*)ctx->h_stage) PB_CUDA(cudaStreamSynchronize(st));  // pairs_host dies with this scope
         }
         grid.bits_y = bits_y;
         grid.bits_z = bits_z;
@@ -496,11 +626,14 @@ static int build_voxel_index(pb200_ctx* ctx, const uint8_t* ppos, uint64_t pstri
     const unsigned key_bits = bits_x + bits_y + bits_z, idx_bits_needed = bits_for(n);
     const bool packed = key_bits + idx_bits_needed <= 64;
     const unsigned shift = packed ? idx_bits_needed : 0;
-    DevTmp d_keys, d_idx, d_tmp, d_tiles;
-    DevTmp &d_keys2 = vi->sorted_keys, &d_idx2 = vi->sorted_idx;
-    PB_CUDA(d_keys.alloc(st, n * 8)); PB_CUDA(d_keys2.alloc(st, n * 8));
-    PB_CUDA(d_idx2.alloc(st, n * 4));
-    if (!packed) PB_CUDA(d_idx.alloc(st, n * 4));
+    vi->packed = packed; vi->shift = shift;
+    DevTmp d_keys, d_idx, d_tmp;
+    DevTmp &d_keys2 = vi->sorted_keys, &d_idx2 = vi->sorted_idx, &d_tiles = vi->tiles;
+    {
+        PB_PHASE(ctx, "host.alloc_keys");
+        PB_CUDA(d_keys.alloc(st, n * 8)); PB_CUDA(d_keys2.alloc(st, n * 8));
+        if (!packed) { PB_CUDA(d_idx.alloc(st, n * 4)); PB_CUDA(d_idx2.alloc(st, n * 4)); }
+    }
     if (((uintptr_t)ppos & 7) || (pstride & 7)) return set_error(PB200_ERR_UNSUPPORTED, "POSITION_3D must be 8-byte aligned in memory");
     const unsigned long long cap = (unsigned long long)ctx->sm_count * 16;
     const unsigned blocks = (unsigned)(((n + 255) / 256) < cap ? ((n + 255) / 256) : cap);
@@ -535,8 +668,9 @@ static int build_voxel_index(pb200_ctx* ctx, const uint8_t* ppos, uint64_t pstri
         }
         g_launches += (uint64_t)((key_bits + 7) / 8) + 1;
     }
-    // voxel boundaries: heads per tile -> scan -> emit
+    // voxel boundaries: heads per tile -> scan (the emit step follows once V is known on the host)
     const uint32_t n_tiles = (uint32_t)((n + HT_TILE - 1) / HT_TILE);
+    vi->n_tiles = n_tiles;
     PB_CUDA(d_tiles.alloc(st, ((size_t)n_tiles + 1) * 4));
     uint32_t* d_total = (uint32_t*)d_tiles.p + n_tiles;
     {
@@ -546,20 +680,55 @@ static int build_voxel_index(pb200_ctx* ctx, const uint8_t* ppos, uint64_t pstri
         g_launches += 2;
     }
     uint32_t* h_total = (uint32_t*)ctx->h_scratch;
-    PB_CUDA(cudaMemcpyAsync(h_total, d_total, 4, cudaMemcpyDeviceToHost, st));
-    PB_CUDA(cudaStreamSynchronize(st));
-    const uint64_t V = *h_total;
-    vi->V = V;
-    DevTmp &d_starts = vi->starts, &d_vkeys = vi->voxel_keys;
-    PB_CUDA(d_starts.alloc(st, (V + 1) * 4));
-    PB_CUDA(d_vkeys.alloc(st, V * 8 + 8));
     {
-        PB_PHASE(ctx, "voxel.heads_emit");
-        heads_emit_kernel<<<n_tiles, HT_THREADS, 0, st>>>((const unsigned long long*)d_keys2.p, n, shift, (const uint32_t*)d_tiles.p, (uint32_t)V,
-                                                          (uint32_t*)d_starts.p, (unsigned long long*)d_vkeys.p, packed ? (uint32_t*)d_idx2.p : nullptr);
-        g_launches++;
+        PB_PHASE(ctx, "host.sync_voxel_count");
+        PB_CUDA(cudaMemcpyAsync(h_total, d_total, 4, cudaMemcpyDeviceToHost, st));
+        PB_CUDA(cudaStreamSynchronize(st));
     }
+    vi->V = *h_total;
+    return PB200_OK;
+}
 
+// Step 2: voxel keys (always), the per-voxel position reduction fused into the same pass (out_kind 0: centroids into
+// out3 = V x 3 doubles; 1: sums into out3 + counts; 2: none), and -- if other attributes are reduced afterwards
+// (need_index) -- segment starts and the unpacked sorted point indices.
+static int voxel_index_emit(pb200_ctx* ctx, VoxelIndex* vi, int out_kind, double* out3, uint32_t* counts, bool need_index) {
+    cudaStream_t st = ctx->stream;
+    const uint64_t V = vi->V, n = vi->n;
+    if (out_kind == 2) need_index = true;  // boundaries only: the caller wants starts / indices, nothing else comes out
+    PB_CUDA(vi->voxel_keys.alloc(st, V * 8 + 8));
+    if (need_index) {
+        PB_CUDA(vi->starts.alloc(st, (V + 1) * 4));
+        if (vi->packed) PB_CUDA(vi->sorted_idx.alloc(st, n * 4));
+    }
+    const unsigned long long* keys = (const unsigned long long*)vi->sorted_keys.p;
+    const uint32_t* tiles = (const uint32_t*)vi->tiles.p;
+    uint32_t* starts = (uint32_t*)vi->starts.p;
+    unsigned long long* vkeys = (unsigned long long*)vi->voxel_keys.p;
+    uint32_t* idx_out = vi->packed ? (uint32_t*)vi->sorted_idx.p : nullptr;
+    const uint32_t* idx_in = vi->packed ? nullptr : (const uint32_t*)vi->sorted_idx.p;
+    if (out_kind == 2) {
+        PB_PHASE(ctx, "voxel.heads_emit");
+        heads_emit_kernel<<<vi->n_tiles, HT_THREADS, 0, st>>>(keys, n, vi->shift, tiles, (uint32_t)V, starts, vkeys, need_index ? idx_out : nullptr);
+        g_launches++;
+        PB_CUDA(cudaGetLastError());
+        return PB200_OK;
+    }
+    if (!ctx->voxel_attr_set) {
+        PB_CUDA(cudaFuncSetAttribute(voxel_emit_reduce_kernel<0, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)ER_SMEM));
+        PB_CUDA(cudaFuncSetAttribute(voxel_emit_reduce_kernel<0, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)ER_SMEM));
+        PB_CUDA(cudaFuncSetAttribute(voxel_emit_reduce_kernel<1, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)ER_SMEM));
+        PB_CUDA(cudaFuncSetAttribute(voxel_emit_reduce_kernel<1, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)ER_SMEM));
+        ctx->voxel_attr_set = true;
+    }
+    PB_PHASE(ctx, "voxel.emit+reduce");
+#define PB_ER_LAUNCH(O, E)                                                                                                        \
+    voxel_emit_reduce_kernel<O, E><<<vi->n_tiles, ER_THREADS, ER_SMEM, st>>>(keys, n, vi->shift, tiles, (uint32_t)V, idx_in, vi->ppos, \
+                                                                            vi->pstride, starts, vkeys, idx_out, out3, counts)
+    if (out_kind == 0) { if (need_index) PB_ER_LAUNCH(0, true); else PB_ER_LAUNCH(0, false); }
+    else { if (need_index) PB_ER_LAUNCH(1, true); else PB_ER_LAUNCH(1, false); }
+#undef PB_ER_LAUNCH
+    g_launches++;
     PB_CUDA(cudaGetLastError());
     return PB200_OK;
 }
@@ -603,6 +772,7 @@ int pb200_voxelgrid_filter(pb200_ctx* ctx, const pb200_buffer_desc* src, double 
     }
     const uint64_t n = src->len;
     cudaStream_t st = ctx->stream;
+    PB_PHASE(ctx, "voxel.call");
 
     // ---- source attribute streams on the device --------------------------------------------------------------
     std::vector<DevTmp> staged(src->layout->attrs.size() + 1);
@@ -650,10 +820,40 @@ int pb200_voxelgrid_filter(pb200_ctx* ctx, const pb200_buffer_desc* src, double 
     if (!some) return set_error(PB200_ERR_INVALID, "calculate_bounds returned None");
     uint64_t pstride = 0;
     const uint8_t* ppos = attr_ptr(pi, &pstride);
+    // the Position3D centroid is reduced inside the boundary pass (voxel_emit_reduce_kernel); segment starts and sorted
+    // indices are only materialised when other attributes are reduced afterwards
+    int a_pos = -1;
+    for (size_t a = 0; a < rules.size(); ++a)
+        if (rules[a]->kind == R_MEAN_VEC_F64) a_pos = (int)a;
+    const bool need_index = rules.size() > (a_pos >= 0 ? 1u : 0u);
     VoxelIndex vi;
-    PB_TRY(build_voxel_index(ctx, ppos, pstride, n, bmin, bmax, leaf, &vi));
+    PB_TRY(voxel_index_sort(ctx, ppos, pstride, n, bmin, bmax, leaf, &vi));
     const uint64_t V = vi.V;
     const unsigned bits_y = vi.bits_y, bits_z = vi.bits_z;
+    pb200_result_buffer* res = new pb200_result_buffer();
+    res->ctx = ctx;
+    res->layout = *dst_layout;
+    res->kind = dst_kind;
+    res->memspace = dst_memspace;
+    res->len = V;
+    std::vector<void*> d_out(dst_layout->attrs.size(), nullptr);
+    auto fail = [&](int rc) {
+        for (void* p : d_out) if (p) cache_free(ctx, p);
+        if (res->d_packed_keys) cache_free(ctx, res->d_packed_keys);
+        delete res;
+        return rc;
+    };
+    {
+        PB_PHASE(ctx, "host.alloc_result");
+        for (size_t a = 0; a < dst_layout->attrs.size(); ++a) {
+            cudaError_t e = cache_alloc(ctx, &d_out[a], (size_t)(V * dst_layout->attrs[a].size) + 16);
+            if (e != cudaSuccess) return fail(cuda_error(e, "result column allocation"));
+        }
+    }
+    {
+        int rc = voxel_index_emit(ctx, &vi, a_pos >= 0 ? 0 : 2, a_pos >= 0 ? (double*)d_out[(size_t)a_pos] : nullptr, nullptr, need_index);
+        if (rc < 0) return fail(rc);
+    }
     DevTmp &d_idx2 = vi.sorted_idx, &d_starts = vi.starts, &d_vkeys = vi.voxel_keys;
     const unsigned long long cap = (unsigned long long)ctx->sm_count * 16;
     const unsigned blocks = (unsigned)(((n + 255) / 256) < cap ? ((n + 255) / 256) : cap);
@@ -665,36 +865,23 @@ int pb200_voxelgrid_filter(pb200_ctx* ctx, const pb200_buffer_desc* src, double 
     uint32_t max_occ = 0;
     DevTmp d_mode_keys, d_mode_keys2, d_best, d_occ;
     if (any_mode) {
-        PB_CUDA(d_occ.alloc(st, 4));
-        PB_CUDA(cudaMemsetAsync(d_occ.p, 0, 4, st));
+        if (d_occ.alloc(st, 4) != cudaSuccess) return fail(set_error(PB200_ERR_OOM, "out of device memory"));
+        cudaMemsetAsync(d_occ.p, 0, 4, st);
         max_occupancy_kernel<<<blocks, 256, 0, st>>>((const uint32_t*)d_starts.p, V, (uint32_t*)d_occ.p);
         g_launches++;
-        PB_CUDA(cudaMemcpyAsync(h_total, d_occ.p, 4, cudaMemcpyDeviceToHost, st));
-        PB_CUDA(cudaStreamSynchronize(st));
+        cudaMemcpyAsync(h_total, d_occ.p, 4, cudaMemcpyDeviceToHost, st);
+        if (cudaStreamSynchronize(st) != cudaSuccess) return fail(cuda_error(cudaGetLastError(), "max occupancy"));
         max_occ = *h_total;
         if (max_occ > MODE_THREAD_LIMIT) {
-            PB_CUDA(d_mode_keys.alloc(st, n * 8)); PB_CUDA(d_mode_keys2.alloc(st, n * 8));
-            PB_CUDA(d_best.alloc(st, (V + 1) * 8));
+            if (d_mode_keys.alloc(st, n * 8) != cudaSuccess || d_mode_keys2.alloc(st, n * 8) != cudaSuccess ||
+                d_best.alloc(st, (V + 1) * 8) != cudaSuccess)
+                return fail(set_error(PB200_ERR_OOM, "out of device memory"));
         }
     }
 
     // ---- per-attribute reductions into a columnar staging result -----------------------------------------------
-    pb200_result_buffer* res = new pb200_result_buffer();
-    res->ctx = ctx;
-    res->layout = *dst_layout;
-    res->kind = dst_kind;
-    res->memspace = dst_memspace;
-    res->len = V;
-    std::vector<void*> d_out(dst_layout->attrs.size(), nullptr);
-    auto fail = [&](int rc) {
-        for (void* p : d_out) if (p) cudaFreeAsync(p, st);
-        if (res->d_packed_keys) cudaFreeAsync(res->d_packed_keys, st);
-        delete res;
-        return rc;
-    };
     for (size_t a = 0; a < dst_layout->attrs.size(); ++a) {
-        cudaError_t e = cudaMallocAsync(&d_out[a], (size_t)(V * dst_layout->attrs[a].size) + 16, st);
-        if (e != cudaSuccess) return fail(cuda_error(e, "cudaMallocAsync(result column)"));
+        if ((int)a == a_pos) continue;  // done by the fused boundary pass
         ReduceArgs ra;
         uint64_t sstride = 0;
         ra.src = attr_ptr(src_idx[a], &sstride);
@@ -758,7 +945,7 @@ int pb200_voxelgrid_filter(pb200_ctx* ctx, const pb200_buffer_desc* src, double 
     // allocate the final storage
     if (dst_kind == PB200_INTERLEAVED) {
         const size_t bytes = (size_t)(V * dst_layout->size) + 16;
-        if (dst_memspace == PB200_DEVICE) { if (cudaMallocAsync(&res->aos, bytes, st) != cudaSuccess) return fail(set_error(PB200_ERR_OOM, "out of device memory")); cudaMemsetAsync(res->aos, 0, bytes, st); }
+        if (dst_memspace == PB200_DEVICE) { if (cache_alloc(ctx, &res->aos, bytes) != cudaSuccess) return fail(set_error(PB200_ERR_OOM, "out of device memory")); cudaMemsetAsync(res->aos, 0, bytes, st); }
         else { res->aos = calloc(1, bytes); if (!res->aos) return fail(set_error(PB200_ERR_OOM, "out of host memory")); }
     } else {
         res->columns.assign(dst_layout->attrs.size(), nullptr);
@@ -782,7 +969,7 @@ int pb200_voxelgrid_filter(pb200_ctx* ctx, const pb200_buffer_desc* src, double 
         pb200_converter_destroy(cv);
         cudaStreamSynchronize(st);
     }
-    for (void* p : d_out) if (p) cudaFreeAsync(p, st);
+    for (void* p : d_out) if (p) cache_free(ctx, p);
     if (rc < 0) {
         std::fill(d_out.begin(), d_out.end(), nullptr);
         pb200_result_buffer_destroy(res);
@@ -844,20 +1031,17 @@ int pb200_voxelgrid_partials(pb200_ctx* ctx, const pb200_buffer_desc* src, doubl
     int rc = voxel_positions(ctx, src, &staged, &ppos, &pstride);
     if (rc < 0) return fail(rc);
     VoxelIndex vi;
-    rc = build_voxel_index(ctx, ppos, pstride, src->len, global_min, global_max, leaf, &vi);
+    rc = voxel_index_sort(ctx, ppos, pstride, src->len, global_min, global_max, leaf, &vi);
     if (rc < 0) return fail(rc);
     res->len = vi.V;
     res->bits_x = vi.bits_x; res->bits_y = vi.bits_y; res->bits_z = vi.bits_z;
     for (int c = 0; c < 3; ++c) res->cells[c] = vi.cells[c];
+    if (cache_alloc(ctx, &res->counts, vi.V * 4 + 4) != cudaSuccess || cache_alloc(ctx, &res->sums, vi.V * 24 + 8) != cudaSuccess)
+        return fail(set_error(PB200_ERR_OOM, "out of device memory"));
+    rc = voxel_index_emit(ctx, &vi, 1, (double*)res->sums, (uint32_t*)res->counts, false);  // keys + per-voxel sums and counts
+    if (rc < 0) return fail(rc);
     res->keys = vi.voxel_keys.p;
     vi.voxel_keys.p = nullptr;  // ownership moves to the result
-    if (cudaMallocAsync(&res->counts, vi.V * 4 + 4, st) != cudaSuccess || cudaMallocAsync(&res->sums, vi.V * 24 + 8, st) != cudaSuccess)
-        return fail(set_error(PB200_ERR_OOM, "out of device memory"));
-    voxel_partial_sums_kernel<<<(unsigned)((vi.V + 127) / 128), 128, 0, st>>>((const uint32_t*)vi.starts.p, (const uint32_t*)vi.sorted_idx.p, vi.V,
-                                                                           ppos, pstride, (uint32_t*)res->counts, (double*)res->sums);
-    g_launches++;
-    cudaError_t e = cudaGetLastError();
-    if (e != cudaSuccess) return fail(cuda_error(e, "voxel partial sums"));
     if (src->memspace == PB200_HOST) cudaStreamSynchronize(st);
     *out = res;
     return PB200_OK;
@@ -901,9 +1085,9 @@ int pb200_voxelgrid_merge_partials(pb200_ctx* ctx, const uint64_t* keys, const u
         const uint64_t V = *h_total;
         res->len = V;
         PB_CUDA(d_starts.alloc(st, (V + 1) * 4));
-        PB_CUDA(cudaMallocAsync(&res->keys, V * 8 + 8, st));
-        PB_CUDA(cudaMallocAsync(&res->counts, V * 4 + 4, st));
-        PB_CUDA(cudaMallocAsync(&res->sums, V * 24 + 8, st));
+        PB_CUDA(cache_alloc(ctx, &res->keys, V * 8 + 8));
+        PB_CUDA(cache_alloc(ctx, &res->counts, V * 4 + 4));
+        PB_CUDA(cache_alloc(ctx, &res->sums, V * 24 + 8));
         heads_emit_kernel<<<n_tiles, HT_THREADS, 0, st>>>((const unsigned long long*)d_keys2.p, m, 0u, (const uint32_t*)d_tiles.p, (uint32_t)V,
                                                           (uint32_t*)d_starts.p, (unsigned long long*)res->keys, nullptr);
         partials_merge_kernel<<<(unsigned)((V + 127) / 128), 128, 0, st>>>((const uint32_t*)d_starts.p, (const uint32_t*)d_idx2.p, V, counts, sums,
@@ -945,9 +1129,7 @@ void pb200_voxel_partials_destroy(pb200_voxel_partials* p) {
     if (!p) return;
     if (p->ctx) cudaSetDevice(p->ctx->device);
     cudaStream_t st = p->ctx ? p->ctx->stream : nullptr;
-    if (p->keys) cudaFreeAsync(p->keys, st);
-    if (p->counts) cudaFreeAsync(p->counts, st);
-    if (p->sums) cudaFreeAsync(p->sums, st);
+    if (p->ctx) { cache_free(p->ctx, p->keys); cache_free(p->ctx, p->counts); cache_free(p->ctx, p->sums); }
     delete p;
 }
 
@@ -982,10 +1164,9 @@ void pb200_result_buffer_destroy(pb200_result_buffer* r) {
     if (!r) return;
     if (r->ctx) cudaSetDevice(r->ctx->device);
     cudaStream_t st = r->ctx ? r->ctx->stream : nullptr;  // device memory goes back to the pool behind queued work
-    if (r->d_packed_keys) cudaFreeAsync(r->d_packed_keys, st);
+    if (r->d_packed_keys && r->ctx) cache_free(r->ctx, r->d_packed_keys);
     if (r->memspace == PB200_DEVICE) {
-        if (r->aos) cudaFreeAsync(r->aos, st);
-        for (void* p : r->columns) if (p) cudaFreeAsync(p, st);
+        if (r->ctx) { cache_free(r->ctx, r->aos); for (void* p : r->columns) cache_free(r->ctx, p); }
     } else {
         free(r->aos);
         for (void* p : r->columns) free(p);

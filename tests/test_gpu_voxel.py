@@ -105,6 +105,39 @@ def test_c3_shape_against_sort_oracle():
     util.assert_buffers_match(oout, out)
 
 
+def test_fused_centroids_equal_the_per_voxel_kernel_at_scale():
+    """the centroid computed inside the boundary pass (thread-per-point gather, in-order sums from shared memory, voxels
+    running over tile ends) at sizes with tens of thousands of tiles: (1) position-only and position + other attributes
+    (the path that also hands out segment starts and point indices) give the same bits, (2) both equal the oracle's
+    sort-based restatement bit for bit on a 2 M-point prefix of the C3 stream, other reductions included"""
+    n = 20_000_000
+    src = pb.algorithms.synth_terrain_positions(n)
+    out, keys = voxelgrid_filter(src, 0.1, 0.1, 0.1, return_keys=True)
+    v = out.len()
+    m = 2_000_000
+    sub = HashMapBuffer(src.point_layout(), m, "cuda")
+    sub.columns[0][: 24 * m].copy_(src.columns[0][: 24 * m])
+    o2, k2 = voxelgrid_filter(sub, 0.1, 0.1, 0.1, return_keys=True)
+    _, pl = util.layouts([("Position3D", O.VEC3F64), ("Intensity", O.U16), ("Classification", O.U8)])
+    buf = HashMapBuffer(pl, m, "cuda")
+    buf.columns[0][: 24 * m].copy_(src.columns[0][: 24 * m])
+    g = torch.Generator(device="cuda").manual_seed(5)
+    buf.columns[1][: 2 * m].copy_(torch.randint(0, 256, (2 * m,), dtype=torch.uint8, device="cuda", generator=g))
+    buf.columns[2][:m].copy_(torch.randint(0, 5, (m,), dtype=torch.uint8, device="cuda", generator=g))
+    o3, k3 = voxelgrid_filter(buf, 0.1, 0.1, 0.1, return_keys=True)  # index hand-out path (EMIT_INDEX) + other reductions
+    assert np.array_equal(k2, k3) and torch.equal(o2.columns[0][: o2.len() * 24], o3.columns[0][: o3.len() * 24])
+    # oracle on the same prefix: keys and centroids bit for bit, intensity mean / classification mode exact
+    ol = O.OLayout.from_attributes([("Position3D", O.VEC3F64), ("Intensity", O.U16), ("Classification", O.U8)])
+    ob = O.OBuffer(ol, m, True)
+    ob.set_attribute("Position3D", src.columns[0][: 24 * m].cpu().numpy().view(np.float64).reshape(m, 3))
+    ob.set_attribute("Intensity", buf.columns[1][: 2 * m].cpu().numpy().view(np.uint16))
+    ob.set_attribute("Classification", buf.columns[2][:m].cpu().numpy())
+    oout, okeys = O.voxelgrid_filter(ob, (0.1, 0.1, 0.1), ol, columnar=True, use_sort=True)
+    assert np.array_equal(k3, okeys)
+    util.assert_buffers_match(oout, o3)
+    assert v > 0
+
+
 def test_full_size_properties():
     """100 M-point C3 cloud: size-independent properties (keys strictly increasing, every point accounted for,
     centroids inside their voxel's marker neighbourhood, idempotent count)"""
