@@ -6,7 +6,7 @@
 //                               one global atomic per bin and CTA); a tiny kernel turns them into bin bases
 //   2. radix_onesweep_kernel    per pass.  A CTA takes the next tile (ticket counter: tiles are claimed in order, so a
 //                               CTA only ever waits for tiles that are already running), ranks its 8192 keys by digit
-//                               (warp match-any + warp-private digit counters, stable), publishes the tile's digit
+//                               (per-bit ballots + warp-private digit counters, stable), publishes the tile's digit
 //                               counts, resolves its global offsets by DECOUPLED LOOK-BACK over the preceding tiles
 //                               (one thread per digit; flag and value share one 32-bit word, so a single relaxed load
 //                               is a consistent snapshot), reorders the tile in shared memory and writes each digit's
@@ -76,6 +76,22 @@ __global__ void __launch_bounds__(MAX_RADIX) radix_bases_kernel(uint32_t* __rest
     h[threadIdx.x] = s[threadIdx.x] - v;
 }
 
+// Lanes of the warp that hold the same digit.  MATCH.ANY does this in one instruction, but its throughput on B200 is one
+// warp-instruction per ~58 cycles and SM for 8-bit digits (benchmarks/match_probe.cu: 0.65 ms per 100 M keys over the
+// whole chip) -- exactly the time of a one-sweep pass, which made the sort MATCH-bound.  One ballot per digit bit and an
+// AND of the matching halves gives the same mask 2.2x faster (0.30 ms per 100 M keys) on the regular pipes.
+template <int RB>
+__device__ __forceinline__ uint32_t digit_peers(uint32_t d) {
+    uint32_t peers = 0xffffffffu;
+#pragma unroll
+    for (int b = 0; b < RB; ++b) {
+        const bool bit = (d >> b) & 1u;
+        const uint32_t v = __ballot_sync(0xffffffffu, bit);
+        peers &= bit ? v : ~v;
+    }
+    return peers;
+}
+
 template <bool PAIRS, int RB>
 __global__ void __launch_bounds__(THREADS, 2)
 radix_onesweep_kernel(const unsigned long long* __restrict__ keys_in, unsigned long long* __restrict__ keys_out,
@@ -112,11 +128,13 @@ radix_onesweep_kernel(const unsigned long long* __restrict__ keys_in, unsigned l
     // stable ranking inside the warp's chunk: rank = (same-digit keys of earlier rows of this warp) + (same-digit lanes
     // below me in this row).  The row's leader (lowest peer lane) bumps the warp-private counter -- two 16-bit counters
     // share a 32-bit word so that a plain 32-bit shared atomic serves both -- and broadcasts the old value.
+    // (Plain load / leader store / __syncwarp instead of the atomic + shuffle was tried: it cost registers -- 100-240 bytes
+    // of spills at the 64-register budget of two CTAs per SM -- and was 3 % (keys) to 14 % (pairs) slower.)
     uint16_t* my_cnt = s_cnt + warp * RADIX;
     uint32_t* my_cnt32 = reinterpret_cast<uint32_t*>(my_cnt);
     const uint32_t lt_mask = (1u << lane) - 1u;
-    // MATCH.ANY has a long latency: GROUP rows are matched back to back (independent), then their counters are bumped in
-    // row order (shared atomics of one warp on one address execute in program order, which keeps the ranking stable)
+    // GROUP rows are matched back to back (independent), then their counters are bumped in row order (shared atomics of
+    // one warp on one address execute in program order, which keeps the ranking stable)
     constexpr int GROUP = 4;
 #pragma unroll
     for (int i0 = 0; i0 < IPT; i0 += GROUP) {
@@ -124,7 +142,7 @@ radix_onesweep_kernel(const unsigned long long* __restrict__ keys_in, unsigned l
 #pragma unroll
         for (int g = 0; g < GROUP; ++g) {
             d[g] = (uint32_t)((key[i0 + g] >> shift) & mask);
-            peers[g] = __match_any_sync(0xffffffffu, d[g]);
+            peers[g] = digit_peers<RB>(d[g]);
         }
         uint32_t old[GROUP];
 #pragma unroll
@@ -207,12 +225,29 @@ radix_onesweep_kernel(const unsigned long long* __restrict__ keys_in, unsigned l
     }
     __syncthreads();
     // every digit's run leaves as one contiguous burst (padding occupies the last slots of the sorted tile)
-    for (uint32_t j = tid; j < n_tile; j += THREADS) {
-        const unsigned long long k = s_keys[j];
-        const uint32_t d = (uint32_t)((k >> shift) & mask);
-        const uint32_t dst = s_goff[d] + j;
-        keys_out[dst] = k;
-        if (PAIRS) vals_out[dst] = s_vals[j];
+    if (n_tile == (uint32_t)TILE) {  // full tile: four independent (key load -> offset load -> store) chains in flight
+#pragma unroll
+        for (int i0 = 0; i0 < IPT; i0 += 4) {
+            unsigned long long k[4];
+            uint32_t dst[4];
+#pragma unroll
+            for (int g = 0; g < 4; ++g) k[g] = s_keys[tid + (uint32_t)(i0 + g) * THREADS];
+#pragma unroll
+            for (int g = 0; g < 4; ++g) dst[g] = s_goff[(uint32_t)((k[g] >> shift) & mask)] + tid + (uint32_t)(i0 + g) * THREADS;
+#pragma unroll
+            for (int g = 0; g < 4; ++g) {
+                keys_out[dst[g]] = k[g];
+                if (PAIRS) vals_out[dst[g]] = s_vals[tid + (uint32_t)(i0 + g) * THREADS];
+            }
+        }
+    } else {
+        for (uint32_t j = tid; j < n_tile; j += THREADS) {
+            const unsigned long long k = s_keys[j];
+            const uint32_t d = (uint32_t)((k >> shift) & mask);
+            const uint32_t dst = s_goff[d] + j;
+            keys_out[dst] = k;
+            if (PAIRS) vals_out[dst] = s_vals[j];
+        }
     }
 }
 
@@ -257,12 +292,14 @@ int exclusive_scan_u32(pb200_ctx* ctx, uint32_t* counts, uint32_t n, uint32_t* t
 }
 
 // digit plan for the bits [begin_bit, end_bit): 9-bit digits only when they save a pass
-static void plan_passes(const pb200_ctx* ctx, int begin_bit, int end_bit, rs::Passes* out, int* width) {
+static void plan_passes(const pb200_ctx* ctx, int begin_bit, int end_bit, bool pairs, rs::Passes* out, int* width) {
     using namespace rs;
     Passes& ps = *out;
     const int bits = end_bit - begin_bit;
     const int p8 = (bits + 7) / 8, p9 = (bits + 8) / 9;
-    const bool wide = p9 < p8 && !ctx->sort_force_8bit;
+    // (key, payload) tiles with 512 bins need 119 KB of shared memory: one CTA per SM instead of two, and a pass takes
+    // 1.38 ms instead of 0.87 ms per 100 M pairs (measured) -- 9-bit digits are for keys-only sorts
+    const bool wide = p9 < p8 && !pairs && !ctx->sort_force_8bit;
     ps.n_passes = wide ? p9 : p8;
     {   // spread the bits: the first passes are 9 bits wide as long as the rest still fills 8-bit passes, the last may be narrower
         int left = bits;
@@ -310,7 +347,7 @@ int radix_sort_u64(pb200_ctx* ctx, unsigned long long* keys, unsigned long long*
     cudaStream_t st = ctx->stream;
     Passes ps;
     int width[MAX_PASSES];
-    plan_passes(ctx, begin_bit, end_bit, &ps, width);
+    plan_passes(ctx, begin_bit, end_bit, vals != nullptr, &ps, width);
     const uint32_t n_tiles = (uint32_t)((n + TILE - 1) / TILE);
     DevTmp d_hist_own, d_status;
     DevTmp* d_hist = &d_hist_own;
