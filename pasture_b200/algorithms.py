@@ -76,9 +76,35 @@ def morton_codes(buffer, bmin, bmax, ctx=None):
     return out[: buffer.len()]
 
 
+class _ResultOwner:
+    """keeps a library-owned result (pb200_result_buffer) alive for as long as tensors view its device memory"""
+
+    def __init__(self, handle, ctx):
+        self._h = handle
+        self._ctx = ctx  # the context must outlive the result (its memory goes back to the context's cache)
+
+    def __del__(self):
+        try:
+            if self._h:
+                lib().pb200_result_buffer_destroy(self._h)
+                self._h = None
+        except Exception:
+            pass
+
+
+class _DeviceView:
+    """a span of library-owned device memory for torch.as_tensor (CUDA array interface); holds the owner"""
+
+    def __init__(self, ptr, nbytes, owner):
+        self._owner = owner
+        self.__cuda_array_interface__ = {"shape": (int(nbytes),), "typestr": "|u1", "data": (int(ptr), False), "version": 2}
+
+
 def voxelgrid_filter(buffer, leafsize_x, leafsize_y, leafsize_z, filtered_layout=None, out_buffer_type=HashMapBuffer,
                      device=None, ctx=None, return_keys=False):
-    """voxel_grid.rs:109-165. Returns the filtered buffer (library result copied into a buffer of out_buffer_type)."""
+    """voxel_grid.rs:109-165. Returns the filtered buffer.  A device-resident result is handed over WITHOUT a copy: the
+    returned buffer's tensors view the memory of the library's result object, which lives as long as they do (then the
+    block goes back to the context's cache).  Host results are copied into torch-owned memory."""
     ctx = context_for(ctx, buffer)
     layout = filtered_layout or buffer.point_layout()
     dev = torch.device(device) if device is not None else buffer.device
@@ -88,10 +114,20 @@ def voxelgrid_filter(buffer, leafsize_x, leafsize_y, leafsize_z, filtered_layout
     h = C.c_void_p()
     check(lib().pb200_voxelgrid_filter(ctx._h, C.byref(d), leafsize_x, leafsize_y, leafsize_z, layout._h, kind, memspace,
                                        C.byref(h)))
-    try:
-        rd = BufferDesc()
-        check(lib().pb200_result_buffer_desc(h, C.byref(rd)))
-        n = int(rd.len)
+    owner = _ResultOwner(h, ctx)
+    rd = BufferDesc()
+    check(lib().pb200_result_buffer_desc(h, C.byref(rd)))
+    n = int(rd.len)
+    if memspace == 1 and n:
+        cdev = torch.device("cuda", ctx.device)
+
+        def view(ptr, nbytes):
+            return torch.as_tensor(_DeviceView(ptr, max(1, nbytes), owner), device=cdev)
+        if kind == 0:
+            out = VectorBuffer(layout, n, cdev, data=view(rd.aos, n * layout.size_of_point_entry()))
+        else:
+            out = HashMapBuffer(layout, n, cdev, columns=[view(rd.columns[i], n * a.size()) for i, a in enumerate(layout.attributes())])
+    else:
         out = out_buffer_type(layout, n, dev)
         od = out.desc()
         if n:
@@ -100,13 +136,11 @@ def voxelgrid_filter(buffer, leafsize_x, leafsize_y, leafsize_z, filtered_layout
             else:
                 for i, a in enumerate(layout.attributes()):
                     _copy(ctx, od.columns[i], rd.columns[i], n * a.size(), memspace)
-        keys = None
-        if return_keys:
-            keys = np.zeros((max(1, n), 3), dtype=np.uint64)
-            check(lib().pb200_result_buffer_voxel_keys(h, C.c_void_p(keys.ctypes.data)))
-            keys = keys[:n]
-    finally:
-        lib().pb200_result_buffer_destroy(h)
+    keys = None
+    if return_keys:
+        keys = np.zeros((max(1, n), 3), dtype=np.uint64)
+        check(lib().pb200_result_buffer_voxel_keys(h, C.c_void_p(keys.ctypes.data)))
+        keys = keys[:n]
     return (out, keys) if return_keys else out
 
 
