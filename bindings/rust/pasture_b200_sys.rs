@@ -141,6 +141,9 @@ extern "C" {
     pub fn pb200_converter_num_mappings(cv: *const pb200_converter) -> u32;
     pub fn pb200_converter_convert_into_range(cv: *mut pb200_converter, src: *const pb200_buffer_desc, src_begin: u64,
         src_end: u64, dst: *const pb200_buffer_desc, dst_begin: u64, dst_end: u64, out_of_range_count: *mut u64) -> c_int;
+    pub fn pb200_converter_convert_fresh_range(cv: *mut pb200_converter, src: *const pb200_buffer_desc, src_begin: u64, src_end: u64,
+                                               dst: *const pb200_buffer_desc, dst_begin: u64, dst_end: u64,
+                                               out_of_range_count: *mut u64) -> c_int;
     pub fn pb200_converter_convert_into(cv: *mut pb200_converter, src: *const pb200_buffer_desc,
                                         dst: *const pb200_buffer_desc, out_of_range_count: *mut u64) -> c_int;
     pub fn pb200_converter_convert_into_range_with_bounds(cv: *mut pb200_converter, src: *const pb200_buffer_desc,

@@ -201,6 +201,15 @@ uint32_t pb200_converter_num_mappings(const pb200_converter* cv);
 int pb200_converter_convert_into_range(pb200_converter* cv, const pb200_buffer_desc* src, uint64_t src_begin,
                                        uint64_t src_end, const pb200_buffer_desc* dst, uint64_t dst_begin,
                                        uint64_t dst_end, uint64_t* out_of_range_count);
+/* BufferLayoutConverter::convert :242-259 on caller-owned memory: the reference creates the target with
+ * `OutBuffer::new_from_layout` + `resize` (zero fill, point_buffer.rs:833-837) and converts into it, so the previous content
+ * of the target range is irrelevant.  This entry point has those semantics for [dst_begin, dst_end): EVERY byte of the
+ * range is written -- mapped attributes with their converted values, everything else (unmapped attributes, padding)
+ * with zero -- and nothing is read back, which saves the read-modify-write of partially mapped interleaved records that
+ * convert_into_range needs (it must preserve unmapped bytes).  The target may be uninitialised memory. */
+int pb200_converter_convert_fresh_range(pb200_converter* cv, const pb200_buffer_desc* src, uint64_t src_begin,
+                                        uint64_t src_end, const pb200_buffer_desc* dst, uint64_t dst_begin,
+                                        uint64_t dst_end, uint64_t* out_of_range_count);
 /* convert_into :268-283 */
 int pb200_converter_convert_into(pb200_converter* cv, const pb200_buffer_desc* src, const pb200_buffer_desc* dst,
                                  uint64_t* out_of_range_count);

@@ -21,11 +21,12 @@ INTERLEAVED, COLUMNAR = 0, 1
 HOST, DEVICE = 0, 1
 
 
-def _alloc(nbytes, device, pinned):
+def _alloc(nbytes, device, pinned, uninitialized=False):
     dev = torch.device(device)
+    make = torch.empty if uninitialized else torch.zeros
     if dev.type == "cpu":
-        return torch.zeros(max(1, nbytes), dtype=torch.uint8, pin_memory=bool(pinned) and torch.cuda.is_available())
-    return torch.zeros(max(1, nbytes), dtype=torch.uint8, device=dev)
+        return make(max(1, nbytes), dtype=torch.uint8, pin_memory=bool(pinned) and torch.cuda.is_available())
+    return make(max(1, nbytes), dtype=torch.uint8, device=dev)
 
 
 def _typed(raw_bytes, dtype, n):
@@ -82,7 +83,7 @@ class _BufferBase:
 class VectorBuffer(_BufferBase):
     """Interleaved buffer: one byte array of len * size_of_point_entry (point_buffer.rs:659-945)."""
 
-    def __init__(self, layout, length=0, device="cpu", pinned=False, data=None):
+    def __init__(self, layout, length=0, device="cpu", pinned=False, data=None, uninitialized=False):
         self._layout = layout
         self._len = int(length)
         self._device = torch.device(device)
@@ -90,8 +91,8 @@ class VectorBuffer(_BufferBase):
         if data is not None:
             self.data = data
             self._device = data.device
-        else:
-            self.data = _alloc(self._len * layout.size_of_point_entry(), device, pinned)  # resize(): zero fill :833-837
+        else:  # resize(): zero fill :833-837 (uninitialized: the caller promises to write every byte, e.g. convert())
+            self.data = _alloc(self._len * layout.size_of_point_entry(), device, pinned, uninitialized)
 
     @classmethod
     def new_from_layout(cls, layout, device="cpu"):
@@ -170,7 +171,7 @@ class VectorBuffer(_BufferBase):
 class HashMapBuffer(_BufferBase):
     """Columnar buffer: one byte array per attribute in layout order (point_buffer.rs:1031-1474)."""
 
-    def __init__(self, layout, length=0, device="cpu", pinned=False, columns=None):
+    def __init__(self, layout, length=0, device="cpu", pinned=False, columns=None, uninitialized=False):
         self._layout = layout
         self._len = int(length)
         self._device = torch.device(device)
@@ -180,7 +181,7 @@ class HashMapBuffer(_BufferBase):
             if columns:
                 self._device = columns[0].device
         else:
-            self.columns = [_alloc(self._len * a.size(), device, pinned) for a in layout.attributes()]
+            self.columns = [_alloc(self._len * a.size(), device, pinned, uninitialized) for a in layout.attributes()]
 
     @classmethod
     def new_from_layout(cls, layout, device="cpu"):

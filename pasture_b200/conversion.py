@@ -96,10 +96,25 @@ class BufferLayoutConverter:
         return lib().pb200_converter_num_mappings(self._h)
 
     def convert(self, source_buffer, out_buffer_type, device=None):  # :242
+        """new_from_layout + resize + convert_into.  The library writes EVERY byte of the new buffer (zeros where no
+        mapping applies), so the target is allocated uninitialised and partially mapped interleaved records need no
+        read-modify-write"""
         dev = device if device is not None else source_buffer.device
-        target = out_buffer_type(self._to, source_buffer.len(), dev)  # new_from_layout + resize (zero fill)
-        self.convert_into(source_buffer, target)
+        n = source_buffer.len()
+        target = out_buffer_type(self._to, n, dev, uninitialized=True)
+        context_for(self._ctx, source_buffer, target)
+        sd, dd = source_buffer.desc(), target.desc()
+        check(lib().pb200_converter_convert_fresh_range(self._h, C.byref(sd), 0, n, C.byref(dd), 0, n, None))
         return target
+
+    def convert_into_fresh(self, source_buffer, target_buffer, source_range=None, target_range=None):
+        """`convert` semantics on an existing buffer (pb200_converter_convert_fresh_range): every byte of the target range is
+        written -- zeros where no mapping applies -- and nothing of its previous content is read"""
+        context_for(self._ctx, source_buffer, target_buffer)
+        sr = source_range if source_range is not None else range(0, source_buffer.len())
+        tr = target_range if target_range is not None else range(0, len(sr))
+        sd, dd = source_buffer.desc(), target_buffer.desc()
+        check(lib().pb200_converter_convert_fresh_range(self._h, C.byref(sd), sr.start, sr.stop, C.byref(dd), tr.start, tr.stop, None))
 
     def convert_into(self, source_buffer, target_buffer, count_out_of_range=False):  # :268
         return self.convert_into_range(source_buffer, range(0, source_buffer.len()), target_buffer,

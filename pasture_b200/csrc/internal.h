@@ -184,6 +184,16 @@ struct PhaseScope {
 int radix_sort_u64(pb200_ctx* ctx, unsigned long long* keys, unsigned long long* keys_alt, uint32_t* vals, uint32_t* vals_alt,
                    uint64_t n, int begin_bit, int end_bit, bool* in_alt);
 
+// convert.cu: conversion into a fresh target range fused with the LAS writer's running statistics (see the definition)
+struct EgressStats {
+    uint64_t out_of_range;
+    uint64_t hist[16];
+    int bounds_tracked, has_bounds;
+    double src_min[3], src_max[3];
+};
+int convert_range_egress(pb200_converter* cv, const pb200_buffer_desc* src, uint64_t sb, uint64_t se, const pb200_buffer_desc* dst,
+                         uint64_t db, uint64_t de, int track_src_attr, int hist_src_attr, EgressStats* out);
+
 // exclusive prefix sum of n device counters in place (one CTA; meant for per-tile counts), total -> *total_out (device)
 int exclusive_scan_u32(pb200_ctx* ctx, uint32_t* counts, uint32_t n, uint32_t* total_out);
 

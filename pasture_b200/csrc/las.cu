@@ -10,41 +10,6 @@
 
 namespace pb200 {
 
-// points by return number (raw_writers.rs:221-229,259-263): counts16[b] += #points with ReturnNumber == b, b = 1..15.
-// Per-warp 256-bin histograms in shared memory (one shared atomic per point; a packed byte column is read 16 points per
-// load), folded into 15 global atomics per CTA.
-__global__ void __launch_bounds__(256) return_histogram_kernel(const uint8_t* __restrict__ base, unsigned long long stride,
-                                                               unsigned long long n, unsigned long long* __restrict__ counts16) {
-    __shared__ unsigned int s_h[8][256];
-    for (unsigned i = threadIdx.x; i < 8 * 256; i += blockDim.x) (&s_h[0][0])[i] = 0;
-    __syncthreads();
-    unsigned int* h = s_h[threadIdx.x >> 5];
-    const unsigned long long step = (unsigned long long)gridDim.x * blockDim.x;
-    const unsigned long long tid = (unsigned long long)blockIdx.x * blockDim.x + threadIdx.x;
-    if (stride == 1 && (reinterpret_cast<uintptr_t>(base) & 15) == 0) {
-        const uint4* v4 = reinterpret_cast<const uint4*>(base);
-        const unsigned long long n16 = n >> 4;
-        for (unsigned long long i = tid; i < n16; i += step) {
-            const uint4 v = __ldg(v4 + i);
-            const unsigned int w[4] = {v.x, v.y, v.z, v.w};
-#pragma unroll
-            for (int k = 0; k < 4; ++k) {
-                atomicAdd(&h[w[k] & 0xFFu], 1u); atomicAdd(&h[(w[k] >> 8) & 0xFFu], 1u);
-                atomicAdd(&h[(w[k] >> 16) & 0xFFu], 1u); atomicAdd(&h[w[k] >> 24], 1u);
-            }
-        }
-        for (unsigned long long i = (n16 << 4) + tid; i < n; i += step) atomicAdd(&h[base[i]], 1u);
-    } else {
-        for (unsigned long long i = tid; i < n; i += step) atomicAdd(&h[base[i * stride]], 1u);
-    }
-    __syncthreads();
-    if (threadIdx.x >= 1 && threadIdx.x < 16) {
-        unsigned long long c = 0;
-        for (int w = 0; w < 8; ++w) c += s_h[w][threadIdx.x];
-        if (c) atomicAdd(&counts16[threadIdx.x], c);
-    }
-}
-
 static uint16_t rd16(const uint8_t* p) { uint16_t v; memcpy(&v, p, 2); return v; }
 static uint32_t rd32(const uint8_t* p) { uint32_t v; memcpy(&v, p, 4); return v; }
 static uint64_t rd64(const uint8_t* p) { uint64_t v; memcpy(&v, p, 8); return v; }
@@ -187,53 +152,19 @@ int pb200_las_write_points(pb200_ctx* ctx, const pb200_buffer_desc* src, uint64_
     dst.len = n;
     dst.aos = out_records;
     dst.columns = nullptr;
-    if (out_memspace == PB200_DEVICE) {
-        const cudaError_t me = cudaMemsetAsync(out_records, 0, (size_t)(n * raw->size), ctx->stream);
-        if (me != cudaSuccess) return done(cuda_error(me, "cudaMemsetAsync(out_records)"));
-    } else memset(out_records, 0, (size_t)(n * raw->size));
-    rc = pb200_converter_convert_into_range(cv, src, begin, end, &dst, 0, n, &stats->out_of_range);
-    if (rc < 0) return done(rc);
-    // running bounds of the written world-space positions (raw_writers.rs:28-47) and points by return
-    pb200_buffer_desc sl = *src;
-    std::vector<void*> cols;
-    sl.len = n;
-    if (src->kind == PB200_INTERLEAVED) sl.aos = (uint8_t*)src->aos + begin * src->layout->size;
-    else {
-        cols.resize(src->layout->attrs.size());
-        for (size_t a = 0; a < cols.size(); ++a) cols[a] = src->columns[a] ? (uint8_t*)src->columns[a] + begin * src->layout->attrs[a].size : nullptr;
-        sl.columns = cols.data();
-    }
-    int some = 0;
-    rc = pb200_calculate_bounds(ctx, &sl, stats->bounds_min, stats->bounds_max, &some);
-    if (rc < 0) return done(rc);
-    stats->has_bounds = some;
+    // one pass: records (every byte written: attributes the source lacks become 0), out-of-range count, points by return,
+    // bounds of the written positions
     const int ri = pb200_layout_index_of(src->layout, "ReturnNumber", PB200_U8);
-    if (ri >= 0) {
-        const pb200_attr& ra = src->layout->attrs[(size_t)ri];
-        const uint64_t stride = src->kind == PB200_INTERLEAVED ? src->layout->size : ra.size;
-        const uint8_t* p = src->kind == PB200_INTERLEAVED ? (const uint8_t*)sl.aos + ra.offset : (const uint8_t*)sl.columns[ri];
-        void* scr = nullptr;
-        rc = scratch(ctx, 8192, &scr);
-        if (rc < 0) return done(rc);
-        unsigned long long* d_counts = (unsigned long long*)((uint8_t*)scr + 4096);
-        cudaMemsetAsync(d_counts, 0, 16 * 8, ctx->stream);
-        void* staged = nullptr;
-        if (src->memspace == PB200_HOST) {  // gather the 1-byte column on the host, stage it
-            std::vector<uint8_t> col((size_t)n);
-            for (uint64_t i = 0; i < n; ++i) col[(size_t)i] = p[i * stride];
-            if (cudaMalloc(&staged, (size_t)n) != cudaSuccess) return done(set_error(PB200_ERR_OOM, "out of device memory"));
-            cudaMemcpyAsync(staged, col.data(), (size_t)n, cudaMemcpyHostToDevice, ctx->stream);
-            cudaStreamSynchronize(ctx->stream);
-        }
-        unsigned long long want = (n + 255) / 256, cap = (unsigned long long)ctx->sm_count * 16;
-        return_histogram_kernel<<<(unsigned)(want < cap ? want : cap), 256, 0, ctx->stream>>>(staged ? (const uint8_t*)staged : p, staged ? 1 : stride, n, d_counts);
-        g_launches++;
-        cudaMemcpyAsync(ctx->h_scratch, d_counts, 16 * 8, cudaMemcpyDeviceToHost, ctx->stream);
-        cudaStreamSynchronize(ctx->stream);
-        if (staged) cudaFree(staged);
-        memcpy(stats->points_by_return, ctx->h_scratch, 16 * 8);
-        cudaError_t e = cudaGetLastError();
-        if (e != cudaSuccess) return done(cuda_error(e, "return_histogram_kernel"));
+    EgressStats es;
+    rc = convert_range_egress(cv, src, begin, end, &dst, 0, n, pi, ri, &es);
+    if (rc < 0) return done(rc);
+    stats->out_of_range = es.out_of_range;
+    for (int b = 1; b < 16; ++b) stats->points_by_return[b] = es.hist[b];
+    if (es.bounds_tracked) {
+        if (!es.has_bounds)  // calculate_bounds on all-NaN positions: AABB::from_min_max panics (bounds.rs:21-26)
+            return done(set_error(PB200_ERR_INVALID, "AABB::from_min_max: Minimum position must be <= maximum position!"));
+        stats->has_bounds = 1;
+        for (int c = 0; c < 3; ++c) { stats->bounds_min[c] = es.src_min[c]; stats->bounds_max[c] = es.src_max[c]; }
     }
     if (out_memspace == PB200_DEVICE) cudaStreamSynchronize(ctx->stream);
     return done(PB200_OK);

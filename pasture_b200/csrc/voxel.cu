@@ -1128,7 +1128,6 @@ int pb200_voxel_partials_centroids(const pb200_voxel_partials* p, double* positi
 void pb200_voxel_partials_destroy(pb200_voxel_partials* p) {
     if (!p) return;
     if (p->ctx) cudaSetDevice(p->ctx->device);
-    cudaStream_t st = p->ctx ? p->ctx->stream : nullptr;
     if (p->ctx) { cache_free(p->ctx, p->keys); cache_free(p->ctx, p->counts); cache_free(p->ctx, p->sums); }
     delete p;
 }
@@ -1163,7 +1162,6 @@ int pb200_result_buffer_voxel_keys(const pb200_result_buffer* r, uint64_t* keys_
 void pb200_result_buffer_destroy(pb200_result_buffer* r) {
     if (!r) return;
     if (r->ctx) cudaSetDevice(r->ctx->device);
-    cudaStream_t st = r->ctx ? r->ctx->stream : nullptr;  // device memory goes back to the pool behind queued work
     if (r->d_packed_keys && r->ctx) cache_free(r->ctx, r->d_packed_keys);
     if (r->memspace == PB200_DEVICE) {
         if (r->ctx) { cache_free(r->ctx, r->aos); for (void* p : r->columns) cache_free(r->ctx, p); }

@@ -285,6 +285,50 @@ def test_random_layout_conversion(ctx, seed):
             assert np.array_equal(odst.aos[: n * olt.size], pdst.raw_bytes()), "padding / unmapped bytes changed"
 
 
+@pytest.mark.parametrize("seed", range(8))
+@pytest.mark.parametrize("device", ["cuda", "cpu"])
+def test_fresh_target_conversion_writes_every_byte(ctx, seed, device):
+    """`convert` semantics on caller-owned memory (buffer_conversion.rs:242-259: a zero-filled new buffer, then
+    convert_into): pb200_converter_convert_fresh_range must leave the target range exactly like the oracle's `convert`,
+    although it starts from garbage -- mapped attributes converted, unmapped attributes / padding zero, and the points
+    outside the range untouched.  Random layouts with holes (missing attributes, alignment padding), all buffer pairs."""
+    import ctypes as C
+    from pasture_b200._lib import check, lib
+    rng = np.random.default_rng(4000 + seed)
+    n_src = int(rng.integers(2, 8))
+    src_attrs = [(f"a{i}", int(rng.choice(list(range(16)))), 0) for i in range(n_src)]
+    ol, pl = util.layouts(src_attrs, packed=int(rng.choice([0, 1])))
+    dst_attrs = [(a, d, e) for (a, d, e) in src_attrs if rng.random() < 0.7] or [src_attrs[0]]
+    dst_attrs.insert(int(rng.integers(0, len(dst_attrs) + 1)), ("hole_u8", O.U8, 0))      # no source: stays default
+    dst_attrs.insert(int(rng.integers(0, len(dst_attrs) + 1)), ("hole_f64", O.F64, 0))
+    olt, plt = util.layouts(dst_attrs, packed=int(rng.choice([0, 1, 4])))
+    n, lo, hi = 3001, 5, 2990
+    for src_col, dst_col in PAIRS:
+        osrc, psrc = util.random_bytes_buffers(ol, pl, n, src_col, seed=seed, finite_floats=True)
+        if device == "cpu":
+            psrc = psrc.to("cpu")
+        ocv = O.OConverter(ol, olt, with_default=True)
+        pcv = BufferLayoutConverter.for_layouts_with_default(pl, plt)
+        want = ocv.convert(osrc, dst_col)  # zero-filled target, convert_into
+        pdst = BUF[dst_col](plt, n, device)
+        for t in (pdst.columns if dst_col else [pdst.data]):
+            t.fill_(0xC3)
+        sd, dd = psrc.desc(), pdst.desc()
+        check(lib().pb200_converter_convert_fresh_range(pcv._h, C.byref(sd), lo, hi, C.byref(dd), lo, hi, None))
+        torch.cuda.synchronize()
+        for i in range(len(plt)):
+            got, exp = pdst._attribute_bytes(i), want.attribute_bytes(i)
+            assert np.array_equal(got[lo:hi], exp[lo:hi]), (seed, src_col, dst_col, plt.at(i))
+            assert np.all(got[:lo] == 0xC3) and np.all(got[hi:] == 0xC3), "points outside the range were touched"
+        if not dst_col:  # padding bytes inside the range are zero as well
+            rec = plt.size_of_point_entry()
+            raw = pdst.raw_bytes().reshape(n, rec)
+            assert np.array_equal(raw[lo:hi], want.aos[: n * rec].reshape(n, rec)[lo:hi])
+        # and the allocating convenience call: uninitialised target, whole range
+        full = pcv.convert(psrc, BUF[dst_col], device=device)
+        util.assert_buffers_match(want, full)
+
+
 @pytest.mark.parametrize("src_col,dst_col", PAIRS)
 def test_ranges_with_unaligned_offsets(ctx, src_col, dst_col):
     """convert_into_range (buffer_conversion.rs:292): arbitrary sub-ranges, neighbours untouched"""
