@@ -187,6 +187,10 @@ extern "C" {
     pub fn pb200_result_buffer_voxel_keys(r: *const pb200_result_buffer, keys_out: *mut u64) -> c_int;
     pub fn pb200_result_buffer_destroy(r: *mut pb200_result_buffer);
     pub fn pb200_knn(ctx: *mut pb200_ctx, buf: *const pb200_buffer_desc, k: u32, idx_out: *mut u32, d2_out: *mut f64) -> c_int;
+    pub fn pb200_knn_range(ctx: *mut pb200_ctx, buf: *const pb200_buffer_desc, k: u32, first_query: u64, n_queries: u64,
+                           idx_out: *mut u32, d2_out: *mut f64) -> c_int;
+    pub fn pb200_compute_normals_range(ctx: *mut pb200_ctx, buf: *const pb200_buffer_desc, k: u32, first_query: u64, n_queries: u64,
+                                       normals_out: *mut f64, curvature_out: *mut f64) -> c_int;
     pub fn pb200_radius_search(ctx: *mut pb200_ctx, buf: *const pb200_buffer_desc, radius: f64, max_neighbors: u32,
                                idx_out: *mut u32, counts_out: *mut u32) -> c_int;
     pub fn pb200_compute_normals(ctx: *mut pb200_ctx, buf: *const pb200_buffer_desc, k: u32, normals_out: *mut f64,

@@ -334,6 +334,13 @@ void pb200_voxel_partials_destroy(pb200_voxel_partials* p);
  * (normal_estimation.rs:103,108): k nearest by squared distance including the point itself, ascending.
  * idx_out: len*k u32, d2_out: len*k f64 (nullable), in buf's memspace; if len < k the tail is 0xFFFFFFFF/inf. */
 int pb200_knn(pb200_ctx* ctx, const pb200_buffer_desc* buf, uint32_t k, uint32_t* idx_out, double* d2_out);
+/* The same for the points [first_query, first_query + n_queries) only (still against the whole buffer): idx_out /
+ * d2_out hold n_queries * k entries, entry 0 belongs to point first_query.  This is the loop body of
+ * normal_estimation.rs:106-127 for a sub-range of its `for point in points` -- the unit of work of the replicas-only
+ * multi-GPU cut: every GPU holds the position column and answers its own range.  The queries are processed
+ * in Morton order, so the work is proportional to n_queries.  PB200_ERR_RANGE if the range leaves the buffer. */
+int pb200_knn_range(pb200_ctx* ctx, const pb200_buffer_desc* buf, uint32_t k, uint64_t first_query, uint64_t n_queries,
+                    uint32_t* idx_out, double* d2_out);
 /* all neighbours with d2 <= r*r, at most max_neighbors per point (nearest first); counts_out: len u32 */
 int pb200_radius_search(pb200_ctx* ctx, const pb200_buffer_desc* buf, double radius, uint32_t max_neighbors,
                         uint32_t* idx_out, uint32_t* counts_out);
@@ -341,6 +348,10 @@ int pb200_radius_search(pb200_ctx* ctx, const pb200_buffer_desc* buf, double rad
  * reference), curvature_out len f64. PB200_ERR_TOO_FEW_POINTS if len < 3, PB200_ERR_INVALID if k < 3. */
 int pb200_compute_normals(pb200_ctx* ctx, const pb200_buffer_desc* buf, uint32_t k, double* normals_out,
                           double* curvature_out);
+
+/* compute_normals for the points [first_query, first_query + n_queries): normals_out n_queries * 3, curvature_out n_queries */
+int pb200_compute_normals_range(pb200_ctx* ctx, const pb200_buffer_desc* buf, uint32_t k, uint64_t first_query, uint64_t n_queries,
+                                double* normals_out, double* curvature_out);
 
 /* ---- 3D-Tiles .pnts FeatureTable body (pasture-io/src/tiles3d) --------------------------------------------
  * The binary body is one packed array per semantic. `attrs` describes the file's layout like PntsReader::layout +

@@ -112,6 +112,7 @@ def lib():
         "po_find_leaf_bsearch": (None, [vp, vp, u64, vp, u64, vp, u64, vp]),
         "po_voxelgrid_filter": (i32, [BP, dbl, dbl, dbl, BP, vp, i32]),
         "po_knn_bruteforce": (None, [vp, u64, vp, u64, u32, vp, vp]),
+        "po_knn_kdtree": (i32, [vp, u64, u64, u64, u32, vp, vp, vp, vp, i32]),
         "po_compute_centroid": (None, [vp, u64, vp]),
         "po_compute_covariance": (i32, [vp, u64, vp]),
         "po_solve_plane_parameter": (None, [vp, vp, vp]),
@@ -533,6 +534,32 @@ def knn_bruteforce(pts, queries, k):
     d2 = np.zeros((len(queries), k), dtype=np.float64)
     lib().po_knn_bruteforce(_ptr(pts), len(pts), _ptr(queries), len(queries), k, _ptr(idx), _ptr(d2))
     return idx, d2
+
+
+def knn_kdtree(pts, k, q_begin=0, q_end=None, with_distances=True, threads=None):
+    """exact kNN of the cloud's own points [q_begin, q_end) over a kd-tree (all host threads by default)"""
+    import os
+    pts = np.ascontiguousarray(pts, dtype=np.float64)
+    q_end = len(pts) if q_end is None else q_end
+    nq = max(0, q_end - q_begin)
+    idx = np.zeros((nq, k), dtype=np.uint32)
+    d2 = np.zeros((nq, k), dtype=np.float64) if with_distances else None
+    _check(lib().po_knn_kdtree(_ptr(pts), len(pts), q_begin, q_end, k, _ptr(idx), _ptr(d2) if with_distances else None, None, None,
+                               threads or os.cpu_count() or 1), "knn_kdtree")
+    return (idx, d2) if with_distances else idx
+
+
+def compute_normals_kdtree(pts, k, q_begin=0, q_end=None, threads=None):
+    """compute_normals (normal_estimation.rs:79-130) with the kd-tree kNN: (normals, curvature) of the points [q_begin, q_end)"""
+    import os
+    pts = np.ascontiguousarray(pts, dtype=np.float64)
+    q_end = len(pts) if q_end is None else q_end
+    nq = max(0, q_end - q_begin)
+    normals = np.zeros((nq, 3))
+    curv = np.zeros(nq)
+    _check(lib().po_knn_kdtree(_ptr(pts), len(pts), q_begin, q_end, k, None, None, _ptr(normals), _ptr(curv),
+                               threads or os.cpu_count() or 1), "compute_normals_kdtree")
+    return normals, curv
 
 
 def compute_centroid(pts):

@@ -187,6 +187,13 @@ int po_voxelgrid_filter(const po_buffer* src, double lx, double ly, double lz, p
 void po_knn_bruteforce(const double* pts, uint64_t n, const double* queries, uint64_t nq, uint32_t k,
                        uint32_t* idx_out, double* d2_out);
 
+/* exact kNN over a hand-written kd-tree (SURVEY 8d's "nanoflann-style" CPU baseline and the checker beyond the reach of the
+ * O(N^2) brute force): neighbours of the cloud's own points [q_begin, q_end), same (d2, index) order and the same d2
+ * arithmetic as po_knn_bruteforce; idx_out / d2_out (n_query x k), normals_out (n_query x 3) / curv_out are each optional.
+ * Tie ORDER at equal distances: parity unpinned (kd-tree 0.3.0 is not in /root/reference). */
+int po_knn_kdtree(const double* pts, uint64_t n, uint64_t q_begin, uint64_t q_end, uint32_t k, uint32_t* idx_out, double* d2_out,
+                  double* normals_out, double* curv_out, int threads);
+
 /* normal_estimation.rs:198-476 on an explicit neighbourhood (k points, xyz packed) */
 void po_compute_centroid(const double* pts, uint64_t k, double out[3]);
 int po_compute_covariance(const double* pts, uint64_t k, double out9[9]); /* row-major 3x3 */

@@ -144,6 +144,8 @@ SIGNATURES = {
     "pb200_voxel_partials_centroids": (i32, [vp, vp]),
     "pb200_voxel_partials_destroy": (None, [vp]),
     "pb200_knn": (i32, [vp, BD, u32, vp, vp]),
+    "pb200_knn_range": (i32, [vp, BD, u32, u64, u64, vp, vp]),
+    "pb200_compute_normals_range": (i32, [vp, BD, u32, u64, u64, vp, vp]),
     "pb200_radius_search": (i32, [vp, BD, dbl, u32, vp, vp]),
     "pb200_compute_normals": (i32, [vp, BD, u32, vp, vp]),
     "pb200_proj_pipeline_for_crs": (i32, [C.c_char_p, C.c_char_p, C.POINTER(ProjOp), u32]),

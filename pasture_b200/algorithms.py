@@ -232,17 +232,20 @@ def _copy(ctx, dst, src, nbytes, memspace):
         C.memmove(dst, src, nbytes)
 
 
-def knn(buffer, k, with_distances=True, ctx=None):
-    """KdTree::nearests for every point against the cloud (normal_estimation.rs:103,108) -> (idx [n,k] int64-view of u32, d2 [n,k])"""
+def knn(buffer, k, with_distances=True, query_range=None, ctx=None):
+    """KdTree::nearests for every point (or the points of `query_range`) against the cloud (normal_estimation.rs:103,108)
+    -> (idx [nq,k] int32 view of u32, d2 [nq,k]); row 0 belongs to query_range.start"""
     ctx = context_for(ctx, buffer)
     n = buffer.len()
+    r = query_range if query_range is not None else range(0, n)
+    nq = len(r)
     dev = buffer.device
-    idx = torch.zeros((max(1, n), k), dtype=torch.int32, device=dev)
-    d2 = torch.zeros((max(1, n), k), dtype=torch.float64, device=dev) if with_distances else None
+    idx = torch.zeros((max(1, nq), k), dtype=torch.int32, device=dev)
+    d2 = torch.zeros((max(1, nq), k), dtype=torch.float64, device=dev) if with_distances else None
     d = buffer.desc()
-    check(lib().pb200_knn(ctx._h, C.byref(d), k, C.c_void_p(idx.data_ptr()),
-                          C.c_void_p(d2.data_ptr()) if with_distances else None))
-    return (idx[:n], d2[:n]) if with_distances else idx[:n]
+    check(lib().pb200_knn_range(ctx._h, C.byref(d), k, r.start, nq, C.c_void_p(idx.data_ptr()),
+                                C.c_void_p(d2.data_ptr()) if with_distances else None))
+    return (idx[:nq], d2[:nq]) if with_distances else idx[:nq]
 
 
 def radius_search(buffer, radius, max_neighbors, ctx=None):
@@ -257,16 +260,21 @@ def radius_search(buffer, radius, max_neighbors, ctx=None):
     return idx[:n], cnt[:n]
 
 
-def compute_normals(point_cloud, k_nn, ctx=None):
-    """normal_estimation.rs:79-130 -> (normals [n,3] f64, curvature [n] f64) tensors on the buffer's device"""
+def compute_normals(point_cloud, k_nn, query_range=None, ctx=None):
+    """normal_estimation.rs:79-130 -> (normals [nq,3] f64, curvature [nq] f64) tensors on the buffer's device, for every
+    point or for the points of `query_range` (the loop body of :106-127 over a sub-range; neighbours come from the whole
+    cloud either way)"""
     ctx = context_for(ctx, point_cloud)
     n = point_cloud.len()
+    r = query_range if query_range is not None else range(0, n)
+    nq = len(r)
     dev = point_cloud.device
-    normals = torch.zeros((max(1, n), 3), dtype=torch.float64, device=dev)
-    curv = torch.zeros(max(1, n), dtype=torch.float64, device=dev)
+    normals = torch.zeros((max(1, nq), 3), dtype=torch.float64, device=dev)
+    curv = torch.zeros(max(1, nq), dtype=torch.float64, device=dev)
     d = point_cloud.desc()
-    check(lib().pb200_compute_normals(ctx._h, C.byref(d), k_nn, C.c_void_p(normals.data_ptr()), C.c_void_p(curv.data_ptr())))
-    return normals[:n], curv[:n]
+    check(lib().pb200_compute_normals_range(ctx._h, C.byref(d), k_nn, r.start, nq, C.c_void_p(normals.data_ptr()),
+                                            C.c_void_p(curv.data_ptr())))
+    return normals[:nq], curv[:nq]
 
 
 # ---- segmentation (pasture-algorithms/src/segmentation.rs) --------------------------------------------------

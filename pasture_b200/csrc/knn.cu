@@ -279,6 +279,9 @@ __device__ void estimate_normal(const uint8_t* __restrict__ base, unsigned long 
 
 struct QueryArgs {
     uint32_t n, nb, k, init_radius;
+    uint32_t nq, out_base;     // queries answered by this launch / original index of the first one (outputs are relative to it)
+    const uint32_t* qpos;      // null: every point is a query (thread t <-> sorted position t); else the sorted positions of
+                               // the queries, ascending (= Morton order), one per thread
     const double* spos;        // positions in Morton order, padded to nb * BUCKET points
     const uint32_t* sidx;      // original index of sorted position i
     const Node* nodes;
@@ -440,9 +443,10 @@ __global__ void __launch_bounds__(128) lbvh_query_kernel(QueryArgs a) {
     constexpr int KREG = HEAP ? 1 : KMAX;
     extern __shared__ __align__(16) uint8_t knn_smem[];
     __shared__ uint32_t s_stack[4][STACK_DEPTH];  // one warp-uniform stack per warp
-    const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
+    const uint32_t t_q = blockIdx.x * blockDim.x + threadIdx.x;
     const uint32_t warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-    const bool active = i < a.n;
+    const bool active = t_q < a.nq;
+    const uint32_t i = active ? (a.qpos ? a.qpos[t_q] : t_q) : 0u;  // sorted position of this thread's query
     // lanes beyond the cloud keep voting but never need anything: NaN fails every comparison
     const double qnan = __longlong_as_double(0x7FF8000000000000ll);
     const double qx = active ? a.spos[3 * (size_t)i] : qnan, qy = active ? a.spos[3 * (size_t)i + 1] : qnan,
@@ -455,10 +459,20 @@ __global__ void __launch_bounds__(128) lbvh_query_kernel(QueryArgs a) {
     typename std::conditional<HEAP, HeapList, KList<KREG>>::type list;
     if constexpr (HEAP) list.init(knn_smem, k);
     else list.init();
-    // prime the lists from the warp's own buckets and their neighbours in Morton order
-    const uint32_t qb0 = (i - lane) / BUCKET, qb1 = qb0 + 32 / BUCKET - 1;
-    const uint32_t ib0 = qb0 > a.init_radius ? qb0 - a.init_radius : 0u;
-    const uint32_t ib1 = (qb1 + a.init_radius < a.nb - 1) ? qb1 + a.init_radius : a.nb - 1;
+    // prime the lists from the buckets of the warp's queries and their neighbours in Morton order.  With every point a
+    // query these are four consecutive buckets; a query subset (qpos) is still in Morton order but spread out, so the
+    // primed window is capped around the warp's middle query and the traversal finds the rest.
+    const uint32_t act = __ballot_sync(0xffffffffu, active);
+    const uint32_t last_lane = act ? 31u - (uint32_t)__clz((int)act) : 0u;
+    const uint32_t qb0 = __shfl_sync(0xffffffffu, i, 0) / BUCKET, qb1 = __shfl_sync(0xffffffffu, i, last_lane) / BUCKET;
+    const uint32_t qbm = __shfl_sync(0xffffffffu, i, last_lane / 2) / BUCKET;
+    constexpr uint32_t PRIME_HALF = 6;
+    uint32_t ib0 = qb0 > a.init_radius ? qb0 - a.init_radius : 0u;
+    uint32_t ib1 = (qb1 + a.init_radius < a.nb - 1) ? qb1 + a.init_radius : a.nb - 1;
+    if (ib1 - ib0 + 1 > 2 * PRIME_HALF) {
+        ib0 = qbm > PRIME_HALF ? qbm - PRIME_HALF : 0u;
+        ib1 = (qbm + PRIME_HALF - 1 < a.nb - 1) ? qbm + PRIME_HALF - 1 : a.nb - 1;
+    }
     uint32_t pend_lo = ib0, pend_hi = ib1 + 1;
     bool more = a.nb > 1 && !(ib0 == 0 && ib1 == a.nb - 1);
     int sp = 0;
@@ -524,7 +538,7 @@ __global__ void __launch_bounds__(128) lbvh_query_kernel(QueryArgs a) {
         } else more = false;
     }
     if (!active) return;
-    const uint32_t self = sidx[i];
+    const uint32_t self = sidx[i] - a.out_base;  // output slot: original index relative to the first query
     if (MODE == 3) {  // (nodes visited, buckets scanned, candidates offered) per query
         a.idx_out[(size_t)self * 3] = st_nodes;
         a.idx_out[(size_t)self * 3 + 1] = st_buckets;
@@ -576,6 +590,50 @@ __global__ void __launch_bounds__(128) lbvh_query_kernel(QueryArgs a) {
         }
         if (a.counts_out) a.counts_out[self] = cnt;
     }
+}
+
+// ---- query subsets: the sorted positions of the points whose ORIGINAL index lies in [first, first + nq), ascending -------
+// (ordered stream compaction of the sorted index array: per-tile counts -> scan -> emit; a thread owns 8 consecutive slots)
+constexpr int QC_THREADS = 256, QC_PER = 8, QC_TILE = QC_THREADS * QC_PER;
+
+__global__ void __launch_bounds__(QC_THREADS) qpos_count_kernel(const uint32_t* __restrict__ sidx, uint32_t n, uint32_t first, uint32_t nq,
+                                                                uint32_t* __restrict__ tile_counts) {
+    __shared__ uint32_t warp_sum[QC_THREADS / 32];
+    const uint32_t b = blockIdx.x * QC_TILE + threadIdx.x * QC_PER;
+    uint32_t c = 0;
+#pragma unroll
+    for (int u = 0; u < QC_PER; ++u)
+        if (b + u < n) c += (sidx[b + u] - first) < nq ? 1u : 0u;
+    for (int o = 16; o > 0; o >>= 1) c += __shfl_xor_sync(0xffffffffu, c, o);
+    if ((threadIdx.x & 31) == 0) warp_sum[threadIdx.x >> 5] = c;
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        uint32_t t = 0;
+        for (int w = 0; w < QC_THREADS / 32; ++w) t += warp_sum[w];
+        tile_counts[blockIdx.x] = t;
+    }
+}
+
+__global__ void __launch_bounds__(QC_THREADS) qpos_emit_kernel(const uint32_t* __restrict__ sidx, uint32_t n, uint32_t first, uint32_t nq,
+                                                               const uint32_t* __restrict__ tile_offsets, uint32_t* __restrict__ qpos) {
+    __shared__ uint32_t warp_sum[QC_THREADS / 32];
+    const uint32_t b = blockIdx.x * QC_TILE + threadIdx.x * QC_PER, lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    uint32_t flags = 0;
+#pragma unroll
+    for (int u = 0; u < QC_PER; ++u)
+        if (b + u < n && (sidx[b + u] - first) < nq) flags |= 1u << u;
+    const uint32_t c = __popc(flags);
+    uint32_t x = c;
+#pragma unroll
+    for (int o = 1; o < 32; o <<= 1) { const uint32_t y = __shfl_up_sync(0xffffffffu, x, o); if ((int)lane >= o) x += y; }
+    if (lane == 31) warp_sum[warp] = x;
+    __syncthreads();
+    uint32_t before = tile_offsets[blockIdx.x];
+    for (uint32_t w = 0; w < warp; ++w) before += warp_sum[w];
+    uint32_t o = before + x - c;
+#pragma unroll
+    for (int u = 0; u < QC_PER; ++u)
+        if ((flags >> u) & 1u) qpos[o++] = b + (uint32_t)u;
 }
 
 static unsigned grid_for(uint64_t n, int sm, unsigned block = 256) {
@@ -679,7 +737,7 @@ static int build_lbvh(pb200_ctx* ctx, const uint8_t* base, uint64_t stride, uint
 
 // the shared-memory heap variant: one instantiation per mode, k * 128 * 12 bytes of dynamic shared memory
 static int launch_query_heap(pb200_ctx* ctx, int mode, const QueryArgs& a, cudaStream_t st) {
-    const unsigned blocks = (a.n + 127) / 128;
+    const unsigned blocks = (a.nq + 127) / 128;
     const size_t smem = (size_t)a.k * 128 * 12;
     if (!ctx->knn_attr_set) {
         const int max_smem = MAX_K * 128 * 12;
@@ -696,7 +754,7 @@ static int launch_query_heap(pb200_ctx* ctx, int mode, const QueryArgs& a, cudaS
 
 template <int KMAX>
 static void launch_query(int mode, const QueryArgs& a, cudaStream_t st) {
-    const unsigned blocks = (a.n + 127) / 128;
+    const unsigned blocks = (a.nq + 127) / 128;
 #ifdef PB200_KNN_DIAGNOSTICS
     if (mode == 3) { if constexpr (KMAX == 16) lbvh_query_kernel<16, 3><<<blocks, 128, 0, st>>>(a); return; }
 #endif
@@ -706,14 +764,19 @@ static void launch_query(int mode, const QueryArgs& a, cudaStream_t st) {
 }
 
 // run a query kernel; outputs may live in host memory (staged through device temporaries)
-static int run_query(pb200_ctx* ctx, const pb200_buffer_desc* buf, int mode, uint32_t k, double radius, uint32_t* idx_out,
-                     double* d2_out, uint32_t* counts_out, double* normals_out, double* curvature_out) {
+// queries: the points [first_query, first_query + n_queries) of the buffer (all outputs hold n_queries entries)
+static int run_query(pb200_ctx* ctx, const pb200_buffer_desc* buf, int mode, uint32_t k, double radius, uint64_t first_query,
+                     uint64_t n_queries, uint32_t* idx_out, double* d2_out, uint32_t* counts_out, double* normals_out,
+                     double* curvature_out) {
     PB_TRY(validate_desc(buf, "buffer"));
     PB_DEVICE(ctx);
     if (buf->len > 0x7FFFFFF0ull) return set_error(PB200_ERR_UNSUPPORTED, "more than 2^31-16 points per call");
     if (k == 0 || k > MAX_K) return set_error(PB200_ERR_UNSUPPORTED, "k must be in 1..%d", MAX_K);
     const uint32_t n = (uint32_t)buf->len;
-    if (n == 0) return PB200_OK;
+    if (first_query > n || n_queries > n - first_query) return set_error(PB200_ERR_RANGE, "query range %llu + %llu exceeds the %u points of the buffer",
+                                                                         (unsigned long long)first_query, (unsigned long long)n_queries, n);
+    const uint32_t nq = (uint32_t)n_queries;
+    if (n == 0 || nq == 0) return PB200_OK;
     DevTmp staged;
     const uint8_t* base = nullptr;
     uint64_t stride = 0;
@@ -724,6 +787,20 @@ static int run_query(pb200_ctx* ctx, const pb200_buffer_desc* buf, int mode, uin
     DevTmp d_idx, d_d2, d_cnt, d_nrm, d_curv;
     QueryArgs a{};
     a.n = n; a.nb = tree.nb; a.k = k;
+    a.nq = nq; a.out_base = (uint32_t)first_query; a.qpos = nullptr;
+    DevTmp d_qpos, d_qtiles;
+    if (nq != n) {  // a query subset: its sorted positions in Morton order (the replicas-only multi-GPU cut)
+        PB_PHASE(ctx, "knn.query_list");
+        const uint32_t tiles = (n + QC_TILE - 1) / QC_TILE;
+        PB_CUDA(d_qpos.alloc(ctx->stream, (size_t)nq * 4));
+        PB_CUDA(d_qtiles.alloc(ctx->stream, ((size_t)tiles + 1) * 4));
+        qpos_count_kernel<<<tiles, QC_THREADS, 0, ctx->stream>>>((const uint32_t*)tree.idx2.p, n, a.out_base, nq, (uint32_t*)d_qtiles.p);
+        PB_TRY(exclusive_scan_u32(ctx, (uint32_t*)d_qtiles.p, tiles, (uint32_t*)d_qtiles.p + tiles));
+        qpos_emit_kernel<<<tiles, QC_THREADS, 0, ctx->stream>>>((const uint32_t*)tree.idx2.p, n, a.out_base, nq, (const uint32_t*)d_qtiles.p,
+                                                                (uint32_t*)d_qpos.p);
+        g_launches += 2;
+        a.qpos = (const uint32_t*)d_qpos.p;
+    }
     // the warp's own four buckets +- init_radius buckets prime every lane's list before the traversal
     a.init_radius = ctx->knn_heap ? (k + 15) / 16 : (k + 7) / 8;  // measured per list variant (benchmarks/knn_probe.py)
     if (ctx->knn_init_radius >= 0) a.init_radius = (uint32_t)ctx->knn_init_radius;
@@ -741,11 +818,11 @@ static int run_query(pb200_ctx* ctx, const pb200_buffer_desc* buf, int mode, uin
         return PB200_OK;
     };
     void* p = nullptr;
-    PB_TRY(out_ptr(idx_out, d_idx, (size_t)n * k * 4, &p)); a.idx_out = (uint32_t*)p;
-    PB_TRY(out_ptr(d2_out, d_d2, (size_t)n * k * 8, &p)); a.d2_out = (double*)p;
-    PB_TRY(out_ptr(counts_out, d_cnt, (size_t)n * 4, &p)); a.counts_out = (uint32_t*)p;
-    PB_TRY(out_ptr(normals_out, d_nrm, (size_t)n * 24, &p)); a.normals_out = (double*)p;
-    PB_TRY(out_ptr(curvature_out, d_curv, (size_t)n * 8, &p)); a.curvature_out = (double*)p;
+    PB_TRY(out_ptr(idx_out, d_idx, (size_t)nq * k * 4, &p)); a.idx_out = (uint32_t*)p;
+    PB_TRY(out_ptr(d2_out, d_d2, (size_t)nq * k * 8, &p)); a.d2_out = (double*)p;
+    PB_TRY(out_ptr(counts_out, d_cnt, (size_t)nq * 4, &p)); a.counts_out = (uint32_t*)p;
+    PB_TRY(out_ptr(normals_out, d_nrm, (size_t)nq * 24, &p)); a.normals_out = (double*)p;
+    PB_TRY(out_ptr(curvature_out, d_curv, (size_t)nq * 8, &p)); a.curvature_out = (double*)p;
     {
         PB_PHASE(ctx, mode == 2 ? "knn.query+normals" : "knn.query");
         if (ctx->knn_heap && mode != 3) PB_TRY(launch_query_heap(ctx, mode, a, ctx->stream));
@@ -757,11 +834,11 @@ static int run_query(pb200_ctx* ctx, const pb200_buffer_desc* buf, int mode, uin
     }
     PB_CUDA(cudaGetLastError());
     if (host) {
-        if (idx_out) PB_CUDA(cudaMemcpyAsync(idx_out, a.idx_out, (size_t)n * k * 4, cudaMemcpyDeviceToHost, ctx->stream));
-        if (d2_out) PB_CUDA(cudaMemcpyAsync(d2_out, a.d2_out, (size_t)n * k * 8, cudaMemcpyDeviceToHost, ctx->stream));
-        if (counts_out) PB_CUDA(cudaMemcpyAsync(counts_out, a.counts_out, (size_t)n * 4, cudaMemcpyDeviceToHost, ctx->stream));
-        if (normals_out) PB_CUDA(cudaMemcpyAsync(normals_out, a.normals_out, (size_t)n * 24, cudaMemcpyDeviceToHost, ctx->stream));
-        if (curvature_out) PB_CUDA(cudaMemcpyAsync(curvature_out, a.curvature_out, (size_t)n * 8, cudaMemcpyDeviceToHost, ctx->stream));
+        if (idx_out) PB_CUDA(cudaMemcpyAsync(idx_out, a.idx_out, (size_t)nq * k * 4, cudaMemcpyDeviceToHost, ctx->stream));
+        if (d2_out) PB_CUDA(cudaMemcpyAsync(d2_out, a.d2_out, (size_t)nq * k * 8, cudaMemcpyDeviceToHost, ctx->stream));
+        if (counts_out) PB_CUDA(cudaMemcpyAsync(counts_out, a.counts_out, (size_t)nq * 4, cudaMemcpyDeviceToHost, ctx->stream));
+        if (normals_out) PB_CUDA(cudaMemcpyAsync(normals_out, a.normals_out, (size_t)nq * 24, cudaMemcpyDeviceToHost, ctx->stream));
+        if (curvature_out) PB_CUDA(cudaMemcpyAsync(curvature_out, a.curvature_out, (size_t)nq * 8, cudaMemcpyDeviceToHost, ctx->stream));
         PB_CUDA(cudaStreamSynchronize(ctx->stream));  // host results must be complete on return
     }
     // the tree and staging buffers are stream-ordered temporaries (DevTmp): released behind the kernels that use them
@@ -774,30 +851,42 @@ using namespace pb200;
 
 extern "C" {
 
-int pb200_knn(pb200_ctx* ctx, const pb200_buffer_desc* buf, uint32_t k, uint32_t* idx_out, double* d2_out) {
-    if (!ctx || !idx_out) return set_error(PB200_ERR_INVALID, "null argument");
+int pb200_knn_range(pb200_ctx* ctx, const pb200_buffer_desc* buf, uint32_t k, uint64_t first_query, uint64_t n_queries,
+                    uint32_t* idx_out, double* d2_out) {
+    if (!ctx || !buf || (!idx_out && n_queries)) return set_error(PB200_ERR_INVALID, "null argument");
     int mode = 0;
 #ifdef PB200_KNN_DIAGNOSTICS  // diagnostic builds only (make KNN_DIAGNOSTICS=1): idx_out[3*i..] = traversal counters
     if (ctx->knn_stats && k > 4 && k <= 16) mode = 3;
 #endif
-    return run_query(ctx, buf, mode, k, 0.0, idx_out, d2_out, nullptr, nullptr, nullptr);
+    return run_query(ctx, buf, mode, k, 0.0, first_query, n_queries, idx_out, d2_out, nullptr, nullptr, nullptr);
+}
+
+int pb200_knn(pb200_ctx* ctx, const pb200_buffer_desc* buf, uint32_t k, uint32_t* idx_out, double* d2_out) {
+    if (!ctx || !buf || !idx_out) return set_error(PB200_ERR_INVALID, "null argument");
+    return pb200_knn_range(ctx, buf, k, 0, buf->len, idx_out, d2_out);
 }
 
 int pb200_radius_search(pb200_ctx* ctx, const pb200_buffer_desc* buf, double radius, uint32_t max_neighbors,
                         uint32_t* idx_out, uint32_t* counts_out) {
-    if (!ctx || !idx_out || !counts_out) return set_error(PB200_ERR_INVALID, "null argument");
+    if (!ctx || !buf || !idx_out || !counts_out) return set_error(PB200_ERR_INVALID, "null argument");
     if (!(radius >= 0.0)) return set_error(PB200_ERR_INVALID, "radius must be >= 0");
-    return run_query(ctx, buf, 1, max_neighbors, radius, idx_out, nullptr, counts_out, nullptr, nullptr);
+    return run_query(ctx, buf, 1, max_neighbors, radius, 0, buf->len, idx_out, nullptr, counts_out, nullptr, nullptr);
+}
+
+int pb200_compute_normals_range(pb200_ctx* ctx, const pb200_buffer_desc* buf, uint32_t k, uint64_t first_query, uint64_t n_queries,
+                                double* normals_out, double* curvature_out) {
+    if (!ctx || !buf || ((!normals_out || !curvature_out) && n_queries)) return set_error(PB200_ERR_INVALID, "null argument");
+    if (buf->len < 3)  // normal_estimation.rs:86-88
+        return set_error(PB200_ERR_TOO_FEW_POINTS, "The point cloud is too small. Please use a point cloud that has 3 or more points!");
+    if (k < 3)  // :89-91
+        return set_error(PB200_ERR_INVALID, "The k nearest neigbors attribute is too small!");
+    return run_query(ctx, buf, 2, k, 0.0, first_query, n_queries, nullptr, nullptr, nullptr, normals_out, curvature_out);
 }
 
 int pb200_compute_normals(pb200_ctx* ctx, const pb200_buffer_desc* buf, uint32_t k, double* normals_out,
                           double* curvature_out) {
     if (!ctx || !buf || !normals_out || !curvature_out) return set_error(PB200_ERR_INVALID, "null argument");
-    if (buf->len < 3)  // normal_estimation.rs:86-88
-        return set_error(PB200_ERR_TOO_FEW_POINTS, "The point cloud is too small. Please use a point cloud that has 3 or more points!");
-    if (k < 3)  // :89-91
-        return set_error(PB200_ERR_INVALID, "The k nearest neigbors attribute is too small!");
-    return run_query(ctx, buf, 2, k, 0.0, nullptr, nullptr, nullptr, normals_out, curvature_out);
+    return pb200_compute_normals_range(ctx, buf, k, 0, buf->len, normals_out, curvature_out);
 }
 
 }  // extern "C"

@@ -101,6 +101,33 @@ def voxelgrid_filter_sharded(shard, leafsize_x, leafsize_y, leafsize_z, group=No
     return alg.voxelgrid_merge_partials(keys, counts, sums, part.bits, part.cells, ctx)
 
 
+# ---- kNN / normals: replicas only -------------------------------------------------------------------------
+
+def compute_normals_sharded(point_cloud, k_nn, group=None, gather=False, ctx=None):
+    """compute_normals (normal_estimation.rs:79-130) over the ranks of `group`: every rank holds the WHOLE position column
+    (a replica: 2.4 GB per 100 M points), builds the same tree and answers the queries of its own point range
+    (`shard_range`), the `for point in points` loop of :106-127 cut into contiguous pieces.  No exchange is needed for the
+    computation; gather=True all-gathers the slices so that every rank ends up with all normals / curvatures.
+    Returns (normals, curvature, range) -- the rank's slice and the point range it covers (or the full arrays)."""
+    from . import algorithms as alg
+    have = dist.is_available() and dist.is_initialized()
+    world = dist.get_world_size(group) if have else 1
+    rank = dist.get_rank(group) if have else 0
+    n = point_cloud.len()
+    r = shard_range(n, rank, world)
+    normals, curv = alg.compute_normals(point_cloud, k_nn, query_range=r, ctx=ctx)
+    if not gather or world == 1:
+        return normals, curv, r
+    sizes = [len(shard_range(n, q, world)) for q in range(world)]
+    dev = normals.device
+    on_gpu = dist.get_backend(group) == "nccl"
+    outs_n = [torch.empty((sz, 3), dtype=torch.float64, device=dev if on_gpu else "cpu") for sz in sizes]
+    outs_c = [torch.empty(sz, dtype=torch.float64, device=dev if on_gpu else "cpu") for sz in sizes]
+    dist.all_gather(outs_n, normals if on_gpu else normals.cpu(), group=group)
+    dist.all_gather(outs_c, curv if on_gpu else curv.cpu(), group=group)
+    return torch.cat(outs_n).to(dev), torch.cat(outs_c).to(dev), range(0, n)
+
+
 # ---- peer-memory communicator: the global AABB inside the convert kernel (no NCCL on the data path) ----------------
 
 class PeerComm:

@@ -81,6 +81,46 @@ def test_knn_larger_cloud_deep_tree():
     assert np.array_equal(idx.cpu().numpy().view(np.uint32), oidx)
 
 
+def test_knn_one_million_points_full_parity_tie_order_unpinned():
+    """1 M points of the C4 stream, k = 16: EVERY neighbour index and distance against the oracle's exact kd-tree
+    (itself checked against the brute force in the CPU suite).  The order inside exact distance ties is (d2, index) on
+    both sides; the reference's kd-tree 0.3.0 is not in /root/reference, so that tie order is unpinned."""
+    n = 1_000_000
+    pts = O.gen_terrain_positions(0, n)
+    oidx, od2 = O.knn_kdtree(pts, 16)
+    src = pb.algorithms.synth_terrain_positions(n)
+    idx, d2 = knn(src, 16)
+    assert torch.equal(d2.cpu(), torch.from_numpy(od2))
+    assert np.array_equal(idx.cpu().numpy().view(np.uint32), oidx)
+    # normals of the same cloud: bit-exact normals, curvature within 1e-9 relative (device atan2/cos vs glibc, SURVEY 8d)
+    on, oc = O.compute_normals_kdtree(pts, 16)
+    nrm, curv = compute_normals(src, 16)
+    assert np.array_equal(nrm.cpu().numpy(), on)
+    np.testing.assert_allclose(curv.cpu().numpy(), oc, rtol=1e-9, atol=1e-12)
+
+
+@pytest.mark.parametrize("n,first,count", [(50_000, 0, 50_000), (50_000, 12_345, 6_000), (50_000, 49_990, 10), (50_000, 7, 0),
+                                           (400_000, 300_000, 100_000), (1_000_000, 125_000, 125_000)])
+def test_query_ranges_equal_the_slices_of_the_full_result(n, first, count):
+    """pb200_knn_range / pb200_compute_normals_range (the replicas-only multi-GPU cut: a rank answers the points of its
+    own range against the whole cloud): exactly the rows [first, first + count) of the full result, for ranges at the
+    start, in the middle, at the very end, empty, and 1/8 of a 1 M-point cloud (queries spread over the Morton order)"""
+    pts = O.gen_terrain_positions(0, n)
+    oidx, od2 = O.knn_kdtree(pts, 16, first, first + count)
+    src = pb.algorithms.synth_terrain_positions(n)
+    r = range(first, first + count)
+    idx, d2 = knn(src, 16, query_range=r)
+    assert idx.shape[0] == count
+    assert np.array_equal(d2.cpu().numpy(), od2) and np.array_equal(idx.cpu().numpy().view(np.uint32), oidx)
+    nrm, curv = compute_normals(src, 16, query_range=r)
+    on, oc = O.compute_normals_kdtree(pts, 16, first, first + count)
+    assert np.array_equal(nrm.cpu().numpy(), on)
+    np.testing.assert_allclose(curv.cpu().numpy(), oc, rtol=1e-9, atol=1e-12)
+    with pytest.raises(pb.PastureB200Error) as e:
+        knn(src, 16, query_range=range(n - 5, n + 1))
+    assert e.value.code == -5
+
+
 def test_knn_georeferenced_coordinates():
     """UTM-like magnitudes (5.4e6 m) with decimetre spacing: boxes are f32 intervals relative to the AABB minimum and
     must stay conservative (result bit-exact) -- and a cloud whose points differ only in the last f64 bits"""

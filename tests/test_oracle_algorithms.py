@@ -263,3 +263,29 @@ def test_reproject_epsg4326_epsg3309():  # reprojection.rs:250-337 (assert_appro
     ops, n = O.pipeline_epsg4326_to_3309()
     out = O.reproject(ops, n, pts)
     assert np.all(np.abs(out - expected) < 1e-4), out - expected
+
+
+# ---- the oracle's two kNN implementations pin each other -------------------------------------------------------------
+
+@pytest.mark.parametrize("seed,n,k", [(0, 5000, 16), (1, 777, 3), (2, 40, 64), (3, 9000, 33)])
+def test_kdtree_knn_equals_brute_force(seed, n, k):
+    """po_knn_kdtree (exact kd-tree, the checker for clouds the O(N^2) brute force cannot reach) returns the same indices
+    and bit-identical distances as po_knn_bruteforce, duplicates and exact ties included ((d2, index) order)"""
+    rng = np.random.default_rng(seed)
+    pts = rng.random((n, 3)) * [30.0, 30.0, 2.0]
+    pts[n // 3] = pts[1]
+    pts[n // 2: n // 2 + 7] = pts[2]                      # a cluster of identical points
+    pts[5:25, 2] = 0.5                                    # a plane of equal z: ties in one coordinate
+    bi, bd = O.knn_bruteforce(pts, pts, k)
+    ki, kd = O.knn_kdtree(pts, k, threads=3)
+    assert np.array_equal(bi, ki) and np.array_equal(bd, kd)
+    lo, hi = n // 4, min(n, n // 4 + 50)
+    ri, rd = O.knn_kdtree(pts, k, lo, hi, threads=2)      # query range: rows of the full result
+    assert np.array_equal(ri, bi[lo:hi]) and np.array_equal(rd, bd[lo:hi])
+
+
+def test_kdtree_normals_equal_brute_force_normals():
+    pts = O.gen_terrain_positions(0, 4000)
+    n1, c1 = O.compute_normals(pts, 16)
+    n2, c2 = O.compute_normals_kdtree(pts, 16)
+    assert np.array_equal(n1, n2) and np.array_equal(c1, c2)
