@@ -177,6 +177,8 @@ extern "C" {
                                   out_max: *mut f64, is_some: *mut c_int) -> c_int;
     pub fn pb200_minmax_attribute(ctx: *mut pb200_ctx, buf: *const pb200_buffer_desc, name: *const c_char, dtype: u32,
                                   out_min: *mut c_void, out_max: *mut c_void, is_some: *mut c_int) -> c_int;
+    pub fn pb200_minmax_attribute_partial(ctx: *mut pb200_ctx, buf: *const pb200_buffer_desc, name: *const c_char, dtype: u32,
+                                          out_min: *mut c_void, out_max: *mut c_void, is_some: *mut c_int) -> c_int;
     pub fn pb200_expand_bits_by_3(v: u64) -> u64;
     pub fn pb200_morton_codes(ctx: *mut pb200_ctx, buf: *const pb200_buffer_desc, bmin: *const f64, bmax: *const f64,
                               codes_out: *mut u64) -> c_int;
@@ -197,6 +199,10 @@ extern "C" {
                                  curvature_out: *mut f64) -> c_int;
     pub fn pb200_proj_pipeline_for_crs(source_crs: *const c_char, target_crs: *const c_char, ops: *mut pb200_proj_op,
                                        cap: u32) -> c_int;
+    pub fn pb200_proj_op_tmerc(a: f64, inv_f: f64, lat0_deg: f64, lon0_deg: f64, k0: f64, false_easting: f64, false_northing: f64,
+                               inverse: c_int, out: *mut pb200_proj_op) -> c_int;
+    pub fn pb200_proj_op_helmert(tx: f64, ty: f64, tz: f64, rx_arcsec: f64, ry_arcsec: f64, rz_arcsec: f64, ds_ppm: f64,
+                                 coordinate_frame: c_int, out: *mut pb200_proj_op) -> c_int;
     pub fn pb200_reproject(ctx: *mut pb200_ctx, src: *const pb200_buffer_desc, dst_or_null: *const pb200_buffer_desc,
                            ops: *const pb200_proj_op, n_ops: u32) -> c_int;
     pub fn pb200_synth_las_fmt0_records(ctx: *mut pb200_ctx, device_out: *mut c_void, first_index: u64, n: u64, seed: u64) -> c_int;

@@ -254,6 +254,14 @@ int pb200_calculate_bounds(pb200_ctx* ctx, const pb200_buffer_desc* buf, double 
  * (name, dtype) must be in the layout (the reference's converting branch always panics, buffer_views.rs:549). */
 int pb200_minmax_attribute(pb200_ctx* ctx, const pb200_buffer_desc* buf, const char* name, uint32_t dtype,
                            void* out_min, void* out_max, int* is_some);
+/* The fold of minmax_attribute over a shard that is NOT the beginning of the cloud ("minmax ints: same with the
+ * attribute's dtype"): the reference seeds (min, max) with the cloud's FIRST value and then only replaces on strict
+ * comparisons (math/minmax.rs:62-96), so later NaNs are ignored while a NaN seed sticks.  This entry point is the
+ * continuation: NaN never enters, and a float component without any non-NaN value comes back as (+MAX, -MAX).  The
+ * ranks' partial results combine by min / max; the rank holding point 0 applies the seed rule (pb200_minmax_attribute on
+ * its shard, or the sharding helper's explicit seed exchange). */
+int pb200_minmax_attribute_partial(pb200_ctx* ctx, const pb200_buffer_desc* buf, const char* name, uint32_t dtype,
+                                   void* out_min, void* out_max, int* is_some);
 /* expand_bits_by_3, pasture-core/src/math/bitmanip.rs:2-10 (host) and 63-bit Morton codes of positions
  * quantised to 21 bits/axis inside [bmin,bmax] (device; codes_out: len u64 in buf's memspace) */
 uint64_t pb200_expand_bits_by_3(uint64_t v);
@@ -400,19 +408,45 @@ int pb200_ransac(pb200_ctx* ctx, const pb200_buffer_desc* buf, int kind, double 
                  uint64_t seed, double* model_out, uint64_t* ranking_out, uint64_t* indices_out, uint64_t capacity);
 
 /* ---- reprojection, pasture-algorithms/src/reprojection.rs:132-146,201-227 -------------------------- */
-/* PROJ is a closed-source-to-us dependency here; the GPU path takes an enumerated operation pipeline. */
+/* The reference hands two CRS strings to PROJ (proj-sys 0.22, not part of the checkout) and calls proj_trans per point.
+ * PROJ strings cannot run on the GPU: the boundary takes an enumerated operation pipeline over (v0, v1, v2), either
+ * composed by hand or by pb200_proj_pipeline_for_crs for the CRS pairs it knows.  Parameters (p[]) per kind:
+ *   AFFINE             v := A v + b                    p[0..8] = A row-major, p[9..11] = b   (Helmert: pb200_proj_op_helmert)
+ *   GEODETIC_TO_ECEF   (lat deg, lon deg, h) -> XYZ    p = a, 1/f
+ *   ECEF_TO_GEODETIC   XYZ -> (lat rad, lon rad, h)    p = a, 1/f
+ *   ALBERS_FWD         (lat rad, lon rad) -> (E, N)    p = a, 1/f, phi1, phi2, phi0, lam0, FE, FN (radians), Snyder 14-*
+ *   SET_Z              v2 := the input z
+ *   WEBMERC_FWD / _INV (lat deg, lon deg) <-> (E, N)   EPSG method 1024 (Popular Visualisation Pseudo Mercator)
+ *   TMERC_FWD / _INV   (lat rad, lon rad) <-> (E, N)   p = a, 1/f, lat0, lon0 (radians), k0, FE, FN; EPSG method 9807, the
+ *                                                      Krueger-series ("JHS") formulas of IOGP Guidance Note 7-2
+ *   DEG2RAD_LATLON / RAD2DEG_LATLON   scale v0, v1
+ * Pinning: EPSG:4326 -> EPSG:3309 by the reference's own known-answer test (reprojection.rs:275-289, 1e-4 m); the Transverse
+ * Mercator, Pseudo-Mercator and Helmert operations by the worked examples of Guidance Note 7-2 and Snyder's UTM example
+ * (tests/test_oracle_algorithms.py), since libproj itself is not available here.  Everything else: parity unpinned. */
 enum pb200_proj_kind {
     PB200_PROJ_AFFINE = 1, PB200_PROJ_GEODETIC_TO_ECEF = 2, PB200_PROJ_ECEF_TO_GEODETIC = 3,
-    PB200_PROJ_ALBERS_FWD = 4, PB200_PROJ_SET_Z = 5, PB200_PROJ_WEBMERC_FWD = 6, PB200_PROJ_TMERC_FWD = 7
+    PB200_PROJ_ALBERS_FWD = 4, PB200_PROJ_SET_Z = 5, PB200_PROJ_WEBMERC_FWD = 6, PB200_PROJ_TMERC_FWD = 7,
+    PB200_PROJ_DEG2RAD_LATLON = 8, PB200_PROJ_RAD2DEG_LATLON = 9, PB200_PROJ_TMERC_INV = 10, PB200_PROJ_WEBMERC_INV = 11
 };
 typedef struct pb200_proj_op {
     uint32_t kind;
     uint32_t _pad;
     double p[12];
 } pb200_proj_op;
-/* fills ops (capacity >= 8) for a known CRS pair ("EPSG:4326" -> "EPSG:3309", "EPSG:4326" -> "EPSG:3857");
- * returns the op count or PB200_ERR_UNSUPPORTED */
+/* fills ops (capacity >= 8) for a known CRS pair and returns the op count, or PB200_ERR_UNSUPPORTED:
+ *   EPSG:4326 -> EPSG:3309;  EPSG:4326 <-> EPSG:3857;  EPSG:4326 <-> UTM on WGS 84 (EPSG:32601-32660, 32701-32760) and on
+ *   ETRS89 (EPSG:25828-25838);  UTM zone <-> UTM zone.  Geographic coordinates are (lat, lon) in degrees (EPSG axis order,
+ *   as in the reference's tests, reprojection.rs:266-272); z passes through. */
 int pb200_proj_pipeline_for_crs(const char* source_crs, const char* target_crs, pb200_proj_op* ops, uint32_t cap);
+/* a Transverse Mercator op for any zone / national grid: ellipsoid (a, 1/f), natural origin (degrees), scale factor,
+ * false easting / northing; inverse != 0: (E, N) -> (lat rad, lon rad) */
+int pb200_proj_op_tmerc(double a, double inv_f, double lat0_deg, double lon0_deg, double k0, double false_easting, double false_northing,
+                        int inverse, pb200_proj_op* out);
+/* a 7-parameter Helmert transformation of geocentric coordinates as an AFFINE op: translations in metres, rotations in
+ * arc-seconds, scale difference in ppm; coordinate_frame == 0: Position Vector convention (EPSG method 1033),
+ * != 0: Coordinate Frame rotation (EPSG 1032) */
+int pb200_proj_op_helmert(double tx, double ty, double tz, double rx_arcsec, double ry_arcsec, double rz_arcsec, double ds_ppm,
+                          int coordinate_frame, pb200_proj_op* out);
 /* reproject_point_cloud_within (dst == NULL) / _between (PB200_ERR_RANGE if lengths differ) on POSITION_3D */
 int pb200_reproject(pb200_ctx* ctx, const pb200_buffer_desc* src, const pb200_buffer_desc* dst_or_null,
                     const pb200_proj_op* ops, uint32_t n_ops);

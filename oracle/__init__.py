@@ -598,6 +598,41 @@ def pipeline_epsg4326_to_3309():
     return ops, n
 
 
+PROJ_AFFINE, PROJ_GEODETIC_TO_ECEF, PROJ_ECEF_TO_GEODETIC, PROJ_ALBERS_FWD, PROJ_SET_Z, PROJ_WEBMERC_FWD, PROJ_TMERC_FWD = range(1, 8)
+PROJ_DEG2RAD_LATLON, PROJ_RAD2DEG_LATLON, PROJ_TMERC_INV, PROJ_WEBMERC_INV = 8, 9, 10, 11
+WGS84, GRS80 = (6378137.0, 298.257223563), (6378137.0, 298.257222101)
+
+
+def make_pipeline(steps):
+    """[(kind, [params...]), ...] -> (ops array, n)"""
+    ops = (ProjOp * 8)()
+    for i, (kind, params) in enumerate(steps):
+        ops[i].kind = kind
+        for j, v in enumerate(params):
+            ops[i].p[j] = float(v)
+    return ops, len(steps)
+
+
+def tmerc_step(ellipsoid, lat0_deg, lon0_deg, k0, fe, fn, inverse=False):
+    import math
+    return (PROJ_TMERC_INV if inverse else PROJ_TMERC_FWD,
+            [ellipsoid[0], ellipsoid[1], math.radians(lat0_deg), math.radians(lon0_deg), k0, fe, fn])
+
+
+def utm_step(zone, south=False, ellipsoid=WGS84, inverse=False):
+    """UTM zone `zone` (EPSG:326zz / 327zz on WGS 84, 258zz on GRS 1980): central meridian 6 zone - 183 deg, k0 0.9996,
+    FE 500 000 m, FN 0 / 10 000 000 m (south)"""
+    return tmerc_step(ellipsoid, 0.0, 6.0 * zone - 183.0, 0.9996, 500000.0, 10000000.0 if south else 0.0, inverse)
+
+
+def helmert_step(tx, ty, tz, rx_as, ry_as, rz_as, ds_ppm):
+    """7-parameter Position Vector transformation (EPSG method 1033, GN7-2 4.3.3) as an affine step"""
+    import math
+    s = math.pi / (180.0 * 3600.0)
+    rx, ry, rz, m = rx_as * s, ry_as * s, rz_as * s, 1.0 + ds_ppm * 1e-6
+    return (PROJ_AFFINE, [m, -m * rz, m * ry, m * rz, m, -m * rx, -m * ry, m * rx, m, tx, ty, tz])
+
+
 def reproject(ops, n_ops, xyz):
     xyz = np.ascontiguousarray(xyz, dtype=np.float64)
     out = np.zeros_like(xyz)

@@ -1432,13 +1432,6 @@ static double albers_q(double e, double sinphi) { /* Snyder 3-12 */
     return (1.0 - e * e) * (sinphi / (1.0 - es * es) - (1.0 / (2.0 * e)) * log((1.0 - es) / (1.0 + es)));
 }
 
-static double tmerc_M(double a, double e2, double phi) { /* Snyder 3-21 */
-    double e4 = e2 * e2, e6 = e4 * e2;
-    return a * ((1.0 - e2 / 4.0 - 3.0 * e4 / 64.0 - 5.0 * e6 / 256.0) * phi -
-                (3.0 * e2 / 8.0 + 3.0 * e4 / 32.0 + 45.0 * e6 / 1024.0) * sin(2.0 * phi) +
-                (15.0 * e4 / 256.0 + 45.0 * e6 / 1024.0) * sin(4.0 * phi) - (35.0 * e6 / 3072.0) * sin(6.0 * phi));
-}
-
 void po_reproject(const po_proj_op* ops, uint32_t n_ops, const double* in, double* out, uint64_t n) {
     for (uint64_t i = 0; i < n; ++i) {
         double v[3] = {in[3 * i], in[3 * i + 1], in[3 * i + 2]};
@@ -1503,17 +1496,58 @@ void po_reproject(const po_proj_op* ops, uint32_t n_ops, const double* in, doubl
                     v[1] = R * log(tan(PO_PI / 4.0 + lat / 2.0));
                     break;
                 }
-                case PO_PROJ_TMERC_FWD: { /* Snyder 8-9..8-15 */
-                    double a = p[0], f = 1.0 / p[1], e2 = f * (2.0 - f), ep2 = e2 / (1.0 - e2);
-                    double lat0 = p[2], lon0 = p[3], k0 = p[4], x0 = p[5], y0 = p[6];
-                    double phi = v[0], lam = v[1];
-                    double sp = sin(phi), cp = cos(phi), tp = tan(phi);
-                    double N = a / sqrt(1.0 - e2 * sp * sp);
-                    double T = tp * tp, Cq = ep2 * cp * cp, A = (lam - lon0) * cp;
-                    double Mv = tmerc_M(a, e2, phi), M0 = tmerc_M(a, e2, lat0);
-                    double A2 = A * A, A3 = A2 * A, A4 = A3 * A, A5 = A4 * A, A6 = A5 * A;
-                    v[0] = x0 + k0 * N * (A + (1.0 - T + Cq) * A3 / 6.0 + (5.0 - 18.0 * T + T * T + 72.0 * Cq - 58.0 * ep2) * A5 / 120.0);
-                    v[1] = y0 + k0 * (Mv - M0 + N * tp * (A2 / 2.0 + (5.0 - T + 9.0 * Cq + 4.0 * Cq * Cq) * A4 / 24.0 + (61.0 - 58.0 * T + T * T + 600.0 * Cq - 330.0 * ep2) * A6 / 720.0));
+                case PO_PROJ_TMERC_FWD: case PO_PROJ_TMERC_INV: {
+                    /* EPSG method 9807 as written in IOGP Guidance Note 7-2 (3.5.3.1, "JHS formulas"); every constant is
+                     * recomputed per point from the public parameters a, 1/f, lat0, lon0, k0, FE, FN (radians) */
+                    double a = p[0], f = 1.0 / p[1], lat0 = p[2], lon0 = p[3], k0 = p[4], fe = p[5], fn = p[6];
+                    double n = f / (2.0 - f), n2 = n * n, n3 = n2 * n, n4 = n2 * n2, e = sqrt(f * (2.0 - f));
+                    double B = a / (1.0 + n) * (1.0 + n2 / 4.0 + n4 / 64.0);
+                    double h[4] = {n / 2.0 - 2.0 / 3.0 * n2 + 5.0 / 16.0 * n3 + 41.0 / 180.0 * n4,
+                                   13.0 / 48.0 * n2 - 3.0 / 5.0 * n3 + 557.0 / 1440.0 * n4,
+                                   61.0 / 240.0 * n3 - 103.0 / 140.0 * n4, 49561.0 / 161280.0 * n4};
+                    double M0 = 0.0;
+                    if (lat0 != 0.0) {
+                        double Q0 = asinh(tan(lat0)) - e * atanh(e * sin(lat0));
+                        double x0 = atan(sinh(Q0)), x = x0;
+                        for (int j = 1; j <= 4; ++j) x += h[j - 1] * sin(2.0 * j * x0);
+                        M0 = B * x;
+                    }
+                    if (ops[k].kind == PO_PROJ_TMERC_FWD) {
+                        double Q = asinh(tan(v[0])) - e * atanh(e * sin(v[0]));
+                        double beta = atan(sinh(Q));
+                        double eta0 = atanh(cos(beta) * sin(v[1] - lon0));
+                        double xi0 = asin(sin(beta) * cosh(eta0));
+                        double xi = xi0, eta = eta0;
+                        for (int j = 1; j <= 4; ++j) {
+                            xi += h[j - 1] * sin(2.0 * j * xi0) * cosh(2.0 * j * eta0);
+                            eta += h[j - 1] * cos(2.0 * j * xi0) * sinh(2.0 * j * eta0);
+                        }
+                        v[0] = fe + k0 * B * eta;
+                        v[1] = fn + k0 * (B * xi - M0);
+                    } else {
+                        double hi[4] = {n / 2.0 - 2.0 / 3.0 * n2 + 37.0 / 96.0 * n3 - 1.0 / 360.0 * n4,
+                                        1.0 / 48.0 * n2 + 1.0 / 15.0 * n3 - 437.0 / 1440.0 * n4,
+                                        17.0 / 480.0 * n3 - 37.0 / 840.0 * n4, 4397.0 / 161280.0 * n4};
+                        double eta = (v[0] - fe) / (B * k0), xi = ((v[1] - fn) + k0 * M0) / (B * k0);
+                        double xi0 = xi, eta0 = eta;
+                        for (int j = 1; j <= 4; ++j) {
+                            xi0 -= hi[j - 1] * sin(2.0 * j * xi) * cosh(2.0 * j * eta);
+                            eta0 -= hi[j - 1] * cos(2.0 * j * xi) * sinh(2.0 * j * eta);
+                        }
+                        double beta = asin(sin(xi0) / cosh(eta0));
+                        double Qp = asinh(tan(beta)), Q = Qp;
+                        for (int it = 0; it < 12; ++it) Q = Qp + e * atanh(e * tanh(Q));
+                        v[0] = atan(sinh(Q));
+                        v[1] = lon0 + asin(tanh(eta0) / cos(beta));
+                    }
+                    break;
+                }
+                case PO_PROJ_DEG2RAD_LATLON: v[0] *= PO_PI / 180.0; v[1] *= PO_PI / 180.0; break;
+                case PO_PROJ_RAD2DEG_LATLON: v[0] *= 180.0 / PO_PI; v[1] *= 180.0 / PO_PI; break;
+                case PO_PROJ_WEBMERC_INV: { /* GN7-2 3.5.1.2 reverse: D = -N/a, lat = pi/2 - 2 atan(e^D) */
+                    double R = 6378137.0;
+                    double lon = v[0] / R, lat = PO_PI / 2.0 - 2.0 * atan(exp(-v[1] / R));
+                    v[0] = lat * (180.0 / PO_PI); v[1] = lon * (180.0 / PO_PI);
                     break;
                 }
                 default: break;

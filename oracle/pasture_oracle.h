@@ -210,7 +210,10 @@ enum {
     PO_PROJ_ALBERS_FWD = 4,      /* (lat_rad, lon_rad, h) -> (E, N, h) params: a, inv_f, phi1, phi2, phi0, lam0, x0, y0 (radians) */
     PO_PROJ_SET_Z = 5,           /* z := saved input z (z passthrough)  */
     PO_PROJ_WEBMERC_FWD = 6,     /* (lat_deg, lon_deg, h) -> EPSG:3857 */
-    PO_PROJ_TMERC_FWD = 7        /* (lat_rad, lon_rad, h) -> (E,N,h) params: a, inv_f, lat0, lon0, k0, x0, y0 */
+    PO_PROJ_TMERC_FWD = 7,       /* (lat_rad, lon_rad, h) -> (E,N,h) params: a, inv_f, lat0, lon0, k0, FE, FN; GN7-2 JHS formulas */
+    PO_PROJ_DEG2RAD_LATLON = 8, PO_PROJ_RAD2DEG_LATLON = 9,
+    PO_PROJ_TMERC_INV = 10,      /* (E,N,h) -> (lat_rad, lon_rad, h), same params */
+    PO_PROJ_WEBMERC_INV = 11     /* EPSG:3857 -> (lat_deg, lon_deg, h) */
 };
 typedef struct {
     uint32_t kind;

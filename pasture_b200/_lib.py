@@ -123,6 +123,7 @@ SIGNATURES = {
     "pb200_filter_into": (i32, [vp, BD, vp, BD, C.POINTER(u64)]),
     "pb200_calculate_bounds": (i32, [vp, BD, PD, PD, C.POINTER(i32)]),
     "pb200_minmax_attribute": (i32, [vp, BD, C.c_char_p, u32, vp, vp, C.POINTER(i32)]),
+    "pb200_minmax_attribute_partial": (i32, [vp, BD, C.c_char_p, u32, vp, vp, C.POINTER(i32)]),
     "pb200_expand_bits_by_3": (u64, [u64]),
     "pb200_morton_codes": (i32, [vp, BD, PD, PD, vp]),
     "pb200_voxelgrid_filter": (i32, [vp, BD, dbl, dbl, dbl, vp, C.c_int32, C.c_int32, PVP]),
@@ -149,6 +150,8 @@ SIGNATURES = {
     "pb200_radius_search": (i32, [vp, BD, dbl, u32, vp, vp]),
     "pb200_compute_normals": (i32, [vp, BD, u32, vp, vp]),
     "pb200_proj_pipeline_for_crs": (i32, [C.c_char_p, C.c_char_p, C.POINTER(ProjOp), u32]),
+    "pb200_proj_op_tmerc": (i32, [dbl, dbl, dbl, dbl, dbl, dbl, dbl, i32, C.POINTER(ProjOp)]),
+    "pb200_proj_op_helmert": (i32, [dbl, dbl, dbl, dbl, dbl, dbl, dbl, i32, C.POINTER(ProjOp)]),
     "pb200_reproject": (i32, [vp, BD, BD, C.POINTER(ProjOp), u32]),
     "pb200_synth_las_fmt0_records": (i32, [vp, vp, u64, u64, u64]),
     "pb200_synth_terrain_positions": (i32, [vp, vp, u64, u64, u64]),

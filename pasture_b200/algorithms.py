@@ -46,13 +46,15 @@ def calculate_bounds(buffer, ctx=None):
     return AABB(mn, mx) if some.value else None
 
 
-def minmax_attribute(buffer, attribute, ctx=None):
-    """minmax.rs:13-51 -> (min, max) of attribute.datatype() or None"""
+def minmax_attribute(buffer, attribute, ctx=None, partial=False):
+    """minmax.rs:13-51 -> (min, max) of attribute.datatype() or None.  partial=True: the continuation fold for a shard that
+    does not start the cloud (NaN never enters; see pb200_minmax_attribute_partial and sharding.minmax_attribute_sharded)"""
     ctx = context_for(ctx, buffer)
     d = buffer.desc()
     mn, mx, some = np.zeros(32, np.uint8), np.zeros(32, np.uint8), C.c_int(0)
-    check(lib().pb200_minmax_attribute(ctx._h, C.byref(d), attribute.name().encode(), int(attribute.datatype()),
-                                       C.c_void_p(mn.ctypes.data), C.c_void_p(mx.ctypes.data), C.byref(some)))
+    fn = lib().pb200_minmax_attribute_partial if partial else lib().pb200_minmax_attribute
+    check(fn(ctx._h, C.byref(d), attribute.name().encode(), int(attribute.datatype()),
+             C.c_void_p(mn.ctypes.data), C.c_void_p(mx.ctypes.data), C.byref(some)))
     if not some.value:
         return None
     dt = attribute.datatype()

@@ -66,6 +66,16 @@ class _BufferBase:
     def _memspace(self):
         return DEVICE if self._device.type == "cuda" else HOST
 
+    def slice_first(self, attribute):
+        """typed value of the attribute in point 0 (one small copy; the seed of minmax.rs' fold)"""
+        idx = self._layout.index_of(attribute)
+        m = self._layout.at(idx)
+        if hasattr(self, "columns"):
+            raw = self.columns[idx][: m.size()]
+        else:
+            raw = self.data[m.offset(): m.offset() + m.size()]
+        return _typed(raw.cpu().numpy().reshape(1, m.size()), m.datatype(), 1)[0]
+
     def view_attribute(self, attribute):
         """typed host copy of one attribute (AttributeView, buffer_views.rs:291). name + datatype must match."""
         if isinstance(attribute, PointAttributeDefinition):

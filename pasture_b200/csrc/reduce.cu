@@ -314,8 +314,21 @@ int pb200_calculate_bounds(pb200_ctx* ctx, const pb200_buffer_desc* buf, double 
     return PB200_OK;
 }
 
+static int minmax_attribute_impl(pb200_ctx* ctx, const pb200_buffer_desc* buf, const char* name, uint32_t dtype, bool seed_rule,
+                                 void* out_min, void* out_max, int* is_some);
+
 int pb200_minmax_attribute(pb200_ctx* ctx, const pb200_buffer_desc* buf, const char* name, uint32_t dtype,
                            void* out_min, void* out_max, int* is_some) {
+    return minmax_attribute_impl(ctx, buf, name, dtype, true, out_min, out_max, is_some);
+}
+
+int pb200_minmax_attribute_partial(pb200_ctx* ctx, const pb200_buffer_desc* buf, const char* name, uint32_t dtype,
+                                   void* out_min, void* out_max, int* is_some) {
+    return minmax_attribute_impl(ctx, buf, name, dtype, false, out_min, out_max, is_some);
+}
+
+static int minmax_attribute_impl(pb200_ctx* ctx, const pb200_buffer_desc* buf, const char* name, uint32_t dtype, bool seed_rule,
+                                 void* out_min, void* out_max, int* is_some) {
     if (!ctx || !name || !out_min || !out_max || !is_some) return set_error(PB200_ERR_INVALID, "null argument");
     PB_TRY(validate_desc(buf, "buffer"));
     *is_some = 0;
@@ -334,7 +347,8 @@ int pb200_minmax_attribute(pb200_ctx* ctx, const pb200_buffer_desc* buf, const c
     unsigned long long keys[6];
     PB_TRY(reduce_attribute_keys(ctx, buf, idx, keys));
     uint8_t first[32];
-    PB_TRY(read_first_element(ctx, buf, idx, first));
+    memset(first, 0, sizeof first);  // (0.0 is not NaN: without the seed rule nothing below replaces a result)
+    if (seed_rule) PB_TRY(read_first_element(ctx, buf, idx, first));
     for (int c = 0; c < nc; ++c) {
         uint8_t* omn = (uint8_t*)out_min + c * cs;
         uint8_t* omx = (uint8_t*)out_max + c * cs;

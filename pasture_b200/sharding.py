@@ -101,6 +101,81 @@ def voxelgrid_filter_sharded(shard, leafsize_x, leafsize_y, leafsize_z, group=No
     return alg.voxelgrid_merge_partials(keys, counts, sums, part.bits, part.cells, ctx)
 
 
+# ---- minmax_attribute over point-range shards ("minmax ints: same with the attribute's dtype") --------------
+
+def combine_minmax(local, first_value, attribute, group=None, device="cpu"):
+    """The exchange step of minmax_attribute_sharded (host logic, any backend).  `local` = this rank's NaN-ignoring
+    (min, max) in the attribute's dtype or None for an empty shard, `first_value` = the attribute of the shard's first point
+    (None for an empty shard).  ONE all-reduce(MIN) over [min, -max] (floats, as f64) or over the order-preserving int64
+    images of the values (integers of every width, u64 included) plus one small all-gather for the seed rule."""
+    import numpy as np
+    from .containers import _NP, _VEC3
+    have = dist.is_available() and dist.is_initialized()
+    world = dist.get_world_size(group) if have else 1
+    dt = attribute.datatype()
+    comp = _NP.get(dt) or _NP[_VEC3[dt]]
+    nc = 1 if dt in _NP else 3
+    is_float = np.issubdtype(comp, np.floating)
+    flip = comp == np.uint64  # u64 -> int64 with the sign bit flipped: order preserving
+
+    def enc(v):
+        v = np.atleast_1d(np.asarray(v, dtype=comp))
+        return (v ^ np.uint64(1 << 63)).view(np.int64) if flip else v.astype(np.int64)
+
+    def dec(v):
+        return (v.view(np.uint64) ^ np.uint64(1 << 63)).astype(comp) if flip else v.astype(comp)
+    if is_float:
+        vec = np.full(2 * nc, F64_MAX)
+        if local is not None:
+            mn, mx = (np.atleast_1d(np.asarray(v, dtype=np.float64)) for v in local)
+            vec = np.concatenate([mn, -mx])
+        t = torch.tensor(vec, dtype=torch.float64, device=device)
+    else:
+        big = np.iinfo(np.int64).max
+        vec = np.full(2 * nc, big, np.int64)
+        if local is not None:  # the max travels as ~v = -(v + 1): no overflow at the extremes, one MIN reduces both
+            vec = np.concatenate([enc(local[0]), ~enc(local[1])])
+        t = torch.tensor(vec, dtype=torch.int64, device=device)
+    seed_nan = [0.0] * nc
+    if first_value is not None and is_float:
+        seed_nan = [1.0 if np.isnan(x) else 0.0 for x in np.atleast_1d(np.asarray(first_value, dtype=np.float64)).reshape(nc)]
+    meta = torch.tensor([0.0 if first_value is None else 1.0] + seed_nan, dtype=torch.float64, device=device)
+    if world > 1:
+        dist.all_reduce(t, op=dist.ReduceOp.MIN, group=group)
+        metas = [torch.zeros_like(meta) for _ in range(world)]
+        dist.all_gather(metas, meta, group=group)
+    else:
+        metas = [meta]
+    metas = [m.cpu().numpy() for m in metas]
+    first = next((m for m in metas if m[0] > 0), None)  # rank order = point order: the first non-empty shard holds point 0
+    if first is None:
+        return None  # minmax.rs:14-16
+    r = t.cpu().numpy()
+    if is_float:
+        mn, mx = r[:nc].copy(), -r[nc:]
+        for c in range(nc):
+            if first[1 + c] > 0:  # a NaN seed is never replaced (math/minmax.rs:62-96)
+                mn[c] = mx[c] = np.nan
+        mn, mx = mn.astype(comp), mx.astype(comp)
+    else:
+        mn, mx = dec(r[:nc].copy()), dec(~r[nc:])
+    return (mn[0], mx[0]) if nc == 1 else (mn, mx)
+
+
+def minmax_attribute_sharded(buffer, attribute, group=None, ctx=None):
+    """minmax_attribute::<T> (pasture-algorithms/src/minmax.rs:13-51) of a cloud sharded by point range: every rank folds its
+    shard on its GPU (NaN ignored: pb200_minmax_attribute_partial) and `combine_minmax` exchanges the partial results and
+    restores the reference's seed rule -- (min, max) start from the cloud's first value and a NaN seed is never replaced --
+    from the first point of the first non-empty shard.  Returns (min, max) in the attribute's dtype on every rank, or None
+    for an empty cloud."""
+    from . import algorithms as alg
+    have = dist.is_available() and dist.is_initialized()
+    on_gpu = have and dist.get_backend(group) == "nccl"
+    local = alg.minmax_attribute(buffer, attribute, ctx=ctx, partial=True) if buffer.len() else None
+    first = buffer.slice_first(attribute) if buffer.len() else None
+    return combine_minmax(local, first, attribute, group, buffer.device if on_gpu else "cpu")
+
+
 # ---- kNN / normals: replicas only (SURVEY 8e) -------------------------------------------------------------------------
 
 def compute_normals_sharded(point_cloud, k_nn, group=None, gather=False, ctx=None):

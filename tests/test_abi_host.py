@@ -137,3 +137,28 @@ def test_product_does_not_import_oracle():
             if f.endswith((".py", ".cu", ".h", ".cpp", ".hpp")) or f == "Makefile":
                 text = open(os.path.join(dirpath, f)).read()
                 assert "import oracle" not in text and "pasture_oracle" not in text, os.path.join(dirpath, f)
+
+
+def test_projection_pipeline_builder_host_side():
+    """pb200_proj_pipeline_for_crs / pb200_proj_op_* are host-only: known CRS pairs, UTM zone parameters, refusals"""
+    L = _lib.lib()
+    ops = (_lib.ProjOp * 8)()
+    assert L.pb200_proj_pipeline_for_crs(b"EPSG:4326", b"EPSG:3309", ops, 8) == 5
+    assert L.pb200_proj_pipeline_for_crs(b"EPSG:4326", b"EPSG:3857", ops, 8) == 1 and ops[0].kind == 6
+    assert L.pb200_proj_pipeline_for_crs(b"EPSG:3857", b"EPSG:4326", ops, 8) == 1 and ops[0].kind == 11
+    assert L.pb200_proj_pipeline_for_crs(b"EPSG:4326", b"EPSG:32633", ops, 8) == 2
+    assert ops[0].kind == 8 and ops[1].kind == 7
+    a, invf, lat0, lon0, k0, fe, fn = list(ops[1].p)[:7]
+    assert (a, invf, lat0, k0, fe, fn) == (6378137.0, 298.257223563, 0.0, 0.9996, 500000.0, 0.0) and abs(np.degrees(lon0) - 15.0) < 1e-12
+    assert L.pb200_proj_pipeline_for_crs(b"EPSG:4326", b"EPSG:32733", ops, 8) == 2 and ops[1].p[6] == 10000000.0
+    assert L.pb200_proj_pipeline_for_crs(b"EPSG:4326", b"EPSG:25832", ops, 8) == 2 and ops[1].p[1] == 298.257222101
+    assert L.pb200_proj_pipeline_for_crs(b"EPSG:25832", b"EPSG:4326", ops, 8) == 2 and ops[0].kind == 10 and ops[1].kind == 9
+    assert L.pb200_proj_pipeline_for_crs(b"EPSG:32632", b"EPSG:32633", ops, 8) == 2 and ops[0].kind == 10 and ops[1].kind == 7
+    for bad in (b"EPSG:27700", b"EPSG:32661", b"EPSG:25839", b"+proj=utm +zone=32"):
+        assert L.pb200_proj_pipeline_for_crs(b"EPSG:4326", bad, ops, 8) == -10
+    op = _lib.ProjOp()
+    assert L.pb200_proj_op_tmerc(6377563.396, 299.32496, 49.0, -2.0, 0.9996012717, 400000.0, -100000.0, 1, C.byref(op)) == 0
+    assert op.kind == 10 and abs(op.p[2] - np.radians(49.0)) < 1e-15
+    assert L.pb200_proj_op_tmerc(0.0, 299.0, 0.0, 0.0, 1.0, 0.0, 0.0, 0, C.byref(op)) == -8
+    assert L.pb200_proj_op_helmert(1.0, 2.0, 3.0, 0.0, 0.0, 0.0, 0.0, 0, C.byref(op)) == 0
+    assert op.kind == 1 and list(op.p) == [1, 0, 0, 0, 1, 0, 0, 0, 1, 1, 2, 3]

@@ -485,6 +485,52 @@ def test_transform_attribute_and_converting_view(ctx):
             pb.view_attribute_with_conversion(psrc, A.INTENSITY.with_custom_datatype(DT.Vec3f64))
 
 
+@pytest.mark.parametrize("columnar,device", [(False, "cuda"), (True, "cuda"), (True, "cpu")])
+def test_converting_views_and_transform_attribute_against_the_oracle(ctx, columnar, device):
+    """Row W against the ORACLE (not numpy): AttributeViewConverting (buffer_views.rs:533-650) materialises an attribute
+    through the same cast table as the converter -- checked for every scalar and Vec3 view type of arbitrary-bit-pattern
+    sources (NaN, inf, saturation) via the oracle's single-mapping conversion -- and transform_attribute
+    (point_buffer.rs:391-404) equals the oracle's same-layout conversion with the transform on the attribute"""
+    attrs = [("s_f64", O.F64), ("s_i16", O.I16), ("s_u64", O.U64), ("v_f32", O.VEC3F32), ("v_i32", O.VEC3I32), ("Position3D", O.VEC3F64)]
+    ol, pl = util.layouts(attrs, packed=1)
+    n = 4099
+    osrc, _ = util.random_bytes_buffers(ol, pl, n, columnar, seed=91, device=device, finite_floats=True)
+    special = np.array([np.inf, -np.inf, np.nan, 1e300, -1e300, 3e9, -3e9, 70000.5, -0.0, 255.9999])
+    for name in ("s_f64", "v_f32", "Position3D"):  # non-finite / saturating / truncating inputs in known places
+        v = osrc.attribute(name).copy()
+        flat = v.reshape(n, -1)
+        with np.errstate(over="ignore"):
+            flat[10:10 + len(special), 0] = special.astype(flat.dtype)
+        osrc.set_attribute(name, v)
+    psrc = util.to_pb(osrc, pl, device)
+
+    def same(got, want):  # bit-equal, except that a NaN may carry any payload (Rust's `as` does not specify it either)
+        got, want = np.ascontiguousarray(got), np.ascontiguousarray(want)
+        if np.issubdtype(want.dtype, np.floating):
+            return np.array_equal(got, want, equal_nan=True) and np.array_equal(np.signbit(got), np.signbit(want))
+        return np.array_equal(got, want)
+    for name, dtype, _ in [(a, d, 0) for a, d in attrs]:
+        views = range(10) if dtype <= O.F64 else range(O.VEC3U8, O.VEC3F64 + 1)
+        for vd in views:
+            if vd == dtype:
+                continue
+            olt, _ = util.layouts([(name, int(vd))])
+            want = O.OConverter(ol, olt).convert(osrc, True).attribute(name)
+            got = pb.view_attribute_with_conversion(psrc, PointAttributeDefinition(name, int(vd)))
+            assert same(got, want), (name, dtype, vd)
+    # transform_attribute: v * s + o on the Vec3f64 positions, v + c on the f64 scalar, in place; everything else untouched
+    t1, t2 = pb.ScaleOffset((0.01, 0.02, 0.03), (5.0, -6.0, 7.0)), pb.Add((1234.5, 0.0, 0.0))
+    ocv = O.OConverter(ol, ol, with_default=True)
+    ocv.set_custom_mapping_with_transformation(("Position3D", O.VEC3F64), ("Position3D", O.VEC3F64), O.VEC3F64, util.oracle_transform(t1), True)
+    ocv.set_custom_mapping_with_transformation(("s_f64", O.F64), ("s_f64", O.F64), O.F64, util.oracle_transform(t2), True)
+    want = ocv.convert(osrc, columnar)
+    pb.transform_attribute(psrc, A.POSITION_3D, t1)
+    pb.transform_attribute(psrc, PointAttributeDefinition("s_f64", DT.F64), t2)
+    torch.cuda.synchronize()
+    for name, _ in attrs:
+        assert same(psrc.view_attribute(name), want.attribute(name)), name
+
+
 def test_large_range_matches_direct_kernel_and_torch(ctx):
     """6 M points (many tiles per CTA): tile pipeline == direct kernel == a torch recomputation of the positions"""
     n = 6_000_011

@@ -258,7 +258,7 @@ def test_reproject_between_and_errors():  # reprojection.rs:292-367
         reproject_point_cloud_between(src, cloud(np.zeros((2, 3))), "EPSG:4326", "EPSG:3309")
     assert e.value.code == -5
     with pytest.raises(pb.PastureB200Error) as e:
-        reproject_point_cloud_within(src, "EPSG:4326", "EPSG:25832")
+        reproject_point_cloud_within(src, "EPSG:4326", "EPSG:27700")  # needs a datum grid: no built-in pipeline
     assert e.value.code == -10
 
 
@@ -273,6 +273,86 @@ def test_reproject_matches_oracle_on_random_points():
     got = buf.view_attribute(A.POSITION_3D)
     assert np.all(np.abs(got - expect) < 1e-6), np.abs(got - expect).max()
     assert np.array_equal(got[:, 2], pts[:, 2])  # z passes through
+
+
+@pytest.mark.parametrize("target,zone,south,ell", [("EPSG:32632", 32, False, O.WGS84), ("EPSG:32718", 18, True, O.WGS84),
+                                                   ("EPSG:25832", 32, False, O.GRS80), ("EPSG:32601", 1, False, O.WGS84)])
+def test_reproject_utm_zones_match_oracle_both_ways(target, zone, south, ell):
+    """EPSG:4326 <-> UTM (WGS 84 north / south, ETRS89): the GPU pipeline against the oracle's restatement of the Guidance
+    Note 7-2 formulas (pinned on the published worked examples in the CPU suite); points over the whole zone width"""
+    rng = np.random.default_rng(zone)
+    n = 50_000
+    lat = rng.uniform(-79.0, -1.0, n) if south else rng.uniform(1.0, 83.0, n)
+    pts = np.stack([lat, 6.0 * zone - 183.0 + rng.uniform(-3.5, 3.5, n), rng.uniform(-50, 4000, n)], 1)
+    fwd, nf = O.make_pipeline([(O.PROJ_DEG2RAD_LATLON, []), O.utm_step(zone, south, ell)])
+    expect = O.reproject(fwd, nf, pts)
+    buf = cloud(pts)
+    reproject_point_cloud_within(buf, "EPSG:4326", target)
+    torch.cuda.synchronize()
+    got = buf.view_attribute(A.POSITION_3D)
+    assert np.max(np.abs(got - expect)) < 1e-6, np.max(np.abs(got - expect))  # device libm vs glibc: nanometres
+    assert np.array_equal(got[:, 2], pts[:, 2])
+    reproject_point_cloud_within(buf, target, "EPSG:4326")  # and back: the reverse series
+    torch.cuda.synchronize()
+    back = buf.view_attribute(A.POSITION_3D)
+    assert np.max(np.abs(back[:, :2] - pts[:, :2])) < 1e-9
+    inv, ni = O.make_pipeline([O.utm_step(zone, south, ell, inverse=True), (O.PROJ_RAD2DEG_LATLON, [])])
+    assert np.max(np.abs(back - O.reproject(inv, ni, expect))) < 1e-9
+
+
+def test_reproject_published_worked_examples_on_the_gpu():
+    """the worked examples that pin the oracle (IOGP Guidance Note 7-2, Snyder), straight through the GPU kernel"""
+    import ctypes as C
+    from pasture_b200._lib import ProjOp, check, lib
+    ctx = pb.get_context()
+
+    def run(ops, pts):
+        arr = (ProjOp * len(ops))(*ops)
+        buf = cloud(np.asarray(pts, dtype=np.float64))
+        d = buf.desc()
+        check(lib().pb200_reproject(ctx._h, C.byref(d), None, arr, len(ops)))
+        torch.cuda.synchronize()
+        return buf.view_attribute(A.POSITION_3D)
+
+    def tm(a, invf, lat0, lon0, k0, fe, fn, inverse=0):
+        op = ProjOp()
+        check(lib().pb200_proj_op_tmerc(a, invf, lat0, lon0, k0, fe, fn, inverse, C.byref(op)))
+        return op
+    d2r, r2d = ProjOp(), ProjOp()
+    d2r.kind, r2d.kind = 8, 9
+    osgb = (6377563.396, 299.32496, 49.0, -2.0, 0.9996012717, 400000.0, -100000.0)
+    out = run([d2r, tm(*osgb)], [[50.5, 0.5, 0.0]])  # GN7-2 3.5.3.1
+    assert abs(out[0, 0] - 577274.99) < 0.011 and abs(out[0, 1] - 69740.50) < 0.011
+    back = run([tm(*osgb, inverse=1), r2d], out)
+    assert abs(back[0, 0] - 50.5) < 1e-9 and abs(back[0, 1] - 0.5) < 1e-9
+    out = run([d2r, tm(6378206.4, 294.978698213898, 0.0, -75.0, 0.9996, 500000.0, 0.0)], [[40.5, -73.5, 0.0]])  # Snyder, UTM 18
+    assert abs(out[0, 0] - 627106.5) < 0.06 and abs(out[0, 1] - 4484124.4) < 0.06
+    buf = cloud(np.array([[24 + 22 / 60 + 54.433 / 3600, -(100 + 20 / 60), 1.0]]))  # GN7-2 3.5.1.2
+    reproject_point_cloud_within(buf, "EPSG:4326", "EPSG:3857")
+    wm = buf.view_attribute(A.POSITION_3D)
+    assert abs(wm[0, 0] + 11169055.58) < 0.01 and abs(wm[0, 1] - 2800000.00) < 0.01
+    reproject_point_cloud_within(buf, "EPSG:3857", "EPSG:4326")
+    ll = buf.view_attribute(A.POSITION_3D)
+    assert abs(ll[0, 0] - (24 + 22 / 60 + 54.433 / 3600)) < 1e-10 and abs(ll[0, 1] + (100 + 20 / 60)) < 1e-10
+    h = ProjOp()
+    check(lib().pb200_proj_op_helmert(0.0, 0.0, 4.5, 0.0, 0.0, 0.554, 0.219, 0, C.byref(h)))  # GN7-2 4.3.3, WGS 72 -> WGS 84
+    out = run([h], [[3657660.66, 255768.55, 5201382.11]])
+    assert np.all(np.abs(out[0] - [3657660.78, 255778.43, 5201387.75]) < 0.01)
+    cf = ProjOp()
+    check(lib().pb200_proj_op_helmert(0.0, 0.0, 4.5, 0.0, 0.0, -0.554, 0.219, 1, C.byref(cf)))  # same in the Coordinate Frame convention
+    assert np.allclose(run([cf], [[3657660.66, 255768.55, 5201382.11]]), out, atol=1e-9)
+
+
+def test_reproject_utm_zone_to_zone():
+    """points near a zone border given in zone 32 -> zone 33 (reverse + forward series): equals the direct projection"""
+    rng = np.random.default_rng(9)
+    pts = np.stack([rng.uniform(45, 55, 5000), rng.uniform(11.0, 13.0, 5000), np.zeros(5000)], 1)
+    b32, b33 = cloud(pts), cloud(pts)
+    reproject_point_cloud_within(b32, "EPSG:4326", "EPSG:32632")
+    reproject_point_cloud_within(b33, "EPSG:4326", "EPSG:32633")
+    reproject_point_cloud_within(b32, "EPSG:32632", "EPSG:32633")
+    torch.cuda.synchronize()
+    assert np.max(np.abs(b32.view_attribute(A.POSITION_3D) - b33.view_attribute(A.POSITION_3D))) < 1e-6
 
 
 def test_radius_search_large_cloud_prunes_by_radius():

@@ -80,18 +80,74 @@ def test_minmax_contract():
     assert minmax_attribute(HashMapBuffer(pl, 0, "cuda"), A.GPS_TIME) is None
 
 
-def test_morton_codes():
-    n = 50000
+def _expand_bits_by_3_np(v):
+    """math/bitmanip.rs:2-10 on a whole array (the same mask sequence as the oracle's scalar po_expand_bits_by_3)"""
+    v = v.astype(np.uint64) & np.uint64(0x1FFFFF)
+    for shift, mask in ((32, 0x00FF00000000FFFF), (16, 0x00FF0000FF0000FF), (8, 0xF00F00F00F00F00F), (4, 0x30C30C30C30C30C3), (2, 0x1249249249249249)):
+        v = (v | (v << np.uint64(shift))) & np.uint64(mask)
+    return v
+
+
+@pytest.mark.parametrize("n,columnar", [(50_000, True), (1_000_003, True), (200_001, False)])
+def test_morton_codes(n, columnar):
+    """EVERY code of the cloud against the restatement (quantise to 21 bits per axis inside the AABB, interleave with
+    expand_bits_by_3); the vectorised interleave itself is checked against the oracle's scalar function first"""
+    L = O.lib()
+    probe = np.array([0, 1, 2, 0x155555, 0x1FFFFF, 0xABCDE, 12345, 0x100000], dtype=np.uint64)
+    assert [int(x) for x in _expand_bits_by_3_np(probe)] == [L.po_expand_bits_by_3(int(x)) for x in probe]
     pts = O.gen_terrain_positions(0, n)
-    ol, pl = util.layouts([("Position3D", O.VEC3F64)])
-    b = HashMapBuffer(pl, n, "cuda")
+    ol, pl = util.layouts([("Position3D", O.VEC3F64)] if columnar else [("Intensity", O.U16), ("Position3D", O.VEC3F64)])
+    b = (HashMapBuffer if columnar else VectorBuffer)(pl, n, "cuda")
     b.set_attribute("Position3D", pts)
     mn, mx = pts.min(0), pts.max(0)
     codes = morton_codes(b, mn, mx).cpu().numpy().view(np.uint64)
     scale = np.where(mx - mn > 0, 2097152.0 / (mx - mn), 0.0)
     q = np.minimum(np.floor((pts - mn) * scale), 2097151).astype(np.uint64)
-    L = O.lib()
-    for i in list(range(50)) + [n - 1, int(np.argmax(pts[:, 0])), int(np.argmin(pts[:, 2]))]:
-        e = (L.po_expand_bits_by_3(int(q[i, 0])) << 2) | (L.po_expand_bits_by_3(int(q[i, 1])) << 1) | L.po_expand_bits_by_3(int(q[i, 2]))
-        assert int(codes[i]) == e
+    expect = (_expand_bits_by_3_np(q[:, 0]) << np.uint64(2)) | (_expand_bits_by_3_np(q[:, 1]) << np.uint64(1)) | _expand_bits_by_3_np(q[:, 2])
+    assert np.array_equal(codes, expect)
     assert int(codes.max()) < (1 << 63)
+
+
+@pytest.mark.parametrize("dtype", [O.U8, O.I16, O.U64, O.I64, O.F32, O.F64, O.VEC3I32, O.VEC3F64])
+def test_minmax_partial_and_logical_shards(dtype):
+    """pb200_minmax_attribute_partial (the fold for a shard that does not start the cloud: NaN never enters) and the
+    sharded helper: three logical shards of one buffer, combined like the ranks of a process group would, must give the
+    reference's sequential result -- including a NaN seed in shard 0 and NaNs opening the later shards"""
+    from pasture_b200 import sharding
+    ol, pl = util.layouts([("pad", O.U8), ("v", dtype)], packed=1)
+    n = 9001
+    ob, pbuf = util.random_bytes_buffers(ol, pl, n, True, seed=70 + int(dtype), finite_floats=True)
+    attr = PointAttributeDefinition("v", dtype)
+    vals = ob.attribute("v").copy()
+    is_float = dtype in (O.F32, O.F64, O.VEC3F64)
+    for nan_seed in ([False, True] if is_float else [False]):
+        if is_float:
+            vals = vals.copy()
+            flat = vals.reshape(n, -1)
+            flat[3000, 0] = np.nan            # opens shard 1
+            flat[6000:6003, -1] = np.nan      # opens shard 2
+            flat[0, 0] = np.nan if nan_seed else 1.0
+            ob.set_attribute("v", vals)
+            pbuf = util.to_pb(ob, pl)
+        omn, omx = O.minmax_attribute(ob, "v", dtype)  # the sequential fold of the whole cloud
+        partials = []
+        for lo, hi in ((0, 3000), (3000, 6000), (6000, n)):
+            shard = HashMapBuffer(pl, hi - lo, "cuda", columns=[c[lo * pl.at(i).size(): hi * pl.at(i).size()] for i, c in enumerate(pbuf.columns)])
+            local = minmax_attribute(shard, attr, partial=True)
+            v = np.asarray(ob.attribute("v")[lo:hi]).reshape(hi - lo, -1)
+            with np.errstate(invalid="ignore"):
+                emn = np.nanmin(v, axis=0) if is_float else v.min(axis=0)
+                emx = np.nanmax(v, axis=0) if is_float else v.max(axis=0)
+            assert np.array_equal(np.atleast_1d(local[0]), emn) and np.array_equal(np.atleast_1d(local[1]), emx)
+            partials.append((local, shard.slice_first(attr)))
+        # combine as combine_minmax does across ranks: min / max of the partials, then the seed rule from shard 0
+        mn = np.min([np.atleast_1d(p[0][0]) for p in partials], axis=0)
+        mx = np.max([np.atleast_1d(p[0][1]) for p in partials], axis=0)
+        if is_float:
+            seed = np.atleast_1d(np.asarray(partials[0][1], dtype=np.float64))
+            mn = np.where(np.isnan(seed), np.nan, mn)
+            mx = np.where(np.isnan(seed), np.nan, mx)
+        assert np.array_equal(mn, omn, equal_nan=True) and np.array_equal(mx, omx, equal_nan=True)
+        # no process group: the helper degenerates to the single-device call
+        r = sharding.minmax_attribute_sharded(pbuf, attr)
+        assert np.array_equal(np.atleast_1d(r[0]), omn, equal_nan=True) and np.array_equal(np.atleast_1d(r[1]), omx, equal_nan=True)

@@ -265,6 +265,78 @@ def test_reproject_epsg4326_epsg3309():  # reprojection.rs:250-337 (assert_appro
     assert np.all(np.abs(out - expected) < 1e-4), out - expected
 
 
+# Published worked examples stand in for libproj (proj-sys 0.22 is not in /root/reference): the Transverse
+# Mercator, Pseudo-Mercator and Helmert operations are pinned on IOGP Guidance Note 7-2 and Snyder (USGS PP 1395).
+
+def _dms(d, m, s):
+    return d + m / 60.0 + s / 3600.0
+
+
+def test_transverse_mercator_guidance_note_example():
+    """GN7-2 3.5.3.1, OSGB 1936 / British National Grid: Airy 1830 (a = 6377563.396, 1/f = 299.32496), origin 49 N 2 W,
+    k0 = 0.9996012717, FE 400000, FN -100000; 50 30' N 0 30' E -> E 577274.99, N 69740.50 (published to the centimetre)"""
+    airy = (6377563.396, 299.32496)
+    ops, n = O.make_pipeline([(O.PROJ_DEG2RAD_LATLON, []), O.tmerc_step(airy, 49.0, -2.0, 0.9996012717, 400000.0, -100000.0)])
+    out = O.reproject(ops, n, np.array([[50.5, 0.5, 7.0]]))
+    assert abs(out[0, 0] - 577274.99) < 0.011 and abs(out[0, 1] - 69740.50) < 0.011 and out[0, 2] == 7.0
+    ops, n = O.make_pipeline([O.tmerc_step(airy, 49.0, -2.0, 0.9996012717, 400000.0, -100000.0, inverse=True), (O.PROJ_RAD2DEG_LATLON, [])])
+    back = O.reproject(ops, n, out)  # the note's reverse example returns to 50 30' 00.000" N, 00 30' 00.000" E
+    assert abs(back[0, 0] - 50.5) < 1e-9 and abs(back[0, 1] - 0.5) < 1e-9
+
+
+def test_utm_snyder_example_and_meridian_arc():
+    """Snyder, Map Projections - A Working Manual, numerical example for the ellipsoidal Transverse Mercator: Clarke 1866,
+    40 30' N 73 30' W in UTM zone 18 -> x = 127106.5 m east of the central meridian, y = 4484124.4 m.  Plus the meridian
+    arc (the series at lon = lon0) against numerical quadrature of the arc-length integral on WGS 84."""
+    from scipy.integrate import quad
+    clarke = (6378206.4, 294.978698213898)
+    ops, n = O.make_pipeline([(O.PROJ_DEG2RAD_LATLON, []), O.utm_step(18, ellipsoid=clarke)])
+    out = O.reproject(ops, n, np.array([[40.5, -73.5, 0.0]]))
+    assert abs(out[0, 0] - 627106.5) < 0.06 and abs(out[0, 1] - 4484124.4) < 0.06
+    a, invf = O.WGS84
+    f = 1.0 / invf
+    e2 = f * (2.0 - f)
+    ops, n = O.make_pipeline([(O.PROJ_DEG2RAD_LATLON, []), O.tmerc_step(O.WGS84, 0.0, 0.0, 1.0, 0.0, 0.0)])
+    for lat in (5.0, 33.0, 60.0, 84.0):
+        arc = quad(lambda p: a * (1.0 - e2) / (1.0 - e2 * np.sin(p) ** 2) ** 1.5, 0.0, np.radians(lat), epsabs=1e-9)[0]
+        out = O.reproject(ops, n, np.array([[lat, 0.0, 0.0]]))
+        assert abs(out[0, 1] - arc) < 1e-6 and abs(out[0, 0]) < 1e-9
+
+
+def test_utm_round_trip_and_zone_parameters():
+    """forward and reverse series have independent coefficients: a round trip over a whole zone (+-4 deg) to 1e-10 deg;
+    zone 32 north has its central meridian at 9 E, false easting 500 km; the southern hemisphere adds 10 000 km"""
+    rng = np.random.default_rng(7)
+    pts = np.stack([rng.uniform(-80, 84, 3000), 9.0 + rng.uniform(-4, 4, 3000), rng.uniform(0, 500, 3000)], axis=1)
+    fwd, nf = O.make_pipeline([(O.PROJ_DEG2RAD_LATLON, []), O.utm_step(32)])
+    inv, ni = O.make_pipeline([O.utm_step(32, inverse=True), (O.PROJ_RAD2DEG_LATLON, [])])
+    en = O.reproject(fwd, nf, pts)
+    back = O.reproject(inv, ni, en)
+    assert np.max(np.abs(back - pts)) < 1e-10
+    on_cm = O.reproject(fwd, nf, np.array([[0.0, 9.0, 0.0], [45.0, 9.0, 0.0]]))
+    assert abs(on_cm[0, 0] - 500000.0) < 1e-9 and abs(on_cm[0, 1]) < 1e-9 and abs(on_cm[1, 0] - 500000.0) < 1e-9
+    south, ns = O.make_pipeline([(O.PROJ_DEG2RAD_LATLON, []), O.utm_step(32, south=True)])
+    assert abs(O.reproject(south, ns, np.array([[0.0, 9.0, 0.0]]))[0, 1] - 10000000.0) < 1e-9
+
+
+def test_pseudo_mercator_guidance_note_example():
+    """GN7-2 3.5.1.2 (EPSG method 1024, WGS 84 / Pseudo-Mercator): 24 22' 54.433" N 100 20' W -> E -11169055.58, N 2800000.00"""
+    ops, n = O.make_pipeline([(O.PROJ_WEBMERC_FWD, [])])
+    out = O.reproject(ops, n, np.array([[_dms(24, 22, 54.433), -_dms(100, 20, 0.0), 3.0]]))
+    assert abs(out[0, 0] + 11169055.58) < 0.01 and abs(out[0, 1] - 2800000.00) < 0.01 and out[0, 2] == 3.0
+    inv, ni = O.make_pipeline([(O.PROJ_WEBMERC_INV, [])])
+    back = O.reproject(inv, ni, out)
+    assert abs(back[0, 0] - _dms(24, 22, 54.433)) < 1e-10 and abs(back[0, 1] + _dms(100, 20, 0.0)) < 1e-10
+
+
+def test_helmert_guidance_note_example():
+    """GN7-2 4.3.3 Position Vector transformation WGS 72 -> WGS 84: tZ = +4.5 m, rZ = +0.554", dS = +0.219 ppm;
+    (3657660.66, 255768.55, 5201382.11) -> (3657660.78, 255778.43, 5201387.75)"""
+    ops, n = O.make_pipeline([O.helmert_step(0.0, 0.0, 4.5, 0.0, 0.0, 0.554, 0.219)])
+    out = O.reproject(ops, n, np.array([[3657660.66, 255768.55, 5201382.11]]))
+    assert np.all(np.abs(out[0] - [3657660.78, 255778.43, 5201387.75]) < 0.01), out
+
+
 # ---- the oracle's two kNN implementations pin each other -------------------------------------------------------------
 
 @pytest.mark.parametrize("seed,n,k", [(0, 5000, 16), (1, 777, 3), (2, 40, 64), (3, 9000, 33)])

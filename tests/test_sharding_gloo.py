@@ -154,3 +154,91 @@ def test_sharded_voxelgrid_equals_single_shot(world, empty_rank):
     assert counts.sum() == len(pts)
     expect = oout.attribute_bytes(0).view(np.float64).reshape(-1, 3)
     assert np.allclose(cent, expect, rtol=1e-9, atol=0)  # sum of per-shard sums vs one in-order sum
+
+
+# ---- minmax_attribute over shards: the exchange and the seed rule (host logic; the per-shard fold is the GPU's job) ------
+
+def _minmax_worker(rank, world, port, case, out_q):
+    os.environ["MASTER_ADDR"] = "127.0.0.1"
+    os.environ["MASTER_PORT"] = str(port)
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    try:
+        import pasture_b200 as pb
+        name, np_dtype, attr, values = _minmax_case(case)
+        r = sharding.shard_range(len(values), rank, world)
+        if case.endswith("empty_first") and rank == 0:
+            r = range(0, 0)
+        if case.endswith("empty_first") and rank == 1:
+            r = range(0, sharding.shard_range(len(values), 1, world).stop)
+        shard = values[r.start:r.stop]
+        local = first = None
+        if len(shard):
+            first = shard[0]
+            with np.errstate(invalid="ignore"):
+                local = (np.nanmin(shard, axis=0), np.nanmax(shard, axis=0)) if np.issubdtype(np_dtype, np.floating) \
+                    else (shard.min(axis=0), shard.max(axis=0))
+                if np.issubdtype(np_dtype, np.floating):  # a component without any non-NaN value: the fold's identity
+                    local = (np.where(np.isnan(local[0]), sharding.F64_MAX, local[0]), np.where(np.isnan(local[1]), -sharding.F64_MAX, local[1]))
+        res = sharding.combine_minmax(local, first, attr)
+        out_q.put((rank, None if res is None else (np.asarray(res[0]).tolist(), np.asarray(res[1]).tolist())))
+    finally:
+        dist.destroy_process_group()
+
+
+def _minmax_case(case):
+    import pasture_b200 as pb
+    from pasture_b200 import PointAttributeDefinition, PointAttributeDataType as DT
+    rng = np.random.default_rng(11)
+    base = case.replace("_empty_first", "")
+    if base == "u64":
+        v = rng.integers(0, 2 ** 64, 1001, dtype=np.uint64)
+        v[500], v[3] = np.uint64(2 ** 64 - 1), np.uint64(0)
+        return base, np.uint64, PointAttributeDefinition("PointID", DT.U64), v
+    if base == "i8":
+        return base, np.int8, PointAttributeDefinition("ScanAngleRank", DT.I8), rng.integers(-128, 128, 1001).astype(np.int8)
+    if base == "vec3i32":
+        return base, np.int32, PointAttributeDefinition("LASLocalPosition", DT.Vec3i32), rng.integers(-2 ** 31, 2 ** 31, (1001, 3)).astype(np.int32)
+    if base == "f64_nan_later":
+        v = rng.normal(size=1001)
+        v[[1, 400, 1000]] = np.nan  # NaNs after the seed are ignored
+        return base, np.float64, PointAttributeDefinition("GpsTime", DT.F64), v
+    if base == "vec3f64_nan_seed":
+        v = rng.normal(size=(1001, 3))
+        v[0, 1] = np.nan  # a NaN seed sticks -- for that component only
+        return base, np.float64, PointAttributeDefinition("Position3D", DT.Vec3f64), v
+    raise KeyError(case)
+
+
+def _sequential_minmax(values):
+    """math/minmax.rs:62-96: seed = first value, strict comparisons"""
+    v = np.asarray(values).reshape(len(values), -1)
+    mn, mx = v[0].copy(), v[0].copy()
+    for row in v[1:]:
+        for c in range(v.shape[1]):
+            if row[c] < mn[c]:
+                mn[c] = row[c]
+            if row[c] > mx[c]:
+                mx[c] = row[c]
+    return mn, mx
+
+
+@pytest.mark.parametrize("case", ["u64", "i8", "vec3i32", "f64_nan_later", "vec3f64_nan_seed", "vec3f64_nan_seed_empty_first"])
+def test_sharded_minmax_exchange_equals_the_sequential_fold(case):
+    world = 3
+    ctx = mp.get_context("spawn")
+    q = ctx.Queue()
+    port = _free_port()
+    procs = [ctx.Process(target=_minmax_worker, args=(r, world, port, case, q)) for r in range(world)]
+    for p in procs:
+        p.start()
+    results = [q.get(timeout=120) for _ in range(world)]
+    for p in procs:
+        p.join(timeout=60)
+        assert p.exitcode == 0
+    _, _, _, values = _minmax_case(case)
+    if case.endswith("empty_first"):  # rank 0 empty, rank 1 holds the cloud's start: the data ranks 0+1 would have held
+        values = values
+    emn, emx = _sequential_minmax(values)
+    for rank, res in results:
+        mn, mx = (np.atleast_1d(np.asarray(x, dtype=values.dtype)) for x in res)
+        assert np.array_equal(mn, emn, equal_nan=True) and np.array_equal(mx, emx, equal_nan=True), (case, rank, mn, emn, mx, emx)
