@@ -59,7 +59,7 @@ def summarise_all(args, header, units, rows):
         return full
 
     for row in rows:
-        name = strip_args(row[header.index("Kernel Name")])
+        name = strip_args(row[header.index("Kernel Name")]).replace("void ", "").strip()
         base = name.split("<")[0].split("::")[-1]
         seen[base] = seen.get(base, 0) + 1
         e = {"kernel": name, "launch": seen[base]}

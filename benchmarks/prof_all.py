@@ -57,12 +57,13 @@ def main():
         wr.set_custom_mapping_with_transformation(pb.attributes.POSITION_3D, pb.ATTRIBUTE_LOCAL_LAS_POSITION,
                                                   pb.InvScaleOffset(0.001, of), True)
         wr.convert_into(aos, back)
-        note("convert_tiles_kernel#4", 55 * n, "C1 on the GPU: interleaved 35 B -> raw LAS fmt0 20 B, (p-o)/s truncating")
+        note("convert_tiles_kernel#4", 55 * n, "C1 on the GPU: interleaved 35 B -> raw LAS fmt0 20 B, (p-o)/s truncating, convert_into (read-modify-write)")
+        wr.convert_into_fresh(aos, back)
+        note("convert_tiles_kernel#5", 55 * n, "C1 on the GPU, convert semantics (fresh target: zero ops, no read-modify-write)")
         del aos, back
         from pasture_b200 import las
         las.write_points(col, 0, sc, of)
-        note("convert_tiles_kernel#5", 55 * n, "LAS egress: columnar default layout -> fmt0 records (bit-field packing, stats)")
-        note("return_histogram_kernel", 1 * n, "LAS egress: points by return number")
+        note("convert_tiles_kernel#6", 55 * n, "LAS egress: columnar default layout -> fmt0 records, bit-field packing, out-of-range count, points by return and bounds fused")
         del col
     if want("reduce"):
         src = alg.synth_terrain_positions(n)
@@ -79,11 +80,20 @@ def main():
         alg.voxelgrid_filter(src, 0.1, 0.1, 0.1)
         note("voxel_key_kernel", 32 * n, "C3 voxel keys (24 B in, 8 B out)")
         note("radix_histogram_kernel", 8 * n, "C3 sort: digit histograms of all passes")
-        note("radix_onesweep_kernel", 16 * n, "C3 sort: one 8-bit pass, keys only (8 B in, 8 B out)")
+        note("radix_onesweep_kernel", 16 * n, "C3 sort: one 8- or 9-bit pass, keys only (8 B in, 8 B out)")
         note("heads_count_kernel", 8 * n, "C3 voxel boundaries: heads per tile")
-        note("heads_emit_kernel", 12 * n, "C3 voxel boundaries: starts, voxel keys, unpacked indices")
-        note("voxel_reduce_kernel", 28 * n + 24 * 0.377 * n, "C3 per-voxel centroid (4 B index + 24 B gathered position per point, 24 B per voxel)")
-        note("voxel_emit_reduce_kernel", 32 * n + 32 * 0.377 * n, "C3 boundaries + per-voxel centroid fused (8 B key + 24 B gathered position per point, 32 B per voxel)")
+        note("voxel_emit_reduce_kernel", 32 * n + 32 * 0.4 * n, "C3 boundaries + per-voxel centroid fused (8 B key + 24 B gathered position per point, 32 B per voxel)")
+        # a second call with other attributes: the index hand-out path, the thread-per-voxel reductions, heads_emit when
+        # the target has no Position3D
+        l3 = pb.PointLayout.from_attributes([pb.attributes.POSITION_3D, pb.attributes.INTENSITY, pb.attributes.CLASSIFICATION])
+        m3 = n // 5
+        b3 = pb.HashMapBuffer(l3, m3, "cuda")
+        b3.columns[0][: 24 * m3].copy_(src.columns[0][: 24 * m3])
+        b3.columns[1][: 2 * m3].random_(0, 255)
+        b3.columns[2][:m3].random_(0, 5)
+        alg.voxelgrid_filter(b3, 0.1, 0.1, 0.1)
+        note("voxel_reduce_kernel", (4 + 2) * m3 + 2 * 0.75 * m3, "voxel mean of a u16 attribute (4 B index + 2 B gathered value per point, 2 B per voxel), 10 M points")
+        del b3
         del src
     if want("reproject"):
         src = alg.synth_terrain_positions(n // 2)
@@ -116,7 +126,7 @@ def main():
         src = pb.HashMapBuffer(_l, n, "cuda")
         src.columns[0][: 24 * n].view(torch.float64).uniform_(-1000.0, 1000.0)
         tiles3d.PntsWriter(_l).write(src)
-        note("convert_tiles_kernel#6", 45 * n, ".pnts egress: Vec3f64 + Vec3u16 columns -> Vec3f32 + Vec3u8 body")
+        note("convert_tiles_kernel#7", 45 * n, ".pnts egress: Vec3f64 + Vec3u16 columns -> Vec3f32 + Vec3u8 body")
         del src
     if want("knn"):
         src = alg.synth_terrain_positions(m)
@@ -128,6 +138,28 @@ def main():
         note("lbvh_refit_kernel", (24 * 8 + 64) * m / 8, "LBVH: bottom-up box refit")
         note("lbvh_query_kernel", 56 * m, "kNN k=16 + normals, packet traversal (compulsory bytes only: latency-bound)")
         del src
+    # kernels that are launched several times get one entry per launch ("name#k", k = order of launch in this script)
+    m3, vn = n // 5, 0.4
+    for k, (nb, w) in enumerate([(24 * n, "AABB of a packed Vec3f64 column"), (24 * n, "AABB (voxel grid call)"), (24 * m3, "AABB, 10 M points"),
+                                 (24 * m, "AABB (LBVH build)")], 1):
+        note(f"bounds_flat_f64_kernel#{k}", nb, w)
+    for k, (nb, w) in enumerate([(32 * n, "C3 voxel keys (24 B in, 8 B out)"), (32 * m3, "voxel keys, 10 M points")], 1):
+        note(f"voxel_key_kernel#{k}", nb, w)
+    for k, (nb, w) in enumerate([(8 * n, "sort: digit histograms of all passes"), (8 * m3, "10 M keys"), (8 * m, "LBVH codes")], 1):
+        note(f"radix_histogram_kernel#{k}", nb, w)
+    for k in range(1, 17):
+        if k <= 4:
+            note(f"radix_onesweep_kernel#{k}", 16 * n, "C3 sort: one pass, keys only (8 B in, 8 B out)")
+        elif k <= 8:
+            note(f"radix_onesweep_kernel#{k}", 16 * m3, "one pass, keys only, 10 M keys")
+        else:
+            note(f"radix_onesweep_kernel#{k}", 24 * m, "LBVH sort: one 8-bit pass of (code, index) pairs")
+    note("heads_count_kernel#1", 8 * n, "voxel boundaries: heads per tile")
+    note("heads_count_kernel#2", 8 * m3, "voxel boundaries, 10 M keys")
+    note("voxel_emit_reduce_kernel#1", 32 * n + 32 * vn * n, "C3 boundaries + per-voxel centroid fused (8 B key + 24 B gathered position per point, 32 B per voxel)")
+    note("voxel_emit_reduce_kernel#2", 36 * m3 + 36 * 0.75 * m3, "same with index hand-out, 10 M points")
+    note("voxel_reduce_kernel#1", 6 * m3 + 2 * 0.75 * m3, "voxel mean of a u16 attribute (4 B index + 2 B gathered value per point)")
+    note("voxel_reduce_kernel#2", 5 * m3 + 0.75 * m3, "voxel mode of a u8 attribute (4 B index + 1 B gathered value per point)")
     torch.cuda.synchronize()
     os.makedirs(os.path.join(ROOT, "gpurun_out"), exist_ok=True)
     with open(os.path.join(ROOT, "gpurun_out", "prof_all_bytes.json"), "w") as fh:

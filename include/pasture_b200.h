@@ -333,6 +333,35 @@ int pb200_voxelgrid_merge_partials(pb200_ctx* ctx, const uint64_t* keys, const u
                                    uint64_t m, uint32_t bits_x, uint32_t bits_y, uint32_t bits_z,
                                    pb200_voxel_partials** out);
 int pb200_voxel_partials_get(const pb200_voxel_partials* p, pb200_voxel_partials_desc* out);
+/* The same for EVERY attribute of a filtered layout (voxel_grid.rs:168-689), so that a sharded cloud can be filtered with
+ * all 18 built-in reductions.  Per voxel of the shard (in the order of pb200_voxel_partials_get's keys):
+ *   mean attributes      one f64 column per component holding the SUM over the shard's points (Intensity, NIR, ColorRGB,
+ *                        Normal); the division by the merged count and the reference's `as` cast happen after the merge
+ *   max-pool attributes  one f64 column with the running maximum, starting from 0.0 like the reference (ClassificationFlags,
+ *                        GpsTime, PointID)
+ * and per "most common value" attribute (ReturnNumber, Classification, ...) a RUN LIST: (voxel key << 16 | value biased to
+ * an unsigned 16-bit field, number of the shard's points with that value in that voxel), ascending -- per-shard modes
+ * cannot be merged, per-shard histograms can.  Columns and lists are numbered in the order of dst_layout's attributes.
+ * Exact for every integer attribute (u16 sums are exact in f64); f32 means differ from the single-device result only by
+ * the f64 summation order (<= 1e-9 relative).  The shard must be device-resident. */
+typedef struct {
+  uint32_t n_columns, n_modes;
+  const double* columns;                 /* device, len * n_columns, voxel-major */
+  uint8_t column_is_max[64];             /* how column c merges: 0 = add, 1 = maximum */
+  uint64_t mode_len[PB200_MAX_ATTRIBUTES];
+  const uint64_t* mode_keys[PB200_MAX_ATTRIBUTES];   /* device, ascending */
+  const uint32_t* mode_counts[PB200_MAX_ATTRIBUTES]; /* device */
+} pb200_voxel_attr_partials_desc;
+int pb200_voxelgrid_partials_layout(pb200_ctx* ctx, const pb200_buffer_desc* src, double leaf_x, double leaf_y, double leaf_z,
+                                    const double global_min[3], const double global_max[3], const pb200_layout* dst_layout,
+                                    pb200_voxel_partials** out);
+int pb200_voxel_partials_get_attrs(const pb200_voxel_partials* p, pb200_voxel_attr_partials_desc* out);
+/* merge of concatenated partials (`pos`: keys / counts / sums of all source ranks in rank order, len = their total;
+ * `attrs`: their columns, row i belonging to pos->keys[i], and the concatenated run lists) into the filtered points of this
+ * rank's key range: a library-owned COLUMNAR DEVICE buffer with dst_layout, one point per voxel in ascending key order
+ * (pb200_result_buffer_voxel_keys gives the (ix, iy, iz) of each).  Mode ties resolve to the smallest value. */
+int pb200_voxelgrid_merge_partials_layout(pb200_ctx* ctx, const pb200_layout* dst_layout, const pb200_voxel_partials_desc* pos,
+                                          const pb200_voxel_attr_partials_desc* attrs, pb200_result_buffer** out);
 /* positions_out: device, len * 3 doubles: sums / count (voxel_grid.rs:382-386) */
 int pb200_voxel_partials_centroids(const pb200_voxel_partials* p, double* positions_out);
 void pb200_voxel_partials_destroy(pb200_voxel_partials* p);

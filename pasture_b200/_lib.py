@@ -47,6 +47,11 @@ class VoxelPartialsDesc(C.Structure):
                 ("cells", C.c_uint64 * 3)]
 
 
+class VoxelAttrPartialsDesc(C.Structure):
+    _fields_ = [("n_columns", C.c_uint32), ("n_modes", C.c_uint32), ("columns", C.c_void_p), ("column_is_max", C.c_uint8 * 64),
+                ("mode_len", C.c_uint64 * 48), ("mode_keys", C.c_void_p * 48), ("mode_counts", C.c_void_p * 48)]
+
+
 class ProjOp(C.Structure):
     _fields_ = [("kind", C.c_uint32), ("_pad", C.c_uint32), ("p", C.c_double * 12)]
 
@@ -142,6 +147,9 @@ SIGNATURES = {
     "pb200_voxelgrid_partials": (i32, [vp, BD, dbl, dbl, dbl, PD, PD, PVP]),
     "pb200_voxelgrid_merge_partials": (i32, [vp, vp, vp, vp, u64, u32, u32, u32, PVP]),
     "pb200_voxel_partials_get": (i32, [vp, C.POINTER(VoxelPartialsDesc)]),
+    "pb200_voxelgrid_partials_layout": (i32, [vp, BD, dbl, dbl, dbl, PD, PD, vp, PVP]),
+    "pb200_voxel_partials_get_attrs": (i32, [vp, C.POINTER(VoxelAttrPartialsDesc)]),
+    "pb200_voxelgrid_merge_partials_layout": (i32, [vp, vp, C.POINTER(VoxelPartialsDesc), C.POINTER(VoxelAttrPartialsDesc), PVP]),
     "pb200_voxel_partials_centroids": (i32, [vp, vp]),
     "pb200_voxel_partials_destroy": (None, [vp]),
     "pb200_knn": (i32, [vp, BD, u32, vp, vp]),

@@ -5,7 +5,7 @@ import ctypes as C
 import numpy as np
 import torch
 
-from ._lib import BufferDesc, ProjOp, VoxelPartialsDesc, check, lib
+from ._lib import BufferDesc, ProjOp, VoxelAttrPartialsDesc, VoxelPartialsDesc, check, lib
 from .containers import _NP, _VEC3, HashMapBuffer, VectorBuffer
 from .context import context_for, get_context
 from .layout import DT
@@ -208,6 +208,90 @@ def voxelgrid_partials(buffer, leafsize_x, leafsize_y, leafsize_z, global_bounds
     h = C.c_void_p()
     check(lib().pb200_voxelgrid_partials(ctx._h, C.byref(d), leafsize_x, leafsize_y, leafsize_z, gmin, gmax, C.byref(h)))
     return _take_partials(ctx, h, False)
+
+
+class VoxelAttrPartials:
+    """one shard's (or several concatenated shards') partials for every attribute of a filtered layout: position partials
+    (VoxelPartials) + per-voxel columns [len, n_columns] + one (keys, counts) run list per "most common value" attribute"""
+
+    def __init__(self, pos, columns, column_is_max, modes):
+        self.pos, self.columns, self.column_is_max, self.modes = pos, columns, column_is_max, modes
+
+
+def voxelgrid_partials_layout(buffer, leafsize_x, leafsize_y, leafsize_z, global_bounds, filtered_layout=None, ctx=None):
+    """pb200_voxelgrid_partials_layout: everything one shard contributes to the filtered cloud in `filtered_layout`"""
+    ctx = context_for(ctx, buffer)
+    layout = filtered_layout or buffer.point_layout()
+    mn, mx = (global_bounds.min(), global_bounds.max()) if isinstance(global_bounds, AABB) else global_bounds
+    gmin, gmax = (C.c_double * 3)(*mn), (C.c_double * 3)(*mx)
+    d = buffer.desc()
+    h = C.c_void_p()
+    check(lib().pb200_voxelgrid_partials_layout(ctx._h, C.byref(d), leafsize_x, leafsize_y, leafsize_z, gmin, gmax, layout._h, C.byref(h)))
+    try:
+        ad = VoxelAttrPartialsDesc()
+        check(lib().pb200_voxel_partials_get_attrs(h, C.byref(ad)))
+        pd = VoxelPartialsDesc()
+        check(lib().pb200_voxel_partials_get(h, C.byref(pd)))
+        v = int(pd.len)
+        dev = torch.device("cuda", ctx.device)
+
+        def take(ptr, shape, dtype):
+            t = torch.empty(shape, dtype=dtype, device=dev)
+            if t.numel():
+                check(lib().pb200_memcpy_d2d(ctx._h, C.c_void_p(t.data_ptr()), C.c_void_p(ptr), t.numel() * t.element_size()))
+            return t
+        cols = take(ad.columns, (v, int(ad.n_columns)), torch.float64)
+        modes = [(take(ad.mode_keys[a], (int(ad.mode_len[a]),), torch.int64), take(ad.mode_counts[a], (int(ad.mode_len[a]),), torch.int32))
+                 for a in range(int(ad.n_modes))]
+        pos = VoxelPartials(take(pd.keys, (v,), torch.int64), take(pd.counts, (v,), torch.int32), take(pd.sums, (v, 3), torch.float64),
+                            (pd.bits_x, pd.bits_y, pd.bits_z), tuple(pd.cells))
+        return VoxelAttrPartials(pos, cols, bytes(ad.column_is_max), modes)
+    finally:
+        lib().pb200_voxel_partials_destroy(h)
+
+
+def voxelgrid_merge_partials_layout(partials, filtered_layout, ctx=None, return_keys=False):
+    """merge concatenated VoxelAttrPartials (rows in source-rank order) -> the filtered points of this key range as a
+    HashMapBuffer viewing the library-owned result (no copy)"""
+    ctx = context_for(ctx, partials.pos.keys)
+    pos = partials.pos
+    keys, counts, sums = pos.keys.contiguous(), pos.counts.contiguous(), pos.sums.contiguous()
+    cols = partials.columns.contiguous()
+    pd = VoxelPartialsDesc()
+    pd.len = keys.numel()
+    pd.keys, pd.counts, pd.sums = keys.data_ptr(), counts.data_ptr(), sums.data_ptr()
+    pd.bits_x, pd.bits_y, pd.bits_z = pos.bits
+    ad = VoxelAttrPartialsDesc()
+    ad.n_columns = cols.shape[1] if cols.dim() == 2 else 0
+    ad.n_modes = len(partials.modes)
+    ad.columns = cols.data_ptr() if cols.numel() else None
+    for i, b in enumerate(partials.column_is_max[:64]):
+        ad.column_is_max[i] = b
+    keep = []
+    for a, (mk, mc) in enumerate(partials.modes):
+        mk, mc = mk.contiguous(), mc.contiguous()
+        keep.append((mk, mc))
+        ad.mode_len[a] = mk.numel()
+        ad.mode_keys[a] = mk.data_ptr() if mk.numel() else None
+        ad.mode_counts[a] = mc.data_ptr() if mc.numel() else None
+    h = C.c_void_p()
+    check(lib().pb200_voxelgrid_merge_partials_layout(ctx._h, filtered_layout._h, C.byref(pd), C.byref(ad), C.byref(h)))
+    owner = _ResultOwner(h, ctx)
+    rd = BufferDesc()
+    check(lib().pb200_result_buffer_desc(h, C.byref(rd)))
+    n = int(rd.len)
+    cdev = torch.device("cuda", ctx.device)
+    if n:
+        out = HashMapBuffer(filtered_layout, n, cdev, columns=[torch.as_tensor(_DeviceView(rd.columns[i], max(1, n * a.size()), owner), device=cdev)
+                                                                for i, a in enumerate(filtered_layout.attributes())])
+    else:
+        out = HashMapBuffer(filtered_layout, 0, cdev)
+    if not return_keys:
+        return out
+    vk = np.zeros((max(1, n), 3), dtype=np.uint64)
+    if n:
+        check(lib().pb200_result_buffer_voxel_keys(h, C.c_void_p(vk.ctypes.data)))
+    return out, vk[:n]
 
 
 def voxelgrid_merge_partials(keys, counts, sums, bits, cells=(0, 0, 0), ctx=None):

@@ -35,9 +35,16 @@ struct pb200_result_buffer {
 struct pb200_voxel_partials {
     pb200_ctx* ctx = nullptr;
     uint64_t len = 0;
-    void *keys = nullptr, *counts = nullptr, *sums = nullptr;  // device, from the stream-ordered pool
+    void *keys = nullptr, *counts = nullptr, *sums = nullptr;  // device, from the context's cache
     uint32_t bits_x = 0, bits_y = 0, bits_z = 0;
     uint64_t cells[3] = {0, 0, 0};
+    // attribute partials (pb200_voxelgrid_partials_layout): columns per voxel, run lists per "most common value" attribute
+    uint32_t n_col = 0, n_modes = 0;
+    void* cols = nullptr;
+    uint8_t col_is_max[64] = {};
+    void* mode_keys[PB200_MAX_ATTRIBUTES] = {};
+    void* mode_counts[PB200_MAX_ATTRIBUTES] = {};
+    uint64_t mode_len[PB200_MAX_ATTRIBUTES] = {};
 };
 
 namespace pb200 {
@@ -342,6 +349,10 @@ struct ReduceArgs {
     uint8_t* dst;               // column of the result (SoA staging), element size = dst_size
     uint32_t dst_size;
     int src_aligned;
+    // sharded grid: instead of the finished value, the raw f64 component sums (mean kinds) / running maximum
+    // (max-pool kinds) of the voxel go to partial[v * partial_stride ...] -- the division and the cast happen after the merge
+    double* partial;
+    uint32_t partial_stride;
 };
 
 // S = source scalar (component) type. One thread per voxel; points are visited in input order.
@@ -371,6 +382,7 @@ __global__ void __launch_bounds__(128) voxel_reduce_kernel(ReduceArgs a) {
             sy = __dadd_rn(sy, (double)ld_attr<S>(p + sizeof(S), al));
             sz = __dadd_rn(sz, (double)ld_attr<S>(p + 2 * sizeof(S), al));
         }
+        if (a.partial) { double* q = a.partial + v * a.partial_stride; q[0] = sx; q[1] = sy; q[2] = sz; return; }
         const double cnt = (double)(e - b);  // :382-386
         const double cx = sx / cnt, cy = sy / cnt, cz = sz / cnt;
         if constexpr (KIND == R_MEAN_VEC_F64) {
@@ -389,6 +401,7 @@ __global__ void __launch_bounds__(128) voxel_reduce_kernel(ReduceArgs a) {
         double s = 0.0;
         for (uint32_t k = b; k < e; ++k)
             s = __dadd_rn(s, (double)ld_attr<S>(a.src + (unsigned long long)a.sorted_idx[k] * a.src_stride, al));
+        if (a.partial) { a.partial[v * a.partial_stride] = s; return; }
         unsigned long long u = f64_as_u64_sat(s / (double)(e - b));
         uint16_t r = (uint16_t)(u > 65535ull ? 65535ull : u);
         memcpy(out, &r, 2);
@@ -415,6 +428,7 @@ __global__ void __launch_bounds__(128) voxel_reduce_kernel(ReduceArgs a) {
             const double x = (double)ld_attr<S>(a.src + (unsigned long long)a.sorted_idx[k] * a.src_stride, al);
             if (x > cur) cur = x;
         }
+        if (a.partial) { a.partial[v * a.partial_stride] = cur; return; }
         if constexpr (KIND == R_MAX_U8) { unsigned long long u = f64_as_u64_sat(cur); uint8_t r = (uint8_t)(u > 255ull ? 255ull : u); memcpy(out, &r, 1); }
         else if constexpr (KIND == R_MAX_F64) memcpy(out, &cur, 8);
         else { unsigned long long r = f64_as_u64_sat(cur); memcpy(out, &r, 8); }
@@ -563,6 +577,80 @@ __global__ void __launch_bounds__(256) partials_centroid_kernel(const uint32_t* 
 // Everything between the bounds and the per-voxel reductions: markers on the host (voxel_grid.rs:63-77), keys, sort,
 // voxel boundaries.  With the AABB of the WHOLE cloud every shard of a sharded cloud derives the same markers and
 // therefore the same global voxel keys.
+// ---- sharded grid, attributes other than POSITION_3D (SURVEY 8e "per-attribute partials") ---------------------------
+// Per voxel and shard the mean / max-pool attributes travel as 8-byte COLUMNS (component sums, running maxima), the
+// "most common value" attributes as RUN LISTS (composite key = voxel key << 16 | biased value, count).
+struct ColOps { uint8_t is_max[64]; };  // per column: 0 = partial sums are added, 1 = the maximum is taken
+
+// merge of concatenated partials, generalised: counts and position sums as before, plus n_col columns
+__global__ void __launch_bounds__(128) partials_merge_columns_kernel(const uint32_t* __restrict__ starts, const uint32_t* __restrict__ sorted_idx,
+                                                                     unsigned long long n_voxels, const double* __restrict__ in_cols,
+                                                                     uint32_t n_col, ColOps ops, double* __restrict__ out_cols) {
+    const unsigned long long v = (unsigned long long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (v >= n_voxels) return;
+    for (uint32_t c = 0; c < n_col; ++c) {
+        double acc = 0.0;  // sums start at 0; the max-pool folds start at 0.0 as well (voxel_grid.rs:168-215)
+        for (uint32_t k = starts[v], e = starts[v + 1]; k < e; ++k) {
+            const double x = in_cols[(size_t)sorted_idx[k] * n_col + c];
+            if (ops.is_max[c]) { if (x > acc) acc = x; }
+            else acc = __dadd_rn(acc, x);
+        }
+        out_cols[v * n_col + c] = acc;
+    }
+}
+
+// runs of equal (voxel rank << 16 | biased value) keys of one shard -> (voxel KEY << 16 | biased value, run length)
+__global__ void __launch_bounds__(256) mode_runs_kernel(const unsigned long long* __restrict__ run_keys, const uint32_t* __restrict__ run_starts,
+                                                        unsigned long long n_runs, const unsigned long long* __restrict__ voxel_keys,
+                                                        unsigned long long* __restrict__ out_keys, uint32_t* __restrict__ out_counts) {
+    const unsigned long long step = (unsigned long long)gridDim.x * blockDim.x;
+    for (unsigned long long r = (unsigned long long)blockIdx.x * blockDim.x + threadIdx.x; r < n_runs; r += step) {
+        const unsigned long long k = run_keys[r];
+        out_keys[r] = (voxel_keys[k >> 16] << 16) | (k & 0xFFFFull);
+        out_counts[r] = run_starts[r + 1] - run_starts[r];
+    }
+}
+
+// merged runs vote: total count of a (voxel, value) pair over all shards competes for its voxel (found by binary search
+// in the merged voxel keys); the largest count wins, ties go to the smallest value -- the rule of the single-device filter
+__global__ void __launch_bounds__(256) mode_merge_vote_kernel(const uint32_t* __restrict__ starts, const uint32_t* __restrict__ sorted_idx,
+                                                              const unsigned long long* __restrict__ run_keys, unsigned long long n_runs,
+                                                              const uint32_t* __restrict__ in_counts,
+                                                              const unsigned long long* __restrict__ voxel_keys, unsigned long long n_voxels,
+                                                              unsigned long long* __restrict__ best) {
+    const unsigned long long step = (unsigned long long)gridDim.x * blockDim.x;
+    for (unsigned long long r = (unsigned long long)blockIdx.x * blockDim.x + threadIdx.x; r < n_runs; r += step) {
+        unsigned long long total = 0;
+        for (uint32_t k = starts[r], e = starts[r + 1]; k < e; ++k) total += in_counts[sorted_idx[k]];
+        const unsigned long long comp = run_keys[r], vkey = comp >> 16;
+        unsigned long long lo = 0, hi = n_voxels;  // first voxel with key >= vkey (it exists: every run belongs to a merged voxel)
+        while (lo < hi) { const unsigned long long mid = lo + (hi - lo) / 2; if (voxel_keys[mid] < vkey) lo = mid + 1; else hi = mid; }
+        if (lo < n_voxels && voxel_keys[lo] == vkey) atomicMax(&best[lo], (total << 16) | (65535ull - (comp & 0xFFFFull)));
+    }
+}
+
+// merged columns -> attribute values: the division by the point count and the reference's casts (voxel_grid.rs:461-679)
+__global__ void __launch_bounds__(256) finalize_columns_kernel(int kind, const double* __restrict__ cols, uint32_t n_col, uint32_t col0,
+                                                               const uint32_t* __restrict__ counts, unsigned long long n_voxels,
+                                                               uint8_t* __restrict__ dst, uint32_t dst_size) {
+    const unsigned long long step = (unsigned long long)gridDim.x * blockDim.x;
+    for (unsigned long long v = (unsigned long long)blockIdx.x * blockDim.x + threadIdx.x; v < n_voxels; v += step) {
+        const double* c = cols + v * n_col + col0;
+        uint8_t* out = dst + v * dst_size;
+        const double cnt = (double)counts[v];
+        auto u16 = [](double x) { unsigned long long u = f64_as_u64_sat(x); return (uint16_t)(u > 65535ull ? 65535ull : u); };
+        switch (kind) {
+            case R_MEAN_U16: { const uint16_t r = u16(c[0] / cnt); memcpy(out, &r, 2); break; }
+            case R_MEAN_VEC_U16: { const uint16_t r[3] = {u16(c[0] / cnt), u16(c[1] / cnt), u16(c[2] / cnt)}; memcpy(out, r, 6); break; }
+            case R_MEAN_VEC_F32: { const float r[3] = {(float)(c[0] / cnt), (float)(c[1] / cnt), (float)(c[2] / cnt)}; memcpy(out, r, 12); break; }
+            case R_MAX_U8: { unsigned long long u = f64_as_u64_sat(c[0]); const uint8_t r = (uint8_t)(u > 255ull ? 255ull : u); memcpy(out, &r, 1); break; }
+            case R_MAX_F64: { memcpy(out, c, 8); break; }
+            case R_MAX_U64: { const unsigned long long r = f64_as_u64_sat(c[0]); memcpy(out, &r, 8); break; }
+            default: break;
+        }
+    }
+}
+
 struct VoxelIndex {
     DevTmp sorted_keys, sorted_idx, starts, voxel_keys, tiles;  // N, N, V+1, V, tiles+1
     uint64_t V = 0, n = 0;
@@ -883,6 +971,8 @@ int pb200_voxelgrid_filter(pb200_ctx* ctx, const pb200_buffer_desc* src, double 
     for (size_t a = 0; a < dst_layout->attrs.size(); ++a) {
         if ((int)a == a_pos) continue;  // done by the fused boundary pass
         ReduceArgs ra;
+        ra.partial = nullptr;
+        ra.partial_stride = 0;
         uint64_t sstride = 0;
         ra.src = attr_ptr(src_idx[a], &sstride);
         ra.src_stride = sstride;
@@ -1102,6 +1192,333 @@ int pb200_voxelgrid_merge_partials(pb200_ctx* ctx, const uint64_t* keys, const u
     return PB200_OK;
 }
 
+// ---- sharded grid with attributes -----------------------------------------------------------------------------
+namespace {
+
+// how the attributes of a filtered layout travel between shards: Position3D through (count, sums); mean and max-pool
+// attributes as columns; "most common value" attributes as run lists.  The same walk over dst_layout on both sides
+// (partials, merge) yields the same column / list numbering.
+struct AttrPlan {
+    std::vector<const Rule*> rules;
+    std::vector<int> col0;      // first column of attribute a, -1 if it has none
+    std::vector<int> mode_no;   // list number of attribute a, -1 if it is not a mode attribute
+    uint32_t n_col = 0, n_modes = 0;
+    ColOps ops;
+};
+
+int plan_attrs(const pb200_layout* dst_layout, AttrPlan* pl) {
+    static const char* WAVE[] = {"WaveformDataOffset", "WaveformPacketSize", "WaveformParameters", "WavePacketDescriptorIndex", "ReturnPointWaveformLocation"};
+    static const uint32_t WAVE_T[] = {PB200_U64, PB200_U32, PB200_VEC3F32, PB200_U8, PB200_F32};
+    for (int w = 0; w < 5; ++w)
+        if (pb200_layout_index_of(dst_layout, WAVE[w], WAVE_T[w]) >= 0) return set_error(PB200_ERR_UNSUPPORTED, "Waveform data currently not supported!");
+    memset(&pl->ops, 0, sizeof pl->ops);
+    for (const auto& a : dst_layout->attrs) {
+        const Rule* r = find_rule(a);
+        if (!r) return set_error(PB200_ERR_UNSUPPORTED, "attribute is non-standard which is not supported currently: %s", a.name);
+        pl->rules.push_back(r);
+        int c0 = -1, mn = -1;
+        uint32_t w = 0;
+        bool mx = false;
+        switch (r->kind) {
+            case R_MEAN_VEC_F64: break;  // position: (count, sums)
+            case R_MEAN_U16: w = 1; break;
+            case R_MEAN_VEC_U16: case R_MEAN_VEC_F32: w = 3; break;
+            case R_MAX_U8: case R_MAX_F64: case R_MAX_U64: w = 1; mx = true; break;
+            case R_MODE: case R_MODE_BOOL: mn = (int)pl->n_modes++; break;
+        }
+        if (w) {
+            if (pl->n_col + w > 64) return set_error(PB200_ERR_UNSUPPORTED, "more than 64 partial columns");
+            c0 = (int)pl->n_col;
+            for (uint32_t k = 0; k < w; ++k) pl->ops.is_max[pl->n_col + k] = mx ? 1 : 0;
+            pl->n_col += w;
+        }
+        pl->col0.push_back(c0);
+        pl->mode_no.push_back(mn);
+    }
+    return PB200_OK;
+}
+
+// run starts / run keys of an ascending key array (shift 0): the heads machinery of the voxel boundaries
+int key_runs(pb200_ctx* ctx, const unsigned long long* sorted_keys, uint64_t m, DevTmp* starts, DevTmp* run_keys, uint64_t* n_runs) {
+    cudaStream_t st = ctx->stream;
+    DevTmp d_tiles;
+    const uint32_t n_tiles = (uint32_t)((m + HT_TILE - 1) / HT_TILE);
+    PB_CUDA(d_tiles.alloc(st, ((size_t)n_tiles + 1) * 4));
+    uint32_t* d_total = (uint32_t*)d_tiles.p + n_tiles;
+    heads_count_kernel<<<n_tiles, HT_THREADS, 0, st>>>(sorted_keys, m, 0u, (uint32_t*)d_tiles.p);
+    PB_TRY(exclusive_scan_u32(ctx, (uint32_t*)d_tiles.p, n_tiles, d_total));
+    uint32_t* h_total = (uint32_t*)ctx->h_scratch;
+    PB_CUDA(cudaMemcpyAsync(h_total, d_total, 4, cudaMemcpyDeviceToHost, st));
+    PB_CUDA(cudaStreamSynchronize(st));
+    const uint64_t R = *h_total;
+    *n_runs = R;
+    PB_CUDA(starts->alloc(st, (R + 1) * 4));
+    PB_CUDA(run_keys->alloc(st, R * 8 + 8));
+    heads_emit_kernel<<<n_tiles, HT_THREADS, 0, st>>>(sorted_keys, m, 0u, (const uint32_t*)d_tiles.p, (uint32_t)R, (uint32_t*)starts->p,
+                                                      (unsigned long long*)run_keys->p, nullptr);
+    g_launches += 3;
+    PB_CUDA(cudaGetLastError());
+    return PB200_OK;
+}
+
+unsigned grid_cap(pb200_ctx* ctx, uint64_t n) {
+    const unsigned long long cap = (unsigned long long)ctx->sm_count * 16, want = (n + 255) / 256;
+    return (unsigned)(want < cap ? (want ? want : 1) : cap);
+}
+
+}  // namespace
+
+int pb200_voxelgrid_partials_layout(pb200_ctx* ctx, const pb200_buffer_desc* src, double lx, double ly, double lz,
+                                    const double global_min[3], const double global_max[3], const pb200_layout* dst_layout,
+                                    pb200_voxel_partials** out) {
+    if (!ctx || !out || !global_min || !global_max || !dst_layout) return set_error(PB200_ERR_INVALID, "null argument");
+    *out = nullptr;
+    PB_TRY(validate_desc(src, "source buffer"));
+    PB_DEVICE(ctx);
+    if (src->memspace != PB200_DEVICE) return set_error(PB200_ERR_UNSUPPORTED, "attribute partials need a device-resident shard");
+    const double leaf[3] = {lx, ly, lz};
+    for (int c = 0; c < 3; ++c) {
+        if (!(leaf[c] > 0.0)) return set_error(PB200_ERR_INVALID, "leaf sizes must be positive (the reference would not terminate)");
+        if (!(global_min[c] <= global_max[c])) return set_error(PB200_ERR_INVALID, "global bounds: min > max (AABB::from_min_max panics)");
+    }
+    if (src->len > 0xFFFFFFFFull) return set_error(PB200_ERR_UNSUPPORTED, "more than 2^32-1 points per call");
+    AttrPlan ap;
+    PB_TRY(plan_attrs(dst_layout, &ap));
+    std::vector<int> src_idx;
+    for (size_t a = 0; a < ap.rules.size(); ++a) {
+        const int si = pb200_layout_index_of(src->layout, ap.rules[a]->name, ap.rules[a]->dtype);
+        if (si < 0) return set_error(PB200_ERR_ATTR_NOT_FOUND, "source buffer has no attribute %s with the default datatype", ap.rules[a]->name);
+        src_idx.push_back(si);
+    }
+    cudaStream_t st = ctx->stream;
+    pb200_voxel_partials* res = new pb200_voxel_partials();
+    res->ctx = ctx;
+    res->n_col = ap.n_col;
+    res->n_modes = ap.n_modes;
+    memcpy(res->col_is_max, ap.ops.is_max, 64);
+    auto fail = [&](int rc) { pb200_voxel_partials_destroy(res); return rc; };
+    if (src->len == 0) {  // an empty shard contributes nothing; grid geometry is still reported
+        for (int c = 0; c < 3; ++c) {
+            uint64_t cnt = 0;
+            for (double cur = global_min[c]; cur < global_max[c]; cur += leaf[c])
+                if (++cnt > (1u << 21)) return fail(set_error(PB200_ERR_UNSUPPORTED, "more than 2^21 voxels along one axis"));
+            res->cells[c] = cnt;
+        }
+        res->bits_x = bits_for(res->cells[0]); res->bits_y = bits_for(res->cells[1]); res->bits_z = bits_for(res->cells[2]);
+        *out = res;
+        return PB200_OK;
+    }
+    DevTmp staged;
+    const uint8_t* ppos = nullptr;
+    uint64_t pstride = 0;
+    int rc = voxel_positions(ctx, src, &staged, &ppos, &pstride);
+    if (rc < 0) return fail(rc);
+    VoxelIndex vi;
+    rc = voxel_index_sort(ctx, ppos, pstride, src->len, global_min, global_max, leaf, &vi);
+    if (rc < 0) return fail(rc);
+    const uint64_t V = vi.V, n = src->len;
+    res->len = V;
+    res->bits_x = vi.bits_x; res->bits_y = vi.bits_y; res->bits_z = vi.bits_z;
+    for (int c = 0; c < 3; ++c) res->cells[c] = vi.cells[c];
+    if (vi.bits_x + vi.bits_y + vi.bits_z > 48 && ap.n_modes) return fail(set_error(PB200_ERR_UNSUPPORTED, "mode attributes need voxel keys of at most 48 bits"));
+    if (cache_alloc(ctx, &res->counts, V * 4 + 4) != cudaSuccess || cache_alloc(ctx, &res->sums, V * 24 + 8) != cudaSuccess)
+        return fail(set_error(PB200_ERR_OOM, "out of device memory"));
+    const bool need_index = ap.n_col + ap.n_modes > 0;
+    rc = voxel_index_emit(ctx, &vi, 1, (double*)res->sums, (uint32_t*)res->counts, need_index);
+    if (rc < 0) return fail(rc);
+    auto attr_ptr = [&](int idx, uint64_t* stride) -> const uint8_t* {
+        const pb200_attr& a = src->layout->attrs[(size_t)idx];
+        if (src->kind == PB200_INTERLEAVED) { *stride = src->layout->size; return (const uint8_t*)src->aos + a.offset; }
+        *stride = a.size;
+        return (const uint8_t*)src->columns[idx];
+    };
+    if (ap.n_col && cache_alloc(ctx, &res->cols, (size_t)V * ap.n_col * 8 + 8) != cudaSuccess) return fail(set_error(PB200_ERR_OOM, "out of device memory"));
+    DevTmp d_mk, d_mk2;
+    if (ap.n_modes && (d_mk.alloc(st, n * 8) != cudaSuccess || d_mk2.alloc(st, n * 8) != cudaSuccess)) return fail(set_error(PB200_ERR_OOM, "out of device memory"));
+    for (size_t a = 0; a < ap.rules.size(); ++a) {
+        const Rule& r = *ap.rules[a];
+        uint64_t sstride = 0;
+        const uint8_t* sp = attr_ptr(src_idx[a], &sstride);
+        const uint64_t comp = pb200_dtype_size(is_cast_vec3(r.dtype) ? vec3_component(r.dtype) : r.dtype, 0);
+        const int aligned = (((uintptr_t)sp % comp) == 0 && (sstride % comp) == 0) ? 1 : 0;
+        if (ap.col0[a] >= 0) {
+            PB_PHASE(ctx, "voxel.partial_columns");
+            ReduceArgs ra;
+            ra.starts = (const uint32_t*)vi.starts.p;
+            ra.sorted_idx = (const uint32_t*)vi.sorted_idx.p;
+            ra.n_voxels = V;
+            ra.src = sp;
+            ra.src_stride = sstride;
+            ra.dst = nullptr;
+            ra.dst_size = 0;
+            ra.src_aligned = aligned;
+            ra.partial = (double*)res->cols + ap.col0[a];
+            ra.partial_stride = ap.n_col;
+            launch_reduce(r, ra, st);
+        } else if (ap.mode_no[a] >= 0) {
+            PB_PHASE(ctx, "voxel.partial_mode_runs");
+            const int mno = ap.mode_no[a];
+            unsigned long long* mk = (unsigned long long*)d_mk.p;
+            const uint32_t *sts = (const uint32_t*)vi.starts.p, *si2 = (const uint32_t*)vi.sorted_idx.p;
+            const unsigned blocks = grid_cap(ctx, n);
+            if (r.dtype == PB200_U8) mode_keys_kernel<uint8_t><<<blocks, 256, 0, st>>>(sts, (uint32_t)V, si2, n, sp, sstride, aligned, mk);
+            else if (r.dtype == PB200_I8) mode_keys_kernel<int8_t><<<blocks, 256, 0, st>>>(sts, (uint32_t)V, si2, n, sp, sstride, aligned, mk);
+            else if (r.dtype == PB200_I16) mode_keys_kernel<int16_t><<<blocks, 256, 0, st>>>(sts, (uint32_t)V, si2, n, sp, sstride, aligned, mk);
+            else mode_keys_kernel<uint16_t><<<blocks, 256, 0, st>>>(sts, (uint32_t)V, si2, n, sp, sstride, aligned, mk);
+            g_launches++;
+            bool in_alt = false;
+            rc = radix_sort_u64(ctx, mk, (unsigned long long*)d_mk2.p, nullptr, nullptr, n, 0, 16 + (int)bits_for(V + 1), &in_alt);
+            if (rc < 0) return fail(rc);
+            const unsigned long long* sorted_mk = in_alt ? (const unsigned long long*)d_mk2.p : mk;
+            DevTmp run_starts, run_keys;
+            uint64_t R = 0;
+            rc = key_runs(ctx, sorted_mk, n, &run_starts, &run_keys, &R);
+            if (rc < 0) return fail(rc);
+            if (cache_alloc(ctx, &res->mode_keys[mno], R * 8 + 8) != cudaSuccess || cache_alloc(ctx, &res->mode_counts[mno], R * 4 + 4) != cudaSuccess)
+                return fail(set_error(PB200_ERR_OOM, "out of device memory"));
+            res->mode_len[mno] = R;
+            mode_runs_kernel<<<grid_cap(ctx, R), 256, 0, st>>>((const unsigned long long*)run_keys.p, (const uint32_t*)run_starts.p, R,
+                                                              (const unsigned long long*)vi.voxel_keys.p, (unsigned long long*)res->mode_keys[mno],
+                                                              (uint32_t*)res->mode_counts[mno]);
+            g_launches++;
+        }
+    }
+    {
+        cudaError_t e = cudaGetLastError();
+        if (e != cudaSuccess) return fail(cuda_error(e, "attribute partials"));
+    }
+    res->keys = vi.voxel_keys.p;
+    vi.voxel_keys.p = nullptr;  // ownership moves to the result
+    *out = res;
+    return PB200_OK;
+}
+
+int pb200_voxel_partials_get_attrs(const pb200_voxel_partials* p, pb200_voxel_attr_partials_desc* out) {
+    if (!p || !out) return set_error(PB200_ERR_INVALID, "null argument");
+    memset(out, 0, sizeof(*out));
+    out->n_columns = p->n_col;
+    out->n_modes = p->n_modes;
+    out->columns = (const double*)p->cols;
+    memcpy(out->column_is_max, p->col_is_max, 64);
+    for (uint32_t a = 0; a < PB200_MAX_ATTRIBUTES; ++a) {
+        out->mode_len[a] = p->mode_len[a];
+        out->mode_keys[a] = (const uint64_t*)p->mode_keys[a];
+        out->mode_counts[a] = (const uint32_t*)p->mode_counts[a];
+    }
+    return PB200_OK;
+}
+
+int pb200_voxelgrid_merge_partials_layout(pb200_ctx* ctx, const pb200_layout* dst_layout, const pb200_voxel_partials_desc* pos,
+                                          const pb200_voxel_attr_partials_desc* attrs, pb200_result_buffer** out) {
+    if (!ctx || !dst_layout || !pos || !attrs || !out) return set_error(PB200_ERR_INVALID, "null argument");
+    *out = nullptr;
+    const uint64_t m = pos->len;
+    if (m && (!pos->keys || !pos->counts || !pos->sums)) return set_error(PB200_ERR_INVALID, "null partial arrays");
+    if (m > 0xFFFFFFFEull) return set_error(PB200_ERR_UNSUPPORTED, "more than 2^32-2 partial voxels per call");
+    const int key_bits = (int)(pos->bits_x + pos->bits_y + pos->bits_z);
+    if (key_bits > 64 || key_bits == 0) return set_error(PB200_ERR_INVALID, "bad key widths");
+    AttrPlan ap;
+    PB_TRY(plan_attrs(dst_layout, &ap));
+    if (ap.n_col != attrs->n_columns || ap.n_modes != attrs->n_modes) return set_error(PB200_ERR_LAYOUT_MISMATCH, "attribute partials do not belong to this layout");
+    if (ap.n_col && m && !attrs->columns) return set_error(PB200_ERR_INVALID, "null partial columns");
+    if (ap.n_modes && key_bits > 48) return set_error(PB200_ERR_UNSUPPORTED, "mode attributes need voxel keys of at most 48 bits");
+    PB_DEVICE(ctx);
+    cudaStream_t st = ctx->stream;
+    pb200_result_buffer* res = new pb200_result_buffer();
+    res->ctx = ctx;
+    res->layout = *dst_layout;
+    res->kind = PB200_COLUMNAR;
+    res->memspace = PB200_DEVICE;
+    res->bits_y = pos->bits_y;
+    res->bits_z = pos->bits_z;
+    res->columns.assign(dst_layout->attrs.size(), nullptr);
+    auto fail = [&](int rc) { pb200_result_buffer_destroy(res); return rc; };
+    if (m == 0) { *out = res; return PB200_OK; }
+    // ---- voxels: sort the concatenated partial keys (stable: source-rank order inside a voxel), find the runs -------------
+    DevTmp d_keys1, d_keys2, d_idx, d_idx2, d_starts, d_vkeys, d_counts, d_sums, d_cols;
+    uint64_t V = 0;
+    auto run = [&]() -> int {
+        PB_PHASE(ctx, "voxel.merge");
+        PB_CUDA(d_keys1.alloc(st, m * 8)); PB_CUDA(d_keys2.alloc(st, m * 8)); PB_CUDA(d_idx.alloc(st, m * 4)); PB_CUDA(d_idx2.alloc(st, m * 4));
+        iota_kernel<<<grid_cap(ctx, m), 256, 0, st>>>((uint32_t*)d_idx.p, m);
+        PB_CUDA(cudaMemcpyAsync(d_keys1.p, pos->keys, m * 8, cudaMemcpyDeviceToDevice, st));
+        bool in_alt = false;
+        PB_TRY(radix_sort_u64(ctx, (unsigned long long*)d_keys1.p, (unsigned long long*)d_keys2.p, (uint32_t*)d_idx.p, (uint32_t*)d_idx2.p,
+                              m, 0, key_bits, &in_alt));
+        if (!in_alt) { std::swap(d_keys1.p, d_keys2.p); std::swap(d_idx.p, d_idx2.p); }
+        PB_TRY(key_runs(ctx, (const unsigned long long*)d_keys2.p, m, &d_starts, &d_vkeys, &V));
+        PB_CUDA(d_counts.alloc(st, V * 4 + 4)); PB_CUDA(d_sums.alloc(st, V * 24 + 8));
+        partials_merge_kernel<<<(unsigned)((V + 127) / 128), 128, 0, st>>>((const uint32_t*)d_starts.p, (const uint32_t*)d_idx2.p, V, pos->counts,
+                                                                           pos->sums, (uint32_t*)d_counts.p, (double*)d_sums.p);
+        if (ap.n_col) {
+            PB_CUDA(d_cols.alloc(st, (size_t)V * ap.n_col * 8 + 8));
+            partials_merge_columns_kernel<<<(unsigned)((V + 127) / 128), 128, 0, st>>>((const uint32_t*)d_starts.p, (const uint32_t*)d_idx2.p, V,
+                                                                                       attrs->columns, ap.n_col, ap.ops, (double*)d_cols.p);
+        }
+        g_launches += 3;
+        PB_CUDA(cudaGetLastError());
+        return PB200_OK;
+    };
+    int rc = run();
+    if (rc < 0) return fail(rc);
+    res->len = V;
+    for (size_t a = 0; a < dst_layout->attrs.size(); ++a)
+        if (cache_alloc(ctx, &res->columns[a], (size_t)(V * dst_layout->attrs[a].size) + 16) != cudaSuccess) return fail(set_error(PB200_ERR_OOM, "out of device memory"));
+    // ---- attribute values ------------------------------------------------------------------------------------------------
+    DevTmp d_best;
+    if (ap.n_modes && d_best.alloc(st, (V + 1) * 8) != cudaSuccess) return fail(set_error(PB200_ERR_OOM, "out of device memory"));
+    for (size_t a = 0; a < ap.rules.size(); ++a) {
+        const Rule& r = *ap.rules[a];
+        uint8_t* dst = (uint8_t*)res->columns[a];
+        const uint32_t dsz = (uint32_t)dst_layout->attrs[a].size;
+        if (r.kind == R_MEAN_VEC_F64) {
+            partials_centroid_kernel<<<grid_cap(ctx, V), 256, 0, st>>>((const uint32_t*)d_counts.p, (const double*)d_sums.p, V, (double*)dst);
+            g_launches++;
+        } else if (ap.col0[a] >= 0) {
+            finalize_columns_kernel<<<grid_cap(ctx, V), 256, 0, st>>>((int)r.kind, (const double*)d_cols.p, ap.n_col, (uint32_t)ap.col0[a],
+                                                                      (const uint32_t*)d_counts.p, V, dst, dsz);
+            g_launches++;
+        } else {
+            PB_PHASE(ctx, "voxel.merge_modes");
+            const int mno = ap.mode_no[a];
+            const uint64_t rl = attrs->mode_len[mno];
+            cudaMemsetAsync(d_best.p, 0, (V + 1) * 8, st);
+            if (rl) {
+                if (!attrs->mode_keys[mno] || !attrs->mode_counts[mno]) return fail(set_error(PB200_ERR_INVALID, "null run list"));
+                if (rl > 0xFFFFFFFEull) return fail(set_error(PB200_ERR_UNSUPPORTED, "more than 2^32-2 runs per call"));
+                DevTmp k1, k2, i1, i2, rs, rk;
+                if (k1.alloc(st, rl * 8) != cudaSuccess || k2.alloc(st, rl * 8) != cudaSuccess || i1.alloc(st, rl * 4) != cudaSuccess ||
+                    i2.alloc(st, rl * 4) != cudaSuccess)
+                    return fail(set_error(PB200_ERR_OOM, "out of device memory"));
+                iota_kernel<<<grid_cap(ctx, rl), 256, 0, st>>>((uint32_t*)i1.p, rl);
+                cudaMemcpyAsync(k1.p, attrs->mode_keys[mno], rl * 8, cudaMemcpyDeviceToDevice, st);
+                bool in_alt = false;
+                rc = radix_sort_u64(ctx, (unsigned long long*)k1.p, (unsigned long long*)k2.p, (uint32_t*)i1.p, (uint32_t*)i2.p, rl, 0, key_bits + 16, &in_alt);
+                if (rc < 0) return fail(rc);
+                if (!in_alt) { std::swap(k1.p, k2.p); std::swap(i1.p, i2.p); }
+                uint64_t R = 0;
+                rc = key_runs(ctx, (const unsigned long long*)k2.p, rl, &rs, &rk, &R);
+                if (rc < 0) return fail(rc);
+                mode_merge_vote_kernel<<<grid_cap(ctx, R), 256, 0, st>>>((const uint32_t*)rs.p, (const uint32_t*)i2.p, (const unsigned long long*)rk.p, R,
+                                                                        attrs->mode_counts[mno], (const unsigned long long*)d_vkeys.p, V,
+                                                                        (unsigned long long*)d_best.p);
+                g_launches += 2;
+            }
+            mode_decode_kernel<<<grid_cap(ctx, V), 256, 0, st>>>((const unsigned long long*)d_best.p, V, dst, dsz, r.kind == R_MODE_BOOL ? 1 : 0,
+                                                                (r.dtype == PB200_I8 || r.dtype == PB200_I16) ? 32768ll : 0ll);
+            g_launches++;
+        }
+    }
+    {
+        cudaError_t e = cudaGetLastError();
+        if (e != cudaSuccess) return fail(cuda_error(e, "merge of attribute partials"));
+    }
+    res->d_packed_keys = d_vkeys.p;
+    d_vkeys.p = nullptr;  // ownership moves to the result
+    *out = res;
+    return PB200_OK;
+}
+
 int pb200_voxel_partials_get(const pb200_voxel_partials* p, pb200_voxel_partials_desc* out) {
     if (!p || !out) return set_error(PB200_ERR_INVALID, "null argument");
     out->len = p->len;
@@ -1128,7 +1545,10 @@ int pb200_voxel_partials_centroids(const pb200_voxel_partials* p, double* positi
 void pb200_voxel_partials_destroy(pb200_voxel_partials* p) {
     if (!p) return;
     if (p->ctx) cudaSetDevice(p->ctx->device);
-    if (p->ctx) { cache_free(p->ctx, p->keys); cache_free(p->ctx, p->counts); cache_free(p->ctx, p->sums); }
+    if (p->ctx) {
+        cache_free(p->ctx, p->keys); cache_free(p->ctx, p->counts); cache_free(p->ctx, p->sums); cache_free(p->ctx, p->cols);
+        for (uint32_t a = 0; a < PB200_MAX_ATTRIBUTES; ++a) { cache_free(p->ctx, p->mode_keys[a]); cache_free(p->ctx, p->mode_counts[a]); }
+    }
     delete p;
 }
 

@@ -101,6 +101,98 @@ def voxelgrid_filter_sharded(shard, leafsize_x, leafsize_y, leafsize_z, group=No
     return alg.voxelgrid_merge_partials(keys, counts, sums, part.bits, part.cells, ctx)
 
 
+def balanced_key_boundaries(sorted_keys, world_size, group=None, samples=2048):
+    """W - 1 splitter keys such that every rank finalises about the same number of voxels WHATEVER the cloud looks like:
+    each rank contributes `samples` evenly spaced quantiles of its own (ascending) partial keys, the gathered samples are
+    sorted and cut into W equal parts.  (Equal x-index ranges, the round-1 rule, leave most ranks idle for any cloud that
+    does not fill its bounding box evenly.)  A key k belongs to rank = number of splitters <= k."""
+    have = dist.is_available() and dist.is_initialized()
+    world = dist.get_world_size(group) if have else 1
+    if world_size <= 1:
+        return []
+    m = int(sorted_keys.numel())
+    dev = sorted_keys.device
+    if m:
+        pos = torch.linspace(0, m - 1, samples, device=dev).round().long()
+        mine = sorted_keys[pos]
+    else:
+        mine = torch.full((samples,), -1, dtype=sorted_keys.dtype, device=dev)  # -1: no contribution
+    if world > 1:
+        allk = [torch.empty_like(mine) for _ in range(world)]
+        dist.all_gather(allk, mine, group=group)
+        allk = torch.cat(allk)
+    else:
+        allk = mine
+    allk = allk[allk >= 0]
+    if allk.numel() == 0:
+        return [0] * (world_size - 1)
+    allk = torch.sort(allk).values
+    cuts = [int(allk[min(allk.numel() - 1, (d * allk.numel()) // world_size)].item()) for d in range(1, world_size)]
+    return cuts
+
+
+def _all_to_all_rows(t, send_sizes, recv_sizes, group):
+    out = torch.empty((sum(recv_sizes),) + tuple(t.shape[1:]), dtype=t.dtype, device=t.device)
+    dist.all_to_all_single(out, t.contiguous(), list(recv_sizes), list(send_sizes), group=group)
+    return out
+
+
+def _exchange_sizes(send_sizes, device, group):
+    sent = torch.tensor(send_sizes, dtype=torch.int64, device=device)
+    recv = torch.empty_like(sent)
+    dist.all_to_all_single(recv, sent, group=group)
+    return recv.tolist()
+
+
+def voxelgrid_filter_sharded_layout(shard, leafsize_x, leafsize_y, leafsize_z, filtered_layout=None, group=None, ctx=None,
+                                    return_keys=False, timings=None):
+    """voxel_grid.rs:109-165 with ALL attribute reductions over a cloud sharded by point range (one shard per rank):
+    global AABB (all-reduce) -> per-shard partials for every attribute of `filtered_layout` -> balanced key-range
+    boundaries from sampled keys -> ONE set of key-range all-to-alls (voxel rows, then one run list per mode attribute)
+    -> merge.  Returns this rank's part of the filtered cloud (a HashMapBuffer; concatenating the ranks' parts in rank
+    order gives the reference's output order) or None for an empty cloud.  `timings` (a dict) receives per-phase
+    milliseconds (device-synchronised) when given."""
+    import time
+    from . import algorithms as alg
+    have = dist.is_available() and dist.is_initialized()
+    world = dist.get_world_size(group) if have else 1
+    layout = filtered_layout or shard.point_layout()
+
+    def mark(name, t0):
+        if timings is not None:
+            torch.cuda.synchronize(shard.device)
+            timings[name] = timings.get(name, 0.0) + (time.perf_counter() - t0) * 1e3
+        return time.perf_counter()
+    t0 = time.perf_counter()
+    b = alg.calculate_bounds(shard) if shard.len() else None
+    v = pack_bounds(None if b is None else (b.min(), b.max()), shard.device)
+    g = unpack_bounds(allreduce_bounds(v, group))
+    t0 = mark("bounds+allreduce", t0)
+    if g is None:
+        return None
+    part = alg.voxelgrid_partials_layout(shard, leafsize_x, leafsize_y, leafsize_z, g, layout, ctx)
+    t0 = mark("partials", t0)
+    if world > 1:
+        bounds = balanced_key_boundaries(part.pos.keys, world, group)
+        send = split_sizes(part.pos.keys, bounds)
+        recv = _exchange_sizes(send, shard.device, group)
+        pos = part.pos
+        keys = _all_to_all_rows(pos.keys, send, recv, group)
+        counts = _all_to_all_rows(pos.counts, send, recv, group)
+        sums = _all_to_all_rows(pos.sums, send, recv, group)
+        cols = _all_to_all_rows(part.columns, send, recv, group) if part.columns.shape[1] else torch.empty((keys.numel(), 0), dtype=torch.float64, device=shard.device)
+        modes = []
+        for mk, mc in part.modes:  # run lists are ascending in (voxel key << 16 | value): the same splitters, shifted
+            msend = split_sizes(mk, [bk << 16 for bk in bounds])
+            mrecv = _exchange_sizes(msend, shard.device, group)
+            modes.append((_all_to_all_rows(mk, msend, mrecv, group), _all_to_all_rows(mc, msend, mrecv, group)))
+        part = alg.VoxelAttrPartials(alg.VoxelPartials(keys, counts, sums, pos.bits, pos.cells), cols, part.column_is_max, modes)
+        t0 = mark("all_to_all", t0)
+    out = alg.voxelgrid_merge_partials_layout(part, layout, ctx, return_keys=return_keys)
+    mark("merge", t0)
+    return out
+
+
 # ---- minmax_attribute over point-range shards (SURVEY 8e: "minmax ints: same with the attribute's dtype") --------------
 
 def combine_minmax(local, first_value, attribute, group=None, device="cpu"):
