@@ -113,7 +113,7 @@ def balanced_key_boundaries(sorted_keys, world_size, group=None, samples=2048):
     m = int(sorted_keys.numel())
     dev = sorted_keys.device
     if m:
-        pos = torch.linspace(0, m - 1, samples, device=dev).round().long()
+        pos = (torch.arange(samples, device=dev, dtype=torch.int64) * (m - 1)) // max(1, samples - 1)  # exact integer quantiles
         mine = sorted_keys[pos]
     else:
         mine = torch.full((samples,), -1, dtype=sorted_keys.dtype, device=dev)  # -1: no contribution

@@ -251,3 +251,89 @@ def test_sharded_voxelgrid_single_process_and_empty():
     b = pb.algorithms.calculate_bounds(whole)
     p = pb.algorithms.voxelgrid_partials(empty, 0.5, 0.5, 0.5, b)  # an empty shard of a non-empty cloud
     assert p.len() == 0 and p.cells[0] > 0
+
+
+# ---- sharded voxel grid with every attribute reduction (pb200_voxelgrid_partials_layout / _merge_partials_layout) ---------
+
+def _slice_buffer(buf, pl, lo, hi):
+    return HashMapBuffer(pl, hi - lo, "cuda", columns=[c[lo * pl.at(i).size(): hi * pl.at(i).size()] for i, c in enumerate(buf.columns)])
+
+
+def _cat_partials(parts):
+    from pasture_b200.algorithms import VoxelAttrPartials, VoxelPartials
+    pos = VoxelPartials(torch.cat([p.pos.keys for p in parts]), torch.cat([p.pos.counts for p in parts]), torch.cat([p.pos.sums for p in parts]),
+                        parts[0].pos.bits, parts[0].pos.cells)
+    cols = torch.cat([p.columns for p in parts])
+    modes = [(torch.cat([p.modes[a][0] for p in parts]), torch.cat([p.modes[a][1] for p in parts])) for a in range(len(parts[0].modes))]
+    return VoxelAttrPartials(pos, cols, parts[0].column_is_max, modes)
+
+
+@pytest.mark.parametrize("seed,n,leaf,shards", [(1, 30000, (0.7, 0.9, 1.1), 3), (2, 50000, (0.25, 0.25, 0.25), 4), (3, 3002, (1.0, 1.0, 1.0), 2),
+                                                 (4, 20000, (40.0, 40.0, 40.0), 5)])
+def test_sharded_attribute_partials_merge_to_the_single_device_result(seed, n, leaf, shards):
+    """S logical shards on one GPU: per-shard partials of ALL attributes (columns for the mean / max-pool rules, run lists
+    for the "most common value" rules), concatenated in rank order and merged, must reproduce the single-device filter:
+    voxel keys, counts and every integer attribute exactly (u16 sums are exact in f64, mode = merged histogram arg-max
+    with ties to the smallest value, max-pool = max of maxima), f64 / f32 means within 1e-9 relative (the f64
+    summation order differs).  leaf 40: a handful of crowded voxels; shards of unequal size, one of them empty."""
+    from pasture_b200.algorithms import calculate_bounds, voxelgrid_merge_partials_layout, voxelgrid_partials_layout
+    rng = np.random.default_rng(seed)
+    attrs = [("Position3D", O.VEC3F64), ("Intensity", O.U16), ("Classification", O.U8), ("GpsTime", O.F64), ("ColorRGB", O.VEC3U16),
+             ("ScanAngleRank", O.I8), ("ScanAngle", O.I16), ("PointSourceID", O.U16), ("PointID", O.U64), ("Normal", O.VEC3F32),
+             ("EdgeOfFlightLine", O.U8), ("ClassificationFlags", O.U8), ("ReturnNumber", O.U8), ("NIR", O.U16)]
+    ol = O.OLayout.from_attributes(attrs)
+    ob = O.OBuffer(ol, n, True)
+    ob.set_attribute("Position3D", rng.random((n, 3)) * [20, 10, 3] - [5, 5, 1])
+    ob.set_attribute("Intensity", rng.integers(0, 65536, n))
+    ob.set_attribute("Classification", rng.integers(0, 4, n))
+    ob.set_attribute("GpsTime", rng.random(n) * 100 - 20)
+    ob.set_attribute("ColorRGB", rng.integers(0, 65536, (n, 3)))
+    ob.set_attribute("ScanAngleRank", rng.integers(-3, 3, n))
+    ob.set_attribute("ScanAngle", rng.integers(-300, 300, n))
+    ob.set_attribute("PointSourceID", rng.integers(0, 3, n))
+    ob.set_attribute("PointID", rng.integers(0, 2**52, n))
+    ob.set_attribute("Normal", rng.random((n, 3)).astype(np.float32) - 0.5)
+    ob.set_attribute("EdgeOfFlightLine", rng.integers(0, 2, n))
+    ob.set_attribute("ClassificationFlags", rng.integers(0, 256, n))
+    ob.set_attribute("ReturnNumber", rng.integers(0, 8, n))
+    ob.set_attribute("NIR", rng.integers(0, 65536, n))
+    pbuf, pl = to_product(ob, attrs, 0)
+    single, skeys = voxelgrid_filter(pbuf, *leaf, return_keys=True)
+    b = calculate_bounds(pbuf)
+    cuts = sorted(rng.integers(0, n, shards - 1).tolist())
+    cuts[0] = cuts[1] if shards > 2 else cuts[0]  # an empty shard in the middle
+    edges = [0] + cuts + [n]
+    parts = [voxelgrid_partials_layout(_slice_buffer(pbuf, pl, lo, hi), *leaf, b, pl) for lo, hi in zip(edges[:-1], edges[1:])]
+    assert sum(int(p.pos.counts.sum().item()) for p in parts) == n
+    merged, mkeys = voxelgrid_merge_partials_layout(_cat_partials(parts), pl, return_keys=True)
+    assert merged.len() == single.len() and np.array_equal(mkeys, skeys)
+    for i, (name, dt) in enumerate(attrs):
+        a, c = merged.view_attribute(name), single.view_attribute(name)
+        if dt in (O.VEC3F64, O.VEC3F32):
+            np.testing.assert_allclose(a, c, rtol=1e-6 if dt == O.VEC3F32 else 1e-9, atol=1e-12, err_msg=name)
+        else:
+            assert np.array_equal(a, c), name
+    # a target layout without positions and with a subset of the attributes
+    _, sub = util.layouts([("Classification", O.U8), ("Intensity", O.U16)])
+    parts = [voxelgrid_partials_layout(_slice_buffer(pbuf, pl, lo, hi), *leaf, b, sub) for lo, hi in zip(edges[:-1], edges[1:])]
+    m2 = voxelgrid_merge_partials_layout(_cat_partials(parts), sub)
+    assert np.array_equal(m2.view_attribute("Classification"), single.view_attribute("Classification"))
+    assert np.array_equal(m2.view_attribute("Intensity"), single.view_attribute("Intensity"))
+
+
+def test_sharded_layout_helper_single_process():
+    """no process group: sharding.voxelgrid_filter_sharded_layout == the single-device filter (all attributes)"""
+    from pasture_b200 import sharding
+    ol, ob = setup_point_cloud(5)
+    pbuf, pl = to_product(ob, COMPLETE, 1)
+    single, skeys = voxelgrid_filter(pbuf, 1.0, 1.0, 1.0, return_keys=True)
+    t = {}
+    out, keys = sharding.voxelgrid_filter_sharded_layout(pbuf, 1.0, 1.0, 1.0, return_keys=True, timings=t)
+    assert np.array_equal(keys, skeys) and set(t) >= {"bounds+allreduce", "partials", "merge"}
+    for i in range(len(pl)):
+        name = pl.at(i).name()
+        a, c = out.view_attribute(name), single.view_attribute(name)
+        if a.dtype.kind == "f":
+            np.testing.assert_allclose(a, c, rtol=1e-9, atol=1e-12, err_msg=name)
+        else:
+            assert np.array_equal(a, c), name

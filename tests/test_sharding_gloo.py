@@ -242,3 +242,55 @@ def test_sharded_minmax_exchange_equals_the_sequential_fold(case):
     for rank, res in results:
         mn, mx = (np.atleast_1d(np.asarray(x, dtype=values.dtype)) for x in res)
         assert np.array_equal(mn, emn, equal_nan=True) and np.array_equal(mx, emx, equal_nan=True), (case, rank, mn, emn, mx, emx)
+
+
+# ---- balanced key-range boundaries and the row exchange of the sharded voxel grid (host logic) ---------------------------
+
+def _boundary_worker(rank, world, port, out_q):
+    os.environ["MASTER_ADDR"] = "127.0.0.1"
+    os.environ["MASTER_PORT"] = str(port)
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    try:
+        rng = np.random.default_rng(100 + rank)
+        # a very uneven cloud: rank 0 sees only low keys, rank 1 a dense cluster, rank 2 nothing at all
+        if rank == 0:
+            keys = np.sort(rng.integers(0, 1 << 20, 5000))
+        elif rank == 1:
+            keys = np.sort(np.concatenate([rng.integers(1 << 30, (1 << 30) + 1000, 40000), rng.integers(0, 1 << 34, 3000)]))
+        else:
+            keys = np.zeros(0, dtype=np.int64)
+        keys = torch.from_numpy(np.unique(keys).astype(np.int64))
+        bounds = sharding.balanced_key_boundaries(keys, world)
+        send = sharding.split_sizes(keys, bounds)
+        recv = sharding._exchange_sizes(send, "cpu", None)
+        rows = torch.stack([keys, keys * 2], dim=1)
+        got = sharding._all_to_all_rows(rows, send, recv, None)
+        out_q.put((rank, bounds, send, got[:, 0].tolist(), bool((got[:, 1] == got[:, 0] * 2).all())))
+    finally:
+        dist.destroy_process_group()
+
+
+def test_balanced_boundaries_and_row_exchange():
+    world = 3
+    ctx = mp.get_context("spawn")
+    q = ctx.Queue()
+    port = _free_port()
+    procs = [ctx.Process(target=_boundary_worker, args=(r, world, port, q)) for r in range(world)]
+    for p in procs:
+        p.start()
+    results = sorted(q.get(timeout=120) for _ in range(world))
+    for p in procs:
+        p.join(timeout=60)
+        assert p.exitcode == 0
+    bounds = results[0][1]
+    assert all(r[1] == bounds for r in results) and bounds == sorted(bounds) and len(bounds) == world - 1  # the same splitters everywhere
+    assert all(r[4] for r in results)  # rows travel intact
+    received = [r[3] for r in results]
+    sizes = [len(x) for x in received]
+    total = sum(sizes)
+    assert total == sum(sum(r[2]) for r in results)
+    assert max(sizes) < 0.6 * total  # the cluster is split up: no rank gets (nearly) everything, as equal key RANGES would give
+    for d, keys in enumerate(received):  # ownership: rank d holds exactly the keys between its splitters
+        lo = bounds[d - 1] if d > 0 else -1
+        hi = bounds[d] if d < world - 1 else 1 << 62
+        assert all(lo <= k < hi for k in keys) or d == 0 and all(k < hi for k in keys)
