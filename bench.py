@@ -218,7 +218,7 @@ def other_configs(pb, ctx, dev, peak):
                "kernel_ms_sum": sum(m for nm, m in phases if not nm.endswith(".call") and not nm.startswith(("host.", "pool."))),
                "pool_MB": {nm: m for nm, m in phases if nm.startswith("pool.")},
                "call_ms_profiled": next((m for nm, m in phases if nm.endswith(".call")), None),
-               "host_timeline_us": [(nm, round(a), round(b)) for nm, a, b in ctx.last_profile_host_us],
+               "host_timeline_us": [(nm, round(a), round(b)) for nm, a, b in ctx.last_profile_host_us if not nm.startswith("pool.")],
                "clocks": clocks.summary(),
                "timing": "CUDA events around the whole library call (best of %d, device-resident input, includes the "
                          "call's host synchronisations); kernels: one extra profiled call" % reps}

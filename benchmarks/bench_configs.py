@@ -16,20 +16,42 @@ import pasture_b200 as pb  # noqa: E402
 from pasture_b200 import algorithms as alg  # noqa: E402
 
 
+LAST_CLOCKS = None
+
+
 def timed(fn, reps=3, warm=1):
+    """best of `reps` CUDA-event timings; the SM clock / throttle reasons are sampled over the timed repetitions (NVML,
+    bench.py's ClockSampler) and attached to the next emitted line"""
+    global LAST_CLOCKS
+    from bench import ClockSampler
     for _ in range(warm):
         fn()
     torch.cuda.synchronize()
     best = None
-    for _ in range(reps):
-        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-        e0.record()
-        fn()
-        e1.record()
-        torch.cuda.synchronize()
-        ms = e0.elapsed_time(e1)
-        best = ms if best is None or ms < best else best
+    with ClockSampler(torch.cuda.current_device()) as clocks:
+        for _ in range(reps):
+            e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            e0.record()
+            fn()
+            e1.record()
+            torch.cuda.synchronize()
+            ms = e0.elapsed_time(e1)
+            best = ms if best is None or ms < best else best
+    LAST_CLOCKS = clocks.summary()
     return best
+
+
+def fp64_peak_ginstr():
+    """measured FP64 instruction rate (benchmarks/fp64_probe.cu, non-fused DMUL/DADD), G instructions/s; None if the probe
+    binary is missing"""
+    import subprocess
+    exe = os.path.join(ROOT, "benchmarks", "build", "fp64_probe")
+    try:
+        out = subprocess.run([exe], capture_output=True, text=True, timeout=120).stdout
+        rows = [json.loads(l) for l in out.splitlines() if l.startswith("{")]
+        return {r["variant"]: r["G_fp64_instr_per_s"] for r in rows}
+    except Exception:
+        return None
 
 
 def main():
@@ -51,13 +73,30 @@ def main():
              "frac_of_measured_peak": (bytes_per_pt * npts / (ms * 1e-3) / 1e9 / peak) if bytes_per_pt else None}
         if extra:
             d.update(extra)
+        d["clocks"] = LAST_CLOCKS
         print(json.dumps(d), flush=True)
 
     if "aabb" not in args.skip:
         src = alg.synth_terrain_positions(n)
         ms = timed(lambda: alg.calculate_bounds(src))
         emit("AABB of packed Vec3f64 column (calculate_bounds, incl. the 48 B readback)", ms, n, 24)
-        del src
+        ms = timed(lambda: alg.morton_codes(src, (0.0, 0.0, -10.0), (500.0, 500.0, 16.0)))
+        emit("63-bit Morton codes of a Vec3f64 column (24 B in, 8 B out; incl. the torch allocation of the output)", ms, n, 32)
+        ms = timed(lambda: alg.minmax_attribute(src, pb.attributes.POSITION_3D))
+        emit("minmax_attribute(POSITION_3D Vec3f64) on the packed column", ms, n, 24)
+        l2 = pb.PointLayout.from_attributes([pb.attributes.POSITION_3D, pb.attributes.INTENSITY])
+        b2 = pb.VectorBuffer(l2, n // 2, "cuda")
+        ms = timed(lambda: alg.minmax_attribute(b2, pb.attributes.INTENSITY))
+        emit("minmax_attribute(INTENSITY u16) on 32 B interleaved records: strided, every sector of the buffer is touched "
+             "(32 B/pt of DRAM traffic; against the 2 B/pt of data it needs the fraction is meaningless, against the touched bytes it is the second figure)",
+             ms, n // 2, 2, {"frac_of_measured_peak_on_touched_bytes": 32 * (n // 2) / (ms * 1e-3) / 1e9 / peak})
+        del b2
+        p = src.columns[0][: 24 * n].view(torch.float64).view(-1, 3)
+        p[:, 0].mul_(0.01).add_(35.0)
+        p[:, 1].mul_(0.01).sub_(120.0)
+        ms = timed(lambda: alg.reproject_point_cloud_within(src, "EPSG:4326", "EPSG:32610"), reps=2)
+        emit("reprojection EPSG:4326 -> UTM zone 10N in place (Krueger series; 24 B in + 24 B out; FP64 transcendental-bound)", ms, n, 48)
+        del src, p
     if "c3" not in args.skip:
         src = alg.synth_terrain_positions(n)
         t0 = time.perf_counter()
@@ -105,11 +144,21 @@ def main():
         m = args.knn_points
         src = alg.synth_terrain_positions(m)
         rng = np.random.default_rng(1)
+        fp64 = fp64_peak_ginstr()
         for kind, name in ((0, "plane"), (1, "line")):
             samples = rng.integers(0, m, (300, 3 if kind == 0 else 2)).astype(np.uint64)
             ms = timed(lambda: alg.ransac_rank_samples(src, kind, samples, 0.5), reps=2)
-            emit(f"RANSAC {name}: 300 models ranked over the cloud (2 launches of <=256 models, 24 B/pt each)", ms, m, 48,
-                 {"point_model_tests_per_s": 300 * m / (ms * 1e-3)})
+            tests = 300 * m / (ms * 1e-3)
+            # FP64-pipe instructions per point-model test of the guard-band path (segmentation.rs:31-44 with every product and
+            # sum rounded separately): plane 3 DMUL + 3 DADD + 2 DSETP = 8, line 3 DSUB + 9 DMUL + 3 DSUB + 2 DADD + 2 DSETP = 19
+            per_test = 8 if kind == 0 else 19
+            extra = {"point_model_tests_per_s": tests, "fp64_instr_per_test": per_test, "fp64_G_instr_per_s": tests * per_test / 1e9,
+                     "roofline": "FP64 pipe (HBM fraction is meaningless here: each 24 B position is reused for up to 256 models)"}
+            if fp64:
+                peak_i = fp64.get("DMUL + DADD (non-fused), 8 chains/thread")
+                extra["fp64_peak_G_instr_per_s_measured"] = peak_i
+                extra["frac_of_measured_fp64_rate"] = tests * per_test / 1e9 / peak_i if peak_i else None
+            emit(f"RANSAC {name}: 300 models ranked over the cloud (2 launches of <=256 models, 24 B/pt each)", ms, m, 48, extra)
         del src
     if "las" not in args.skip:
         from pasture_b200 import las
