@@ -59,7 +59,11 @@ def main():
     ap.add_argument("--points", type=int, default=100_000_000)
     ap.add_argument("--knn-points", type=int, default=20_000_000)
     ap.add_argument("--skip", default="")
+    ap.add_argument("--params", default="", help="context parameters for tuning sweeps, e.g. convert.threads=1024,convert.ctas_per_sm=2")
     args = ap.parse_args()
+    for kv in filter(None, args.params.split(",")):
+        k, v = kv.split("=")
+        pb.get_context().set_param(k, int(v))
     n = args.points
     peak = 6536.4
     try:

@@ -220,6 +220,7 @@ int pb200_ctx_set_param(pb200_ctx* ctx, const char* key, int64_t v) {
     else if (k == "convert.stages") ctx->stages = v;
     else if (k == "convert.ctas_per_sm") ctx->ctas_per_sm = v;
     else if (k == "convert.force_direct") ctx->force_direct = v;
+    else if (k == "convert.no_grouped_copy") ctx->no_grouped_copy = v;
     else if (k == "convert.stage_chunk_mb") ctx->stage_chunk_mb = v;
     else if (k == "convert.cost_div") g_cost_div = v;
     else if (k == "convert.cost_pack_base") g_cost_pack_base = v;

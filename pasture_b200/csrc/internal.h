@@ -29,6 +29,7 @@ struct pb200_ctx {
     size_t smem_optin = 0;
     // tuning knobs (0 = automatic)
     int64_t tile_points = 0, threads = 0, stages = 0, ctas_per_sm = 0, force_direct = 0;
+    int64_t no_grouped_copy = 0;  // differential tests: columnar -> packed-record copies with one lane per record
     int64_t sort_force_8bit = 0;  // experiments: keep 8-bit digits even where 9-bit ones save a pass
     int64_t stage_chunk_mb = 0;  // staged bytes per chunk of the HOST-memspace pipeline (0 = 128 MB)
     int64_t knn_init_radius = -1, knn_stats = 0, knn_per_axis_codes = 0, knn_heap = 1;  // experiments / diagnostics

@@ -42,7 +42,7 @@ def write_points(point_buffer, point_format, scale, offset, point_range=None, de
     n = len(r)
     rec = PointLayout.las_raw(point_format).size_of_point_entry()
     dev = torch.device(device) if device is not None else point_buffer.device
-    out = torch.zeros(max(1, n * rec), dtype=torch.uint8, device=dev)
+    out = torch.empty(max(1, n * rec), dtype=torch.uint8, device=dev)  # the writer produces every byte of every record
     st = LasWriteStats()
     d = point_buffer.desc()
     check(lib().pb200_las_write_points(ctx._h, C.byref(d), r.start, r.stop, point_format, (C.c_double * 3)(*scale),

@@ -175,7 +175,8 @@ class PntsWriter:
         arr = (Attr * 4)()
         k, nbytes = C.c_uint32(0), C.c_uint64(0)
         check(lib().pb200_pnts_compatible_layout(points.point_layout()._h, n, arr, C.byref(k), C.byref(nbytes)))
-        body = torch.zeros(max(1, nbytes.value), dtype=torch.uint8, device=points.device)
+        # every array and its padding to 8 bytes is written by the library (pnts.cu: pb200_pnts_write_points)
+        body = torch.empty(max(1, nbytes.value), dtype=torch.uint8, device=points.device)
         d = points.desc()
         check(lib().pb200_pnts_write_points(ctx._h, C.byref(d), C.c_void_p(body.data_ptr()), nbytes.value))
         self._chunks.append((n, [(int(arr[i].offset), int(arr[i].size)) for i in range(k.value)], body))

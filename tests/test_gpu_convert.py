@@ -605,3 +605,89 @@ def test_c2_full_size_bit_exact_against_torch_and_direct_kernel(ctx):
     assert int((xyz2 - xyz).abs().max()) <= 1
     assert oor == 0
     assert torch.equal(back.data[: 20 * n].view(n, 20)[:, 12:14], rec[:, 12:14])  # intensity survives the round trip
+
+
+# ---- columnar -> packed interleaved records: the grouped copy (G consecutive records per lane) -----------------
+
+GROUPED_LAYOUTS = {
+    # record stride 35 (odd, G = 4): the default LAS format-0 layout, every copy size 1 / 2 / 24
+    "las_default_0": None,
+    # stride 41 (odd): 8-, 12-, 6-, 4-, 3-byte elements at every alignment residue
+    "odd_41": [("p", O.VEC3F32, 0), ("t", O.F64, 0), ("c", O.VEC3U16, 0), ("i", O.U32, 0), ("rgb", O.VEC3U8, 0), ("k", O.U64, 0)],
+    # stride 26 (= 2 mod 4, G = 2)
+    "even_26": [("p", O.VEC3I32, 0), ("i", O.U16, 0), ("f", O.U8, 0), ("c", O.U8, 0), ("a", O.I8, 0), ("u", O.U8, 0), ("s", O.U16, 0), ("c3", O.VEC3U16, 0)],
+    # stride 25 (odd) with a Vec3f64
+    "odd_25": [("Position3D", O.VEC3F64, 0), ("cls", O.U8, 0)],
+}
+
+
+@pytest.mark.parametrize("name", list(GROUPED_LAYOUTS))
+@pytest.mark.parametrize("n", [1, 127, 128, 129, 2048, 2049, 12345, 70001])
+def test_columnar_to_packed_records_grouped_copy(ctx, name, n):
+    """buffer_conversion.rs:494-544 (columnar -> interleaved) into packed records whose stride is not a multiple of 4: the
+    tile kernel stores G consecutive records per lane (copy_loop_grouped).  Same bytes as the oracle, as the
+    one-lane-per-record loops (convert.no_grouped_copy) and as the direct kernel, for whole buffers and for ranges whose
+    first point makes the column tiles start at unaligned addresses; neighbours of the target range untouched."""
+    if GROUPED_LAYOUTS[name] is None:
+        ol, pl = util.las_layouts(0, False)
+    else:
+        ol, pl = util.layouts(GROUPED_LAYOUTS[name], packed=1)
+    assert ol.size % 4 != 0
+    osrc, psrc = util.random_bytes_buffers(ol, pl, n + 5, True, seed=n, finite_floats=False)
+    ocv = O.OConverter(ol, ol, with_default=True)
+    pcv = BufferLayoutConverter.for_layouts_with_default(pl, pl)
+    for (sb, db) in [(0, 0), (1, 3), (5, 0)]:
+        m = n + 5 - sb if sb else n
+        results = []
+        for param in (None, "no_grouped_copy", "force_direct"):
+            odst = O.OBuffer(ol, m + 7, False)
+            odst.aos[:] = 0x5A
+            pdst = VectorBuffer(pl, m + 7, "cuda")
+            pdst.data.fill_(0x5A)
+            ocv.convert_into_range(osrc, sb, sb + m, odst, db, db + m)
+            if param:
+                ctx.set_param("convert." + param, 1)
+            try:
+                pcv.convert_into_range(psrc, range(sb, sb + m), pdst, range(db, db + m))
+                torch.cuda.synchronize()
+            finally:
+                if param:
+                    ctx.set_param("convert." + param, 0)
+            assert np.array_equal(odst.aos[: (m + 7) * ol.size], pdst.raw_bytes()), (name, n, sb, db, param)
+
+
+@pytest.mark.parametrize("dst", [O.I32, O.U8, O.I16, O.U32, O.I64, O.F32, O.F64])
+@pytest.mark.parametrize("before", [True, False])
+def test_inverse_scale_offset_division_bit_exact(ctx, dst, before):
+    """(v - offset) / scale (write_helpers.rs:15-17) uses a reciprocal refined once per work item plus the division's own
+    residual correction; it must equal the IEEE division of the oracle for every operand: random bit patterns (infinities,
+    NaNs, denormals, huge and tiny magnitudes), quotients next to integers, and scales of every magnitude."""
+    if not before and dst != O.F64:
+        pytest.skip("a transform applied after the cast works on the target type: f64 only")
+    rng = np.random.default_rng(77 + dst)
+    n = 400_000
+    ol, pl = util.layouts([("v", O.F64, 0)])
+    olt, plt = util.layouts([("v", dst, 0)])
+    scales = [0.001, 0.01, 3.0, -0.37, 1e-300, 1e300, 5e-324, 2.0 ** -1022, 1.0, float(np.nextafter(1.0, 2.0)), 1e-7, 123456.789,
+              float("inf"), float("nan")]
+    for k, s in enumerate(scales):
+        o = [0.0, 500000.0, -1e-3][k % 3]
+        vals = rng.integers(0, 2 ** 64, n, dtype=np.uint64).view(np.float64).copy()
+        q = rng.integers(-2 ** 31 - 5, 2 ** 31 + 5, n // 4).astype(np.float64)           # quotients at / next to integers
+        with np.errstate(all="ignore"):
+            near = q * s + o
+            vals[: n // 4] = near
+            vals[n // 4: n // 2] = np.nextafter(near, np.inf)
+            vals[n // 2: 3 * n // 4] = np.nextafter(near, -np.inf)
+        osrc = O.OBuffer(ol, n, True)
+        osrc.columns[0][:] = vals.view(np.uint8)
+        psrc = util.to_pb(osrc, pl)
+        t = pb.InvScaleOffset(s, (o, o, o))
+        ocv = O.OConverter(ol, olt, with_default=False)
+        ocv.set_custom_mapping_with_transformation(("v", O.F64), ("v", dst), O.F64, util.oracle_transform(t), before)
+        pcv = BufferLayoutConverter.for_layouts(pl, plt)
+        pcv.set_custom_mapping_with_transformation(util.PointAttributeDefinition("v", O.F64, 0), util.PointAttributeDefinition("v", dst, 0), t, before)
+        odst = ocv.convert(osrc, True)
+        pdst = pcv.convert(psrc, HashMapBuffer)
+        torch.cuda.synchronize()
+        util.assert_buffers_match(odst, pdst, f"scale {s!r} offset {o}")
