@@ -1,0 +1,21 @@
+#!/bin/bash
+mkdir -p gpurun_out
+python -m pytest tests/test_gpu_convert.py tests/test_gpu_las_io.py tests/test_gpu_pnts.py tests/test_gpu_multigpu.py -x -q 2>&1 | tail -5
+for P in "" "convert.autotune=1"; do
+echo "== params: $P"
+PB200_TUNE_LOG=1 python benchmarks/bench_configs.py --params "$P" --skip aabb,c3,filter,ransac,c4 2> gpurun_out/r3h.err | python -c "
+import sys, json
+for l in sys.stdin:
+    d = json.loads(l); print('  ', round(d['ms'],3), round(d['frac_of_measured_peak'] or 0,3), d['config'][:60])"
+done
+grep "default\|\*" gpurun_out/r3h.err | head -40
+python bench.py --steps 50 --no-e2e --no-cpu-baseline --no-other-configs | python -c "
+import sys, json
+d=json.loads(sys.stdin.read().strip().splitlines()[-1]); print('C2', d['ms_per_step'], d['roofline']['frac'])"
+PB200_TUNE_LOG=1 python bench.py --steps 50 --no-e2e --no-cpu-baseline --no-other-configs --param convert.autotune=1 2> gpurun_out/r3h_c2.err | python -c "
+import sys, json
+d=json.loads(sys.stdin.read().strip().splitlines()[-1]); print('C2 autotune', d['ms_per_step'], d['roofline']['frac'])"
+grep "default\|\*" gpurun_out/r3h_c2.err | head
+python bench.py --steps 50 --no-e2e --no-cpu-baseline --no-other-configs --fused-bounds | python -c "
+import sys, json
+d=json.loads(sys.stdin.read().strip().splitlines()[-1]); print('C2 fused', d['ms_per_step'], d['roofline']['frac'])"

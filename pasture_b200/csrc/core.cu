@@ -6,7 +6,7 @@
 #include <cctype>
 
 namespace pb200 {
-extern int64_t g_cost_div, g_cost_pack_base, g_cost_pack_per_src, g_cost_copy_base, g_cost_store;  // convert.cu cost model
+extern pb200_ctx::CostModel g_cost;  // convert.cu cost model
 
 std::atomic<uint64_t> g_launches{0};
 thread_local pb200_ctx* tl_ctx = nullptr;
@@ -221,12 +221,17 @@ int pb200_ctx_set_param(pb200_ctx* ctx, const char* key, int64_t v) {
     else if (k == "convert.ctas_per_sm") ctx->ctas_per_sm = v;
     else if (k == "convert.force_direct") ctx->force_direct = v;
     else if (k == "convert.no_grouped_copy") ctx->no_grouped_copy = v;
+    else if (k == "convert.autotune") { ctx->autotune = v; if (!v) ctx->tuned.clear(); }
     else if (k == "convert.stage_chunk_mb") ctx->stage_chunk_mb = v;
-    else if (k == "convert.cost_div") g_cost_div = v;
-    else if (k == "convert.cost_pack_base") g_cost_pack_base = v;
-    else if (k == "convert.cost_pack_per_src") g_cost_pack_per_src = v;
-    else if (k == "convert.cost_copy_base") g_cost_copy_base = v;
-    else if (k == "convert.cost_store") g_cost_store = v;
+    else if (k == "convert.cost_div") g_cost.div = v;
+    else if (k == "convert.cost_pack_base") g_cost.pack_base = v;
+    else if (k == "convert.cost_pack_per_src") g_cost.pack_per_src = v;
+    else if (k == "convert.cost_copy_base") g_cost.copy_base = v;
+    else if (k == "convert.cost_store") g_cost.store = v;
+    else if (k == "convert.cost_group_base") g_cost.group_base = v;
+    else if (k == "convert.cost_group_store") g_cost.group_store = v;
+    else if (k == "convert.cost_hist") g_cost.hist = v;
+    else if (k == "convert.cost_item") g_cost.item = v;
     else if (k == "profile.phases") ctx->profile = v;
     else if (k == "sort.force_8bit") ctx->sort_force_8bit = v;
     else if (k == "knn.init_radius") ctx->knn_init_radius = v;

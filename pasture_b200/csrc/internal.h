@@ -50,6 +50,12 @@ struct pb200_ctx {
     std::vector<std::pair<void*, size_t>> cache_free_blocks;
     std::unordered_map<void*, size_t> cache_live;
     size_t cache_reserved = 0;
+    // schedule tuning of the tile pipeline ("convert.autotune" = 1): cost-model weights that gave the fastest schedule, per plan
+    // signature (convert.cu: tune_schedule)
+    int64_t autotune = 0;
+    struct CostModel { int64_t div = 24, pack_base = 24, pack_per_src = 12, copy_base = 6, store = 1, group_base = 4, group_store = 4, hist = 16, item = 120; };
+    std::unordered_map<uint64_t, CostModel> tuned;
+    cudaEvent_t tune_e0 = nullptr, tune_e1 = nullptr;
     bool convert_attr_set = false;  // cudaFuncSetAttribute is per device: every context configures its kernels once
     bool sort_attr_set[2] = {false, false}, knn_attr_set = false, voxel_attr_set = false;
 };

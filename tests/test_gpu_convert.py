@@ -691,3 +691,47 @@ def test_inverse_scale_offset_division_bit_exact(ctx, dst, before):
         pdst = pcv.convert(psrc, HashMapBuffer)
         torch.cuda.synchronize()
         util.assert_buffers_match(odst, pdst, f"scale {s!r} offset {o}")
+
+
+def test_schedule_autotune_is_result_neutral(ctx):
+    """"convert.autotune": the first large conversion of a plan shape times alternative schedules on a prefix of its own
+    range and keeps the fastest.  Schedules only move work between warps: the bytes (and the fused accumulators: AABB,
+    out-of-range count) must be those of the untuned run and of the oracle; the trial runs must not leak into the accumulators."""
+    n = 4_500_000
+    ol, pl = util.las_layouts(0, True)
+    olt, plt = util.las_layouts(0, False)
+    osrc = O.OBuffer(ol, n, False)
+    osrc.aos[: 20 * n] = O.gen_las_fmt0_records(0, n)
+    psrc = util.to_pb(osrc, pl)
+    scale, offset = (0.001,) * 3, (500000.0, 5400000.0, 100.0)
+    odst = O.OConverter.las_default(ol, olt, scale, offset).convert(osrc, True)
+    pcv = pb.get_default_las_converter(pl, plt, scale, offset)
+    ref = HashMapBuffer(plt, n, "cuda")
+    b0 = pcv.convert_into_range_with_bounds(psrc, range(0, n), ref, range(0, n))
+    ctx.set_param("convert.autotune", 1)
+    try:
+        for _ in range(2):  # first call tunes, second reuses the tuned schedule
+            got = HashMapBuffer(plt, n, "cuda")
+            b1 = pcv.convert_into_range_with_bounds(psrc, range(0, n), got, range(0, n))
+            torch.cuda.synchronize()
+            util.assert_buffers_match(odst, got, "autotuned C2")
+            assert b1 == b0
+        # write direction with the out-of-range counter and a packed 35 B source
+        aos = BufferLayoutConverter.for_layouts_with_default(plt, plt).convert(got, VectorBuffer)
+        oaos = O.OConverter(olt, olt, with_default=True).convert(odst, False)
+        util.assert_buffers_match(oaos, aos, "autotuned columnar -> interleaved")
+        t = pb.InvScaleOffset(scale, offset)
+        owr = O.OConverter(olt, ol, with_default=True)
+        owr.set_custom_mapping_with_transformation(("Position3D", O.VEC3F64), ("LASLocalPosition", O.VEC3I32), O.VEC3F64,
+                                                   util.oracle_transform(t), True)
+        oback = owr.convert(oaos, False)
+        wr = BufferLayoutConverter.for_layouts_with_default(plt, pl)
+        wr.set_custom_mapping_with_transformation(A.POSITION_3D, pb.ATTRIBUTE_LOCAL_LAS_POSITION, t, True)
+        for _ in range(2):
+            back = VectorBuffer(pl, n, "cuda")
+            oor = wr.convert_into(aos, back, count_out_of_range=True)
+            torch.cuda.synchronize()
+            assert oor == 0
+            util.assert_buffers_match(oback, back, "autotuned write direction")
+    finally:
+        ctx.set_param("convert.autotune", 0)
