@@ -1,16 +1,13 @@
 #!/bin/bash
 mkdir -p gpurun_out
 python -m pytest tests/test_gpu_convert.py tests/test_gpu_las_io.py tests/test_gpu_pnts.py tests/test_gpu_multigpu.py -x -q 2>&1 | tail -3
-for V in G H; do
-cp benchmarks/build/variants/$V.so pasture_b200/libpasture_b200.so
 for P in "" "convert.autotune=1"; do
-[ "$V" = "G" ] && [ -n "$P" ] && continue
-echo "== variant $V params: $P"
-PB200_TUNE_LOG=1 python benchmarks/bench_configs.py --params "$P" --skip aabb,c3,filter,ransac,c4 2> gpurun_out/r3i.err | python -c "
+echo "== params: $P"
+PB200_TUNE_LOG=1 python benchmarks/bench_configs.py --params "$P" --skip aabb,c3,filter,ransac,c4 2> gpurun_out/r3m.err | python -c "
 import sys, json
 for l in sys.stdin:
     d = json.loads(l); print('  ', round(d['ms'],3), round(d['frac_of_measured_peak'] or 0,3), d['config'][:60])"
-grep "default\|\*" gpurun_out/r3i.err | head -30
+grep "default\|\*" gpurun_out/r3m.err | head -30
 done
 python bench.py --steps 50 --no-e2e --no-cpu-baseline --no-other-configs 2>/dev/null | python -c "
 import sys, json
@@ -18,8 +15,7 @@ d=json.loads(sys.stdin.read().strip().splitlines()[-1]); print('   C2', d['ms_pe
 python bench.py --steps 50 --no-e2e --no-cpu-baseline --no-other-configs --fused-bounds 2>/dev/null | python -c "
 import sys, json
 d=json.loads(sys.stdin.read().strip().splitlines()[-1]); print('   C2 fused', d['ms_per_step'], d['roofline']['frac'])"
-done
-PB200_TUNE_LOG=1 python bench.py --steps 50 --no-e2e --no-cpu-baseline --no-other-configs --param convert.autotune=1 2> gpurun_out/r3i_c2.err | python -c "
+PB200_TUNE_LOG=1 python bench.py --steps 50 --no-e2e --no-cpu-baseline --no-other-configs --param convert.autotune=1 2> gpurun_out/r3m_c2.err | python -c "
 import sys, json
 d=json.loads(sys.stdin.read().strip().splitlines()[-1]); print('   C2 autotune', d['ms_per_step'], d['roofline']['frac'])"
-grep "default\|\*" gpurun_out/r3i_c2.err | head
+grep "default\|\*" gpurun_out/r3m_c2.err | head
