@@ -71,6 +71,17 @@ def main():
     except Exception:
         pass
 
+    def tuned(fn, reps=3):
+        """the same call with the library's schedule autotuning on ("convert.autotune": the first large conversion of a plan
+        shape times alternative schedules on a prefix of its own range and the context keeps the fastest)"""
+        ctx = pb.get_context()
+        ctx.set_param("convert.autotune", 1)
+        try:
+            fn()  # tunes
+            return timed(fn, reps=reps)
+        finally:
+            ctx.set_param("convert.autotune", 0)
+
     def emit(name, ms, npts, bytes_per_pt, extra=None):
         d = {"config": name, "points": npts, "ms": ms, "points_per_s": npts / (ms * 1e-3),
              "algorithmic_bytes_per_point": bytes_per_pt, "achieved_GBps": bytes_per_pt * npts / (ms * 1e-3) / 1e9 if bytes_per_pt else None,
@@ -122,6 +133,7 @@ def main():
         ident = pb.BufferLayoutConverter.for_layouts(tgt, tgt)
         ms = timed(lambda: ident.convert_into(col, aos))
         emit("columnar -> interleaved (LasPointFormat0 35 B, identity mappings)", ms, n, 70)
+        emit("columnar -> interleaved (LasPointFormat0 35 B, identity mappings), schedule autotuned", tuned(lambda: ident.convert_into(col, aos)), n, 70, {"autotune": True})
         # write direction (C1 on the GPU): 35 B default layout -> 20 B raw records, (p-o)/s truncation
         back = pb.VectorBuffer(raw, n, "cuda")
         wr = pb.BufferLayoutConverter.for_layouts_with_default(tgt, raw)
@@ -130,6 +142,7 @@ def main():
         ms = timed(lambda: wr.convert_into_fresh(aos, back))
         emit("C1 on GPU: interleaved LasPointFormat0 (35 B) -> raw LAS fmt0 (20 B), (p-o)/s truncating; `convert` semantics "
              "(fresh target: unmapped flags byte written as 0, no read-modify-write)", ms, n, 55)
+        emit("C1 on GPU, `convert` semantics, schedule autotuned", tuned(lambda: wr.convert_into_fresh(aos, back)), n, 55, {"autotune": True})
         ms = timed(lambda: wr.convert_into(aos, back))
         emit("same with `convert_into` semantics (unmapped target bytes preserved: read-modify-write, 75 B/pt of real traffic)", ms, n, 55)
         del col, aos, back
@@ -174,6 +187,7 @@ def main():
         del src
         ms = timed(lambda: las.write_points(col, 0, (0.001,) * 3, (500000.0, 5400000.0, 100.0)), reps=2)
         emit("LAS egress: columnar default layout (35 B) -> fmt0 records (20 B) + counts by return + bounds", ms, n, 55)
+        emit("LAS egress, schedule autotuned", tuned(lambda: las.write_points(col, 0, (0.001,) * 3, (500000.0, 5400000.0, 100.0)), reps=2), n, 55, {"autotune": True})
         del col
     if "pnts" not in args.skip:
         from pasture_b200 import tiles3d
@@ -186,6 +200,7 @@ def main():
             w.write(src)
         ms = timed(wr, reps=2)
         emit(".pnts egress: Vec3f64 + Vec3u16 columns -> FeatureTable body (Vec3f32 + Vec3u8)", ms, n, 30 + 15)
+        emit(".pnts egress, schedule autotuned", tuned(wr, reps=2), n, 30 + 15, {"autotune": True})
         del src
     if "c4" not in args.skip:
         m = args.knn_points

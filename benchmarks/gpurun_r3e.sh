@@ -27,4 +27,6 @@ from pasture_b200 import las
 open("gpurun_out/tile_trace.txt", "a").write("== egress\n")
 las.write_points(col, 0, (0.001,) * 3, (500000.0, 5400000.0, 100.0)); torch.cuda.synchronize()
 PY
+python - <<PY2
+PY2
 wc -l gpurun_out/tile_trace.txt
