@@ -134,6 +134,11 @@ def main():
         ms = timed(lambda: ident.convert_into(col, aos))
         emit("columnar -> interleaved (LasPointFormat0 35 B, identity mappings)", ms, n, 70)
         emit("columnar -> interleaved (LasPointFormat0 35 B, identity mappings), schedule autotuned", tuned(lambda: ident.convert_into(col, aos)), n, 70, {"autotune": True})
+        col2 = pb.HashMapBuffer(tgt, n, "cuda")
+        ms = timed(lambda: ident.convert_into(aos, col2))
+        emit("interleaved -> columnar (LasPointFormat0 35 B packed records, identity mappings)", ms, n, 70)
+        emit("interleaved -> columnar (35 B packed records), schedule autotuned", tuned(lambda: ident.convert_into(aos, col2)), n, 70, {"autotune": True})
+        del col2
         # write direction (C1 on the GPU): 35 B default layout -> 20 B raw records, (p-o)/s truncation
         back = pb.VectorBuffer(raw, n, "cuda")
         wr = pb.BufferLayoutConverter.for_layouts_with_default(tgt, raw)
