@@ -144,6 +144,10 @@ extern "C" {
     pub fn pb200_converter_convert_fresh_range(cv: *mut pb200_converter, src: *const pb200_buffer_desc, src_begin: u64, src_end: u64,
                                                dst: *const pb200_buffer_desc, dst_begin: u64, dst_end: u64,
                                                out_of_range_count: *mut u64) -> c_int;
+    /// Host-side description of the tile schedule (no device needed; `cv` may come from `pb200_converter_create(null, ..)`).
+    pub fn pb200_converter_describe_schedule(cv: *const pb200_converter, src: *const pb200_buffer_desc, src_begin: u64, src_end: u64,
+                                             dst: *const pb200_buffer_desc, dst_begin: u64, fresh_target: i32,
+                                             out: *mut core::ffi::c_char, capacity: u64) -> i32;
     pub fn pb200_converter_convert_into(cv: *mut pb200_converter, src: *const pb200_buffer_desc,
                                         dst: *const pb200_buffer_desc, out_of_range_count: *mut u64) -> c_int;
     pub fn pb200_converter_convert_into_range_with_bounds(cv: *mut pb200_converter, src: *const pb200_buffer_desc,

@@ -178,6 +178,16 @@ int pb200_las_default_layout(int point_format, pb200_layout** out);
  * pair has no cast (attribute_conversion.rs:184-271). */
 int pb200_converter_create(pb200_ctx* ctx, const pb200_layout* from, const pb200_layout* to, int with_default,
                            pb200_converter** out);
+/* ctx may be NULL: a planning-only converter for pb200_converter_describe_schedule; every conversion with it returns
+ * PB200_ERR_NO_DEVICE. */
+/* Host-side description of the tile schedule a conversion of src[sb, se) into dst[db, ...) would run (no device needed;
+ * the descriptors' pointers are only used as addresses).  Text, one line per work item:
+ *   tiles tile_points=.. threads=.. stages=.. ctas_per_sm=.. smem=.. ops=.. items=.. load_first=..
+ *   item warp=.. kind=copy|scalar|pack|zero src_type=.. dst_type=.. xf=.. bytes=.. group=.. src_rel=.. dst_rel=.. p0=.. p1=..
+ * or "direct ops=.." when the plan does not fit the tile pipeline.  Returns the text length or a negative error code. */
+int pb200_converter_describe_schedule(const pb200_converter* cv, const pb200_buffer_desc* src, uint64_t sb, uint64_t se,
+                                      const pb200_buffer_desc* dst, uint64_t db, int fresh_target, char* out, uint64_t capacity);
+
 /* set_custom_mapping :156-183 */
 int pb200_converter_set_custom_mapping(pb200_converter* cv, const char* from_name, uint32_t from_dtype,
                                        const char* to_name, uint32_t to_dtype);

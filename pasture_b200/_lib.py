@@ -112,6 +112,7 @@ SIGNATURES = {
     "pb200_converter_num_mappings": (u32, [vp]),
     "pb200_converter_convert_into_range": (i32, [vp, BD, u64, u64, BD, u64, u64, C.POINTER(u64)]),
     "pb200_converter_convert_fresh_range": (i32, [vp, BD, u64, u64, BD, u64, u64, C.POINTER(u64)]),
+    "pb200_converter_describe_schedule": (i32, [vp, BD, u64, u64, BD, u64, i32, C.c_char_p, u64]),
     "pb200_converter_convert_into": (i32, [vp, BD, BD, C.POINTER(u64)]),
     "pb200_converter_convert_into_range_with_bounds": (i32, [vp, BD, u64, u64, BD, u64, u64, PD, PD, C.POINTER(i32)]),
     "pb200_converter_convert_into_range_with_bounds_device": (i32, [vp, BD, u64, u64, BD, u64, u64, vp]),

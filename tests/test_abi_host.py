@@ -162,3 +162,92 @@ def test_projection_pipeline_builder_host_side():
     assert L.pb200_proj_op_tmerc(0.0, 299.0, 0.0, 0.0, 1.0, 0.0, 0.0, 0, C.byref(op)) == -8
     assert L.pb200_proj_op_helmert(1.0, 2.0, 3.0, 0.0, 0.0, 0.0, 0.0, 0, C.byref(op)) == 0
     assert op.kind == 1 and list(op.p) == [1, 0, 0, 0, 1, 0, 0, 0, 1, 1, 2, 3]
+
+
+def _schedule(cv_handle, src_layout, src_kind, dst_layout, dst_kind, n=1 << 20, sb=0, fresh=0):
+    """pb200_converter_describe_schedule on fake device addresses (planning only: nothing is dereferenced)"""
+    def desc(layout, kind, base):
+        d = _lib.BufferDesc()
+        d.layout, d.kind, d.memspace, d.len = layout._h, kind, 1, n
+        cols = (C.c_void_p * len(layout))(*[base + (i + 1) * (1 << 28) for i in range(len(layout))])
+        d.aos = C.c_void_p(base)
+        d.columns = C.cast(cols, C.POINTER(C.c_void_p))
+        d._keep = cols
+        return d
+    s, t = desc(src_layout, src_kind, 1 << 32), desc(dst_layout, dst_kind, 1 << 36)
+    out = C.create_string_buffer(1 << 16)
+    rc = _lib.lib().pb200_converter_describe_schedule(cv_handle, C.byref(s), sb, n, C.byref(t), 0, fresh, out, len(out))
+    assert rc > 0, rc
+    lines = out.value.decode().splitlines()
+    head = dict(kv.split("=") for kv in lines[0].split()[1:])
+    items = [dict(kv.split("=") for kv in l.split()[1:]) for l in lines[1:]]
+    return lines[0].split()[0], head, items
+
+
+def _check_schedule(head, items):
+    """every point of the tile is covered exactly once per op, by at most threads/32 warps; grouped copies are cut at
+    whole blocks of G x 32 points"""
+    T, warps = int(head["tile_points"]), int(head["threads"]) // 32
+    assert len(items) == int(head["items"]) <= int(head["ops"]) + warps
+    assert max(int(i["warp"]) for i in items) < warps
+    by_op = {}
+    for i in items:  # an op is identified by what it reads and writes at point 0 of the tile
+        p0, p1 = int(i["p0"]), int(i["p1"])
+        assert 0 <= p0 < p1 <= T and p0 % 32 == 0 and (p1 % 32 == 0 or p1 == T)
+        g = int(i["group"])
+        if g:
+            assert p0 % (32 * g) == 0 and (p1 % (32 * g) == 0 or p1 == T)
+        by_op.setdefault((i["kind"], i["src_type"], i["dst_type"], i["xf"], i["bytes"]), []).append((p0, p1))
+    n_rows = 0
+    for key, cuts in by_op.items():
+        total = sum(b - a for a, b in cuts)
+        assert total % T == 0, (key, cuts)  # (several ops can share a key: x / y / z of a Vec3)
+        n_rows += total // T
+    assert n_rows == int(head["ops"])
+    order = [int(i["warp"]) for i in items]
+    assert order == sorted(order)  # the ops are laid out in order over the warps
+
+
+def test_tile_schedule_host_side():
+    """the converter's schedule (convert.cu: assign_items) is host logic: a planning-only converter (ctx == NULL) describes it
+    without a device.  C2 (interleaved raw LAS fmt0 -> columnar default layout), the write direction with a fresh target, and
+    columnar -> packed 35 B records (grouped copies)"""
+    L = _lib.lib()
+    raw, tgt = pb.PointLayout.las_raw(0), pb.PointLayout.las_default(0)
+    h = C.c_void_p()
+    assert L.pb200_las_default_converter(None, raw._h, tgt._h, (C.c_double * 3)(0.001, 0.001, 0.001),
+                                         (C.c_double * 3)(5e5, 5.4e6, 100.0), C.byref(h)) == 0
+    mode, head, items = _schedule(h, raw, 0, tgt, 1)
+    assert mode == "tiles" and int(head["tile_points"]) == 2048 and int(head["threads"]) == 512 and head["load_first"] == "1"
+    assert int(head["ops"]) == 12
+    _check_schedule(head, items)
+    # a range that starts at an odd point: the tile shape stays, the streams are skewed
+    mode2, head2, items2 = _schedule(h, raw, 0, tgt, 1, sb=3)
+    _check_schedule(head2, items2)
+    # conversions with a planning-only converter fail loudly
+    d = _lib.BufferDesc()
+    d.layout, d.kind, d.memspace, d.len, d.aos = raw._h, 0, 1, 16, C.c_void_p(1 << 32)
+    e = _lib.BufferDesc()
+    cols = (C.c_void_p * len(tgt))(*[(1 << 36) + i * 4096 for i in range(len(tgt))])
+    e.layout, e.kind, e.memspace, e.len, e.columns = tgt._h, 1, 1, 16, C.cast(cols, C.POINTER(C.c_void_p))
+    assert L.pb200_converter_convert_into_range(h, C.byref(d), 0, 16, C.byref(e), 0, 16, None) == -100
+    L.pb200_converter_destroy(h)
+
+    h = C.c_void_p()
+    assert L.pb200_converter_create(None, tgt._h, tgt._h, 0, C.byref(h)) == 0
+    mode, head, items = _schedule(h, tgt, 1, tgt, 0)  # columnar -> interleaved 35 B: every copy is grouped (G = 4)
+    assert mode == "tiles" and all(i["kind"] == "copy" and i["group"] == "4" for i in items) and head["load_first"] == "0"
+    _check_schedule(head, items)
+    mode, head, items = _schedule(h, tgt, 0, tgt, 1)  # interleaved 35 B -> columnar: plain copies
+    assert all(i["group"] == "0" for i in items)
+    _check_schedule(head, items)
+    L.pb200_converter_destroy(h)
+
+    h = C.c_void_p()
+    assert L.pb200_converter_create(None, tgt._h, raw._h, 1, C.byref(h)) == 0
+    mode, head, items = _schedule(h, tgt, 0, raw, 0, fresh=1)  # write direction, `convert` semantics: zero ops fill the holes
+    assert any(i["kind"] == "zero" for i in items)
+    _check_schedule(head, items)
+    mode, head, items = _schedule(h, tgt, 0, raw, 0, fresh=0)
+    assert not any(i["kind"] == "zero" for i in items)
+    L.pb200_converter_destroy(h)
