@@ -239,7 +239,78 @@ def other_configs(pb, ctx, dev, peak):
     out.append(row)
     del res, src
     ctx.trim()
+    out.append(converter_directions(pb, dev, peak))
+    ctx.trim()
     return out
+
+
+def converter_directions(pb, dev, peak):
+    """the other loops of BufferLayoutConverter (buffer_conversion.rs:418-662) and the two egress paths at 100 M points, default
+    schedule: columnar -> interleaved packed records, interleaved packed records -> columnar, the write direction (C1 on the
+    GPU) with `convert` and `convert_into` semantics, LAS egress, .pnts egress.  One clock sample over the block."""
+    import torch
+    from pasture_b200 import algorithms as alg, las, tiles3d
+    n = POINTS_PER_GPU
+    raw, tgt = pb.PointLayout.las_raw(0), pb.PointLayout.las_default(0)
+    rows = []
+
+    def timed(fn, reps=5):
+        fn()
+        torch.cuda.synchronize()
+        best = None
+        for _ in range(reps):
+            e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            e0.record()
+            fn()
+            e1.record()
+            torch.cuda.synchronize()
+            ms = e0.elapsed_time(e1)
+            best = ms if best is None or ms < best else best
+        return best
+
+    def emit(name, ms, bpp, note=None):
+        r = {"direction": name, "ms": ms, "algorithmic_bytes_per_point": bpp, "achieved_GBps": bpp * n / (ms * 1e-3) / 1e9,
+             "frac": bpp * n / (ms * 1e-3) / 1e9 / peak}
+        if note:
+            r["note"] = note
+        rows.append(r)
+
+    with ClockSampler(dev.index) as clocks:
+        src = alg.synth_las_fmt0_records(n, device=dev)
+        col = pb.HashMapBuffer(tgt, n, dev)
+        pb.get_default_las_converter(raw, tgt, SCALE, OFFSET).convert_into(src, col)
+        del src
+        aos = pb.VectorBuffer(tgt, n, dev)
+        ident = pb.BufferLayoutConverter.for_layouts(tgt, tgt)
+        emit("columnar -> interleaved LasPointFormat0 (35 B packed records)", timed(lambda: ident.convert_into(col, aos)), 70)
+        col2 = pb.HashMapBuffer(tgt, n, dev)
+        emit("interleaved LasPointFormat0 (35 B packed records) -> columnar", timed(lambda: ident.convert_into(aos, col2)), 70)
+        del col2
+        back = pb.VectorBuffer(raw, n, dev)
+        wr = pb.BufferLayoutConverter.for_layouts_with_default(tgt, raw)
+        wr.set_custom_mapping_with_transformation(pb.attributes.POSITION_3D, pb.ATTRIBUTE_LOCAL_LAS_POSITION,
+                                                  pb.InvScaleOffset(SCALE[0], OFFSET), True)
+        emit("C1 on the GPU: interleaved 35 B -> raw LAS fmt0 20 B, (p-o)/s truncating, `convert` semantics (fresh target)",
+             timed(lambda: wr.convert_into_fresh(aos, back)), 55)
+        emit("same, `convert_into` semantics (unmapped target bytes preserved)", timed(lambda: wr.convert_into(aos, back)), 55,
+             "read-modify-write of the partially mapped records: 75 B/pt of real traffic")
+        del aos, back
+        emit("LAS egress: columnar default layout -> fmt0 records + out-of-range count + points by return + bounds",
+             timed(lambda: las.write_points(col, 0, SCALE, OFFSET), reps=3), 55)
+        del col
+        lay = pb.PointLayout.from_attributes([pb.attributes.POSITION_3D, pb.attributes.COLOR_RGB])
+        s2 = pb.HashMapBuffer(lay, n, dev)
+        s2.columns[0][: 24 * n].view(torch.float64).uniform_(-1000.0, 1000.0)
+        w = tiles3d.PntsWriter(lay)
+
+        def pnts():
+            w._chunks.clear()
+            w.write(s2)
+        emit(".pnts egress: Vec3f64 + Vec3u16 columns -> FeatureTable body (Vec3f32 + Vec3u8)", timed(pnts, reps=3), 45)
+        del s2, w
+    return {"workload": "converter directions and egress paths at 100M points on 1xB200 (default schedule)", "points": n,
+            "rows": rows, "clocks": clocks.summary(),
+            "timing": "CUDA events around the library call, best of 5 (egress: 3) after one warm-up, device-resident buffers"}
 
 
 def oracle_convert_rate(n_points, threads, repeats=1):
