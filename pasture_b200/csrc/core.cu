@@ -235,6 +235,7 @@ int pb200_ctx_set_param(pb200_ctx* ctx, const char* key, int64_t v) {
     else if (k == "convert.load_first") g_cost.load_first = v;
     else if (k == "convert.cost_warp0") g_cost.warp0 = v;
     else if (k == "convert.cost_track") g_cost.track = v;
+    else if (k == "convert.cut_rows") g_cost.cut_rows = v > 0 ? v : 1;
     else if (k == "profile.phases") ctx->profile = v;
     else if (k == "sort.force_8bit") ctx->sort_force_8bit = v;
     else if (k == "knn.init_radius") ctx->knn_init_radius = v;

@@ -53,7 +53,7 @@ struct pb200_ctx {
     // schedule tuning of the tile pipeline ("convert.autotune" = 1): cost-model weights that gave the fastest schedule, per plan
     // signature (convert.cu: tune_schedule)
     int64_t autotune = 0;
-    struct CostModel { int64_t div = 24, pack_base = 24, pack_per_src = 12, copy_base = 6, store = 1, group_base = 4, group_store = 4, hist = 16, item = 260, load_first = -1, warp0 = 250, track = 4; };
+    struct CostModel { int64_t div = 24, pack_base = 24, pack_per_src = 12, copy_base = 6, store = 1, group_base = 4, group_store = 4, hist = 16, item = 260, load_first = -1, warp0 = 250, track = 4, cut_rows = 2; };
     std::unordered_map<uint64_t, CostModel> tuned;
     cudaEvent_t tune_e0 = nullptr, tune_e1 = nullptr;
     bool convert_attr_set = false;  // cudaFuncSetAttribute is per device: every context configures its kernels once
