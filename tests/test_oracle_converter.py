@@ -165,3 +165,30 @@ def test_oracle_filter_into_like_reference_test():  # point_buffer.rs:2296-2329 
         assert np.array_equal(dst.attribute("Position3D"), np.arange(24, dtype=np.float64).reshape(8, 3)[::2])
     with pytest.raises(O.OracleError):
         O.filter_into(src, lambda i: True, O.OBuffer(ol, 4, True))
+
+
+@pytest.mark.parametrize("scale", [0.001, 0.01, -0.37, 3.0, 1e-300, 1e300, 5e-324, 123456.789])
+def test_inverse_scale_offset_is_ieee_division_then_rust_cast(scale):
+    """pins the oracle side of tests/test_gpu_convert.py::test_inverse_scale_offset_division_bit_exact: `(v - offset) / scale`
+    (write_helpers.rs:15-17) in the oracle is the IEEE-754 subtraction and division numpy performs, followed by Rust's
+    saturating `as i32` (NaN -> 0)"""
+    rng = np.random.default_rng(int(abs(scale) * 1e6) % 1000 + 5)
+    n = 200_000
+    offset = 500000.0
+    vals = rng.integers(0, 2 ** 64, n, dtype=np.uint64).view(np.float64).copy()
+    q = rng.integers(-2 ** 31 - 5, 2 ** 31 + 5, n // 2).astype(np.float64)
+    with np.errstate(all="ignore"):
+        vals[: n // 2] = q * scale + offset
+    ol = O.OLayout.from_attributes([("v", O.F64, 0)])
+    olt = O.OLayout.from_attributes([("v", O.I32, 0)])
+    src = O.OBuffer(ol, n, True)
+    src.columns[0][:] = vals.view(np.uint8)
+    cv = O.OConverter(ol, olt, with_default=False)
+    cv.set_custom_mapping_with_transformation(("v", O.F64), ("v", O.I32), O.F64,
+                                               O.make_transform(O.T_INV_SCALE_OFFSET,
+                                                                s=(scale,) * 3, o=(offset,) * 3), True)
+    got = cv.convert(src, True).columns[0][: 4 * n].view(np.int32)
+    with np.errstate(all="ignore"):
+        t = (vals - offset) / scale
+    want = np.where(np.isnan(t), 0.0, np.clip(np.trunc(t), -2.0 ** 31, 2.0 ** 31 - 1)).astype(np.int64).astype(np.int32)
+    assert np.array_equal(got, want)
