@@ -123,9 +123,38 @@ static int run_convert(void) {
     return bad ? 1 : 0;
 }
 
+/* host side only (no device): a planning-only converter (ctx == NULL) for the read path of the LAS reader and the tile
+ * schedule a 1 M-point conversion from interleaved records into columns would run */
+static int run_plan(void) {
+    pb200_layout *raw = NULL, *def = NULL;
+    CHECK(pb200_las_raw_layout(0, &raw));
+    CHECK(pb200_las_default_layout(0, &def));
+    const double scale[3] = {0.001, 0.001, 0.001}, offset[3] = {500000.0, 5400000.0, 100.0};
+    pb200_converter* cv = NULL;
+    CHECK(pb200_las_default_converter(NULL, raw, def, scale, offset, &cv));
+    void* columns[10];
+    for (int i = 0; i < 10; ++i) columns[i] = (void*)(uintptr_t)(0x100000000ull + 0x10000000ull * (unsigned)i); /* addresses only */
+    pb200_buffer_desc src = {raw, PB200_INTERLEAVED, PB200_DEVICE, 1u << 20, (void*)(uintptr_t)0x80000000ull, NULL};
+    pb200_buffer_desc dst = {def, PB200_COLUMNAR, PB200_DEVICE, 1u << 20, NULL, columns};
+    static char text[1 << 16];
+    int n = pb200_converter_describe_schedule(cv, &src, 0, 1u << 20, &dst, 0, 0, text, sizeof text);
+    if (n <= 0) {
+        fprintf(stderr, "describe_schedule -> %d (%s)\n", n, pb200_last_error());
+        return 1;
+    }
+    fputs(text, stdout);
+    /* and conversions with it are refused */
+    int rc = pb200_converter_convert_into_range(cv, &src, 0, 16, &dst, 0, 16, NULL);
+    pb200_converter_destroy(cv);
+    pb200_layout_destroy(raw);
+    pb200_layout_destroy(def);
+    return rc == PB200_ERR_NO_DEVICE ? 0 : 1;
+}
+
 int main(int argc, char** argv) {
+    if (argc > 1 && strcmp(argv[1], "plan") == 0) return run_plan();
     if (argc > 1 && strcmp(argv[1], "layout") == 0) return print_layout();
     if (argc > 1 && strcmp(argv[1], "convert") == 0) return run_convert();
-    fprintf(stderr, "usage: abi_consumer layout|convert\n");
+    fprintf(stderr, "usage: abi_consumer layout|plan|convert\n");
     return 2;
 }

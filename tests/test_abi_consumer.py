@@ -93,6 +93,14 @@ def test_rust_declarations_list_the_same_fields_in_the_same_order():
         assert [w for _, w in cf] == [w for _, w in rf], (name, cf, rf)
 
 
+def test_consumer_plans_a_conversion_without_a_device(exe):
+    """the C program builds the LAS read-path converter with ctx == NULL and prints its tile schedule: host logic only"""
+    out = subprocess.run([exe, "plan"], capture_output=True, text=True, check=True).stdout.splitlines()
+    assert out[0].startswith("tiles tile_points=2048 threads=512") and "ops=12" in out[0]
+    items = [l for l in out[1:] if l.startswith("item ")]
+    assert len(items) == int(re.search(r"items=(\d+)", out[0]).group(1)) and 16 <= len(items) <= 28
+
+
 def test_consumer_fails_loudly_without_a_device(exe):
     import torch
     if torch.cuda.is_available():
