@@ -251,3 +251,27 @@ def test_tile_schedule_host_side():
     mode, head, items = _schedule(h, tgt, 0, raw, 0, fresh=0)
     assert not any(i["kind"] == "zero" for i in items)
     L.pb200_converter_destroy(h)
+
+
+@pytest.mark.parametrize("fmt", range(11))
+def test_tile_schedule_of_every_las_format(fmt):
+    """the schedule invariants (every op covers the tile exactly once, at most threads/32 warps, item limits) for the LAS
+    read path (raw records -> default layout, both target kinds) and the write direction of every point format 0..10"""
+    L = _lib.lib()
+    raw, tgt = pb.PointLayout.las_raw(fmt), pb.PointLayout.las_default(fmt)
+    h = C.c_void_p()
+    assert L.pb200_las_default_converter(None, raw._h, tgt._h, (C.c_double * 3)(0.01, 0.01, 0.01),
+                                         (C.c_double * 3)(0.0, 0.0, 0.0), C.byref(h)) == 0
+    for dst_kind in (1, 0):
+        mode, head, items = _schedule(h, raw, 0, tgt, dst_kind)
+        assert mode == "tiles"
+        _check_schedule(head, items)
+    L.pb200_converter_destroy(h)
+    h = C.c_void_p()
+    assert L.pb200_converter_create(None, tgt._h, raw._h, 1, C.byref(h)) == 0
+    for src_kind in (1, 0):
+        for fresh in (0, 1):
+            mode, head, items = _schedule(h, tgt, src_kind, raw, 0, fresh=fresh)
+            assert mode == "tiles"
+            _check_schedule(head, items)
+    L.pb200_converter_destroy(h)
