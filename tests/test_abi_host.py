@@ -275,3 +275,42 @@ def test_tile_schedule_of_every_las_format(fmt):
             assert mode == "tiles"
             _check_schedule(head, items)
     L.pb200_converter_destroy(h)
+
+
+@pytest.mark.parametrize("seed", range(40))
+def test_tile_schedule_of_random_layouts(seed):
+    """random source / target layouts (all scalar and Vec3 types, byte arrays, packed and aligned members, missing and extra
+    attributes), all four buffer-kind pairs, `convert` and `convert_into` semantics: the schedule invariants hold or the plan
+    falls back to the direct kernel"""
+    import numpy as np
+    import oracle as O
+    from tests import util
+    rng = np.random.default_rng(9000 + seed)
+    n_src = int(rng.integers(1, 12))
+    src_attrs = [(f"a{i}", int(rng.choice(list(range(16)) + [O.BYTEARRAY])), int(rng.integers(1, 40))) for i in range(n_src)]
+    src_attrs = [(a, d, e if d == O.BYTEARRAY else 0) for a, d, e in src_attrs]
+    _, pl = util.layouts(src_attrs, packed=int(rng.choice([0, 1, 2])))
+    dst_attrs = []
+    for (a, d, e) in src_attrs:
+        if rng.random() < 0.2:
+            continue
+        if d <= O.F64 and rng.random() < 0.6:
+            d = int(rng.integers(0, 10))
+        elif O.VEC3U8 <= d <= O.VEC3F64 and rng.random() < 0.6:
+            d = int(rng.integers(O.VEC3U8, O.VEC3F64 + 1))
+        dst_attrs.append((a, d, e))
+    if rng.random() < 0.5:
+        dst_attrs.append(("missing_in_source", O.U32, 0))
+    if not dst_attrs:
+        dst_attrs = [src_attrs[0]]
+    _, plt = util.layouts(dst_attrs, packed=int(rng.choice([0, 1, 4])))
+    L = _lib.lib()
+    h = C.c_void_p()
+    assert L.pb200_converter_create(None, pl._h, plt._h, 1, C.byref(h)) == 0
+    for src_kind in (0, 1):
+        for dst_kind in (0, 1):
+            for fresh in (0, 1):
+                mode, head, items = _schedule(h, pl, src_kind, plt, dst_kind, n=1 << 16, sb=int(rng.integers(0, 5)), fresh=fresh)
+                if mode == "tiles":
+                    _check_schedule(head, items)
+    L.pb200_converter_destroy(h)
